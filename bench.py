@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- SA-LSTM caption hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|greedy|beam|recnet_global|recnet_local]
+
+Default workload (BASELINE.json configs[1]): `AVCaptioning` (early fusion, no reconstructor)
+teacher-forced forward + ModalityWiseReconstructionLoss + backward (+ gradient all-reduce for
+N>1) + clip_grad_value_ + Adam(amsgrad) -- one optimiser step of the reference's train loop
+(train.py:186-210) -- on MSVD-shaped synthetic features, batch 128 PER GPU (weak scaling),
+bf16 tensor-core compute with fp32 master weights.
+
+One JSON line on rank 0.  `value` = samples/s with the step's inputs already in HBM; `e2e` = the
+same step fed from pinned HOST buffers (H2D of audio/visual/captions + D2H of the loss inside the
+timed region).  `roofline` is the dominant kernel's in-situ duration (CUDA events bracketing each of
+its launches, mvc_prof_arm) against MEASURED_PEAKS.json.  `cpu_baseline` / `--impl reference` time
+the CPU restatement of the reference (oracle/, torch CPU ops incl. the same ATen LSTM call) on the
+host cores of this box.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "multimodal-video-captioning_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+SHAPES = {
+    # name: (B per GPU, T, L, V)
+    "msvd": (128, 44, 24, 3201),
+    "msrvtt": (512, 30, 30, 10547),
+}
+WORKLOADS = {
+    "train": dict(shape="msvd", rec="none", metric="train_samples_per_sec", unit="samples/s",
+                  desc="C2: AVCaptioning SA-LSTM decoder fwd + CE/entropy loss + bwd + clip + Adam(amsgrad), "
+                       "MSVD-shaped B=128/GPU T=44 L=24 V=3201"),
+    "recnet_global": dict(shape="msvd", rec="global", metric="train_samples_per_sec", unit="samples/s",
+                          desc="C5: AVCaptioning + global reconstructor train step, MSVD-shaped B=128/GPU"),
+    "recnet_local": dict(shape="msvd", rec="local", metric="train_samples_per_sec", unit="samples/s",
+                         desc="C5: AVCaptioning + local reconstructor train step, MSVD-shaped B=128/GPU"),
+    "greedy": dict(shape="msrvtt", rec="none", metric="greedy_captions_per_sec", unit="captions/s",
+                   desc="C3: AVCaptioning.predict(mode='direct') ids, MSR-VTT-shaped B=512/GPU T=30 L=30 V=10547"),
+    "beam": dict(shape="msrvtt", rec="none", metric="beam5_captions_per_sec", unit="captions/s",
+                 desc="C4: beam_search_predict(width=5), MSR-VTT-shaped B=512/GPU T=30 L=30 V=10547"),
+}
+LAMBDAS = dict(reg_lambda=0.0005, audio_recon_lambda=0.00005, visual_recon_lambda=0.5)   # train.py:412-461
+N_ROT = 4   # rotating input batches: 4 x 49 MB (msvd) / 4 x 134 MB (msrvtt) > 126 MB L2
+
+
+class Vocab:
+    def __init__(self, n):
+        self.n = n
+        self.stoi = {"<PAD>": 0, "<SOS>": 1, "<EOS>": 2, "<UNK>": 3}
+
+    def __len__(self):
+        return self.n
+
+    def decode_indexes(self, idx):
+        out = []
+        for i in idx:
+            if int(i) == 2:
+                break
+            out.append(str(int(i)))
+        return " ".join(out)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            d = json.load(fh)
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor=d["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, src="fallback")
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples in the upper half of the observed clock range are the busy ones
+        busy = [x for x in sm if x >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- synthetic data
+def make_batches(shape, n, seed0=1):
+    from oracle import salstm_oracle as O     # synthetic-input generator only
+    B, T, L, V = shape
+    return [O.synth_batch(B, T, L, V, seed=seed0 + i) for i in range(n)]
+
+
+# --------------------------------------------------------------------------- reference / CPU arm
+def cpu_train_step_fn(shape, rec, sample_B, threads):
+    """The reference's arithmetic for one train step on the CPU: oracle restatement with the same ATen LSTM
+    call and the per-step U.feats recompute the reference does (hoist=False), torch.optim.Adam(amsgrad)."""
+    from oracle import salstm_oracle as O
+    torch.set_num_threads(threads)
+    B, T, L, V = shape
+    gen = torch.Generator().manual_seed(0)
+    p = O.init_decoder_params("decoder.", 2176, V, gen=gen)
+    if rec != "none":
+        p.update(O.init_recon_params("reconstructor.", rec, 512, 2176, gen=gen))
+    p = {k: v.requires_grad_() for k, v in p.items()}
+    opt = torch.optim.Adam(list(p.values()), lr=1e-4, weight_decay=1e-5, amsgrad=True)
+    audio, visual, caps = O.synth_batch(sample_B, T, L, V, seed=1)
+
+    def step():
+        opt.zero_grad()
+        out, ar, vr = O.av_forward(p, audio, visual, caps, 1.0, rec, hoist=False, aten_lstm=True)
+        terms = O.modality_wise_loss(out, caps, audio, ar, visual, vr, rec_type=rec, **LAMBDAS)
+        terms[0].mean().backward()
+        torch.nn.utils.clip_grad_value_(list(p.values()), 5.0)
+        opt.step()
+        return float(terms[0])
+    return step
+
+
+def cpu_decode_step_fn(shape, sample_B, threads, beam):
+    from oracle import salstm_oracle as O
+    torch.set_num_threads(threads)
+    B, T, L, V = shape
+    gen = torch.Generator().manual_seed(0)
+    p = O.init_decoder_params("decoder.", 2176, V, gen=gen)
+    audio, visual, _ = O.synth_batch(sample_B, T, L, V, seed=1)
+
+    def step():
+        with torch.no_grad():
+            if beam:
+                return O.decoder_beam_search(p, "decoder.", torch.cat([audio, visual], -1), max_len=L, width=5)
+            return O.av_greedy_ids(p, audio, visual, L, hoist=False)
+    return step
+
+
+def cpu_arm(workload, steps, warmup):
+    w = WORKLOADS[workload]
+    shape = SHAPES[w["shape"]]
+    threads = os.cpu_count() or 1
+    if workload in ("greedy", "beam"):
+        sample_B = 64 if workload == "greedy" else 16
+        fn = cpu_decode_step_fn(shape, sample_B, threads, workload == "beam")
+    else:
+        sample_B = shape[0] if steps + warmup <= 12 else 32
+        fn = cpu_train_step_fn(shape, w["rec"], sample_B, threads)
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = time.perf_counter() - t0
+    value = sample_B * steps / dt
+    sample = (f"{steps} step(s) of batch {sample_B} (of {shape[0]}) of the same workload, oracle port "
+              f"(torch {torch.__version__} CPU ops, ATen LSTM, U.feats recomputed per step as the reference does)")
+    return value, dt * 1e3 / steps, dict(value=value, unit=w["unit"], cores=threads, kind="port", sample=sample)
+
+
+# --------------------------------------------------------------------------- B200 arm
+def build_model(workload, dev, precision):
+    from models import AVCaptioning
+    w = WORKLOADS[workload]
+    B, T, L, V = SHAPES[w["shape"]]
+    torch.manual_seed(0)
+    model = AVCaptioning(Vocab(V), teacher_forcing_ratio=1.0, reconstructor_type=w["rec"], device=dev,
+                         precision=precision).to(dev)
+    return model
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    shape = SHAPES[w["shape"]]
+    B, T, L, V = shape
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        value, ms, cb = cpu_arm(args.workload, args.steps, max(args.warmup, 1))
+        print(json.dumps({"impl": "reference", "metric": w["metric"], "value": value, "unit": w["unit"],
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": w["desc"], "parallelism": "host CPU threads"},
+                          "cpu_baseline": cb,
+                          "e2e": {"value": value, "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as G
+    if not os.path.exists(G.LIB):
+        G.build()
+    from salstm import cabi
+    from salstm.trainer import FlatClipAdam
+    import losses as Lm
+    lib = cabi.lib()
+
+    model = build_model(args.workload, dev, args.precision)
+    training = args.workload in ("train", "recnet_global", "recnet_local")
+    host = make_batches(shape, N_ROT, seed0=1 + 100 * rank)
+    pinned = [tuple(t.pin_memory() for t in b) for b in host]
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    if not training:
+        h2d_bytes -= host[0][2].numel() * host[0][2].element_size()
+
+    if training:
+        loss_fn = Lm.ModalityWiseReconstructionLossBuilder(rec_type=w["rec"], **LAMBDAS)
+        opt = FlatClipAdam(model.parameters(), lr=1e-4, weight_decay=1e-5, clip_value=5.0, world_size=world)
+
+        def step(batch):
+            audio, visual, caps = batch
+            opt.zero_grad()
+            out, ar, vr = model(audio, visual, caps)
+            terms = loss_fn(out, caps, audio, ar, visual, vr)
+            terms[0].mean().backward()
+            if world > 1:
+                opt.all_reduce_grads()
+            opt.step()
+            return terms[0]
+        d2h_bytes = 4
+    elif args.workload == "greedy":
+        def step(batch):
+            return model.decoder.greedy_ids((batch[0], batch[1]), L)
+        d2h_bytes = B * L * 8
+    else:
+        def step(batch):
+            return cabi_beam(model, batch, L)
+        d2h_bytes = B * (L + 2) * 8
+
+    def cabi_beam(model, batch, L):
+        from salstm import functional as Fn
+        dec = model.decoder
+        return Fn.decoder_beam(dec._dims(batch[0].shape[0], batch[0].shape[1], L), batch[0], batch[1], dec._params(), 5, 0.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # clocks are sampled (nvidia-smi, 100 ms period) from before the warm-up until after the last timed
+    # region, so the samples "under load" cover every timed loop of this process
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident timing
+    for i in range(warmup):
+        step(resident[i % N_ROT])
+    barrier()
+    l0 = lib.mvc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(resident[i % N_ROT])
+    e1.record()
+    barrier()
+    launches = lib.mvc_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- end-to-end timing: pinned host inputs -> H2D -> step -> D2H of the result, every step.
+    # Inputs of step i+1 are prefetched on a copy stream while step i computes (double buffering);
+    # all copies are inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    n_in = 3 if training else 2
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            for dst, src in list(zip(slots[s], pinned[i % N_ROT]))[:n_in]:
+                dst.copy_(src, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def run_e2e(n):
+        res = None
+        for s in range(2):
+            freed[s].record(torch.cuda.current_stream())
+        prefetch(0)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[s])
+            r = step(slots[s])
+            freed[s].record(torch.cuda.current_stream())
+            res = r.item() if training else r.cpu()      # D2H of the step's result, every step
+        return res
+
+    run_e2e(3)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    run_e2e(args.steps)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel, timed in situ over K more steps
+    pk = peaks()
+    roof = None
+    if rank == 0:
+        roof = roofline_pass(lib, args, step, resident, shape, pk)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb_steps = 1 if training else 1
+        _, _, cb = cpu_arm(args.workload, cb_steps, 1)
+
+    line = {"metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world, "T": T, "L": L, "V": V,
+                       "parallelism": f"dp{world}" if training else f"batch-sharded x{world} (no comm)",
+                       "master_weights": "fp32", "l2": f"rotating {N_ROT} distinct input batches "
+                       f"({N_ROT * h2d_bytes / 1e6:.0f} MB > 126 MB L2) + weights/activations rewritten every step"},
+            "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "peaks": pk["src"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_pass(lib, args, step, resident, shape, pk):
+    """Arm in-situ event timing for the dominant kernel class and run the timed loop again."""
+    B, T, L, V = shape
+    F, H, A, E = 2176, 512, 256, 300
+    es = 2 if args.precision == "bf16" else 4
+    if args.workload in ("train", "recnet_global", "recnet_local", "greedy", "beam"):
+        # soft-attention forward: reads keys [B,T,F] + U.k [B,T,A] once, writes ctx + alpha
+        rows = B if args.workload != "beam" else 5 * B
+        kid, m, n, k = 3, rows, T, F
+        alg = rows * T * (F * es + A * 4) + rows * (F * es + T * 4 + A * 4)
+        bound, peak, unit = "hbm", pk["hbm"], "GB/s"
+        name = f"soft_attention_fwd B={rows} T={T} F={F} ({'bf16' if es == 2 else 'fp32'} keys)"
+    lib.mvc_prof_arm(kid, m, n, k)
+    for i in range(args.steps):
+        step(resident[i % N_ROT])
+    torch.cuda.synchronize()
+    tot, cnt = C.c_double(0), C.c_longlong(0)
+    lib.mvc_prof_collect(C.byref(tot), C.byref(cnt))
+    if cnt.value == 0:
+        return None
+    avg_s = tot.value / cnt.value / 1e3
+    achieved = alg / avg_s / 1e9
+    return {"bound": bound, "kernel": name, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+            "traffic": None, "launches": cnt.value, "avg_us": avg_s * 1e6, "algorithmic_bytes_per_launch": alg,
+            "peak_source": pk["src"] + " (hbm_gbs)"}
+
+
+if __name__ == "__main__":
+    main()

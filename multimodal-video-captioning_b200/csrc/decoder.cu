@@ -1,0 +1,858 @@
+// decoder.cu -- host-side orchestration of the SA-LSTM decoder on one stream:
+// teacher-forced / scheduled-sampling / free-running forward, BPTT backward,
+// greedy ids and beam search.  No device synchronisation, no allocation.
+//
+// Restructuring relative to the reference's per-step Python loop
+// (features_captioning.py:91-119), all exact algebra:
+//   * U.feats is loop invariant -> one GEMM before the loop (the reference
+//     recomputes it every step, temporal_attention.py:21);
+//   * the embedding half of the LSTM input projection is hoisted: under full
+//     teacher forcing as one [S*B,E]x[E,4H] GEMM, otherwise as a [V,4H] table
+//     (embedding . W_ih[:, :E]^T + b_ih + b_hh) gathered per step inside the
+//     cell kernel;
+//   * the vocabulary projection + log-softmax runs once over all S*B rows when
+//     no step needs its own argmax;
+//   * backward: every weight gradient is one GEMM over all S*B rows after the
+//     time loop; only d[ctx;h] = dgates.[W_ih[:,E:]|W_hh], the attention
+//     backward and dh += dwq.W stay inside the loop.
+#include "step.cuh"
+
+namespace mvc {
+
+struct DecWs {
+  // saved for backward
+  void* feats;    // [B*T, F]        compute dtype
+  float* uk;      // [B*T, A]
+  float* wq;      // [S, B, A]
+  float* alpha;   // [S, B, T]
+  void* xh;       // [S+1, B, F+H]   compute dtype: slot s = [ctx_s ; h_s]
+  float* act;     // [S, B, 4H]
+  float* c;       // [S+1, B, H]
+  void* xemb;     // [S*B, Ep]       compute dtype
+  // weights in compute dtype (rebuilt every forward)
+  void* wcat;     // [4H, F+H] = [W_ih[:,E:] | W_hh]
+  void* wie;      // [4H, Ep]  = W_ih[:, :E] (bf16: zero padded to Ep)
+  void* U;        // [A, F]
+  void* W;        // [A, H]
+  void* outw;     // [V, H]
+  void* embb;     // [V, Ep]
+  float* bsum;    // [4H] = b_ih + b_hh
+  // scratch
+  float* pre;     // [B, 4H]
+  float* gx;      // [S*B, 4H]
+  float* embtab;  // [V, 4H]
+  float* hzero;   // [B, H] zeros (c_0 / fp32 h_0)
+  size_t bytes;
+};
+
+static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
+  const int64_t B = d->B, T = d->T, F = d->F, H = d->H, E = d->E, A = d->A, V = d->V, S = d->L - 1;
+  const bool bf = d->precision == MVC_BF16;
+  const size_t es = bf ? 2 : 4;
+  const int64_t Ep = bf ? pad8((int)E) : E;
+  Arena ar(base);
+  DecWs w{};
+  w.feats = ar.take<char>(B * T * F * es);
+  w.uk = ar.take<float>(B * T * A);
+  w.wq = ar.take<float>(S * B * A);
+  w.alpha = ar.take<float>(S * B * T);
+  w.xh = ar.take<char>((S + 1) * B * (F + H) * es);
+  w.act = ar.take<float>(S * B * 4 * H);
+  w.c = ar.take<float>((S + 1) * B * H);
+  w.xemb = ar.take<char>(S * B * Ep * es);
+  w.wcat = ar.take<char>(4 * H * (F + H) * es);
+  w.wie = bf ? ar.take<char>(4 * H * Ep * es) : nullptr;
+  w.U = bf ? ar.take<char>(A * F * es) : nullptr;
+  w.W = bf ? ar.take<char>(A * H * es) : nullptr;
+  w.outw = bf ? ar.take<char>(V * H * es) : nullptr;
+  w.embb = bf ? ar.take<char>(V * Ep * es) : nullptr;
+  w.bsum = ar.take<float>(4 * H);
+  w.pre = ar.take<float>(B * 4 * H);
+  w.gx = ar.take<float>(S * B * 4 * H);
+  w.embtab = ar.take<float>(V * 4 * H);
+  w.hzero = ar.take<float>(B * H);
+  w.bytes = ar.off + 256;
+  return w;
+}
+
+// ------------------------------------------------------------------ small kernels
+// out[4H, F+H] = [w_x (4H x F, row pitch wx_ld) | w_hh (4H x H)]
+template <typename OutT>
+__global__ void pack_wcat_kernel(const float* __restrict__ w_x, int64_t wx_ld, const float* __restrict__ w_hh, int F,
+                                 int H, OutT* __restrict__ out) {
+  const int64_t K = F + H, total = (int64_t)4 * H * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / K;
+    const int k = (int)(i - r * K);
+    const float v = k < F ? w_x[r * wx_ld + k] : w_hh[r * H + (k - F)];
+    if constexpr (sizeof(OutT) == 2) out[i] = __float2bfloat16(v);
+    else out[i] = v;
+  }
+}
+
+// out[r, 0:Cp] = bf16(src[r*lds + 0:C]) zero padded
+__global__ void cast_pad_bf16_kernel(const float* __restrict__ src, int64_t rows, int C, int64_t lds, int Cp,
+                                     __nv_bfloat16* __restrict__ out) {
+  const int64_t total = rows * Cp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Cp;
+    const int c = (int)(i - r * Cp);
+    out[i] = __float2bfloat16(c < C ? src[r * lds + c] : 0.f);
+  }
+}
+
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] + b[i];
+}
+
+__global__ void fill_i64_kernel(int64_t* __restrict__ p, int64_t v, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ids[b*ld + col] = src[b]
+__global__ void scatter_col_i64_kernel(const int64_t* __restrict__ src, int64_t* __restrict__ dst, int64_t ld, int col,
+                                       int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) dst[b * ld + col] = src[b];
+}
+
+// dst[r*ldd + c] (+)= src[r*lds + c]
+__global__ void add_rows_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd,
+                                int64_t rows, int C, int accumulate) {
+  const int64_t total = rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    const float v = src[r * lds + c];
+    if (accumulate) dst[r * ldd + c] += v;
+    else dst[r * ldd + c] = v;
+  }
+}
+
+
+__global__ void iota_i64_kernel(int64_t* __restrict__ p, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+int launch_pack_wcat(const float* w_x, int64_t wx_ld, const float* w_hh, int F, int H, void* out, int out_bf16,
+                     cudaStream_t st) {
+  const int64_t n = (int64_t)4 * H * (F + H);
+  if (out_bf16) pack_wcat_kernel<__nv_bfloat16><<<gridn(n), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H, (__nv_bfloat16*)out);
+  else pack_wcat_kernel<float><<<gridn(n), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H, (float*)out);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_cast_pad_bf16(const float* src, int64_t rows, int C, int64_t lds, int Cp, void* out, cudaStream_t st) {
+  cast_pad_bf16_kernel<<<gridn(rows * Cp), 256, 0, st>>>(src, rows, C, lds, Cp, (__nv_bfloat16*)out);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_add_vec(const float* a, const float* b, float* o, int n, cudaStream_t st) {
+  add_vec_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a, b, o, n);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_fill_i64(int64_t* p, int64_t v, int64_t n, cudaStream_t st) {
+  fill_i64_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(p, v, n);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_iota_i64(int64_t* p, int64_t n, cudaStream_t st) {
+  iota_i64_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(p, n);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_add_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int C, int accumulate,
+                    cudaStream_t st) {
+  add_rows_kernel<<<gridn(rows * C), 256, 0, st>>>(src, lds, dst, ldd, rows, C, accumulate);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+// Prepare weights/features in the compute dtype + U.feats.  Shared by forward, greedy and beam.
+static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const float* audio, int Fa,
+                       const float* visual, int Fv, DecWs& w, bool need_embtab, cudaStream_t st) {
+  const int B = d->B, T = d->T, F = d->F, H = d->H, E = d->E, A = d->A, V = d->V;
+  const bool bf = d->precision == MVC_BF16;
+  const int Ep = bf ? pad8(E) : E;
+  MVC_CHECK(Fa + Fv == F, "decoder: Fa (%d) + Fv (%d) != in_feature_size (%d)", Fa, Fv, F);
+  MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, bf, st));
+  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, st));
+  MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, bf, st));
+  if (bf) {
+    MVC_TRY(launch_cast_pad_bf16(p->w_ih, 4 * H, E, E + F, Ep, w.wie, st));
+    MVC_TRY(mvc_cast_bf16(p->att_U, w.U, (int64_t)A * F, st));
+    MVC_TRY(mvc_cast_bf16(p->att_W, w.W, (int64_t)A * H, st));
+    MVC_TRY(mvc_cast_bf16(p->out_w, w.outw, (int64_t)V * H, st));
+    if (need_embtab) MVC_TRY(launch_cast_pad_bf16(p->embedding, V, E, E, Ep, w.embb, st));
+  }
+  // uk = feats . U^T      (temporal_attention.py:21, hoisted)
+  MVC_TRY(gemm_nt(d->precision, B * T, A, F, w.feats, F, bf ? w.U : (const void*)p->att_U, F, 0.f, w.uk, A, nullptr, st));
+  if (need_embtab) {
+    // embtab[v,:] = embedding[v] . W_ih[:, :E]^T + b_ih + b_hh
+    if (bf) MVC_TRY(gemm_nt(MVC_BF16, V, 4 * H, Ep, w.embb, Ep, w.wie, Ep, 0.f, w.embtab, 4 * H, w.bsum, st));
+    else MVC_TRY(gemm_nt(MVC_F32, V, 4 * H, E, p->embedding, E, p->w_ih, E + F, 0.f, w.embtab, 4 * H, w.bsum, st));
+  }
+  return 0;
+}
+
+static StepCfg dec_cfg(const MvcDecoderDims* d, const MvcDecoderParams* p, const DecWs& w, float* pre) {
+  const bool bf = d->precision == MVC_BF16;
+  StepCfg c{};
+  c.prec = d->precision;
+  c.T = d->T; c.F = d->F; c.H = d->H; c.A = d->A;
+  c.uk = w.uk;
+  c.keys = w.feats; c.keys_batch = d->B; c.k_sb = (int64_t)d->T * d->F; c.k_st = d->F;
+  c.mask = nullptr; c.m_sb = 0; c.m_st = 0;                 // decoder attention is unmasked
+  c.wcat = w.wcat; c.wcatT = nullptr;
+  c.attW = bf ? w.W : (const void*)p->att_W;
+  c.attW32 = p->att_W;
+  c.att_b = p->att_b; c.att_w = p->att_w;
+  c.cell_bias = nullptr;                                    // b_ih + b_hh is folded into gx / embtab
+  c.embtab = w.embtab;
+  c.pre = pre ? pre : w.pre;
+  return c;
+}
+
+}  // namespace mvc
+
+using namespace mvc;
+
+extern "C" size_t mvc_decoder_fwd_workspace_bytes(const MvcDecoderDims* d, int) { return dec_layout(d, nullptr).bytes; }
+
+static int check_dims(const MvcDecoderDims* d) {
+  MVC_CHECK(d, "decoder: null dims");
+  MVC_CHECK(d->B > 0 && d->T > 0 && d->F > 0 && d->H > 0 && d->E > 0 && d->A > 0 && d->V > 2 && d->L >= 2,
+            "decoder: bad dims B=%d T=%d F=%d H=%d E=%d A=%d V=%d L=%d", d->B, d->T, d->F, d->H, d->E, d->A, d->V, d->L);
+  MVC_CHECK(d->precision == MVC_F32 || d->precision == MVC_BF16, "decoder: unknown precision %d", d->precision);
+  if (d->precision == MVC_BF16)
+    MVC_CHECK(d->F % 8 == 0 && d->H % 8 == 0 && d->A % 8 == 0,
+              "decoder(bf16): F, H, A must be multiples of 8 (TMA 16-byte row pitch); got F=%d H=%d A=%d", d->F, d->H, d->A);
+  return 0;
+}
+
+extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderParams* p, const float* audio, int Fa,
+                                   const float* visual, int Fv, const int64_t* captions, const uint8_t* tf_flags_host,
+                                   float* out_logp, float* out_hid, int64_t* tokens_in, void* workspace,
+                                   size_t workspace_bytes, int save_for_backward, void* stream) {
+  (void)save_for_backward;
+  MVC_TRY(check_dims(d));
+  MVC_CHECK(p && out_logp && out_hid && tokens_in && workspace, "mvc_decoder_forward: null argument");
+  DecWs w = dec_layout(d, workspace);
+  MVC_CHECK(workspace_bytes >= w.bytes, "mvc_decoder_forward: workspace %zu < %zu", workspace_bytes, w.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = d->B, T = d->T, F = d->F, H = d->H, E = d->E, A = d->A, V = d->V, S = d->L - 1;
+  const bool bf = d->precision == MVC_BF16;
+  const size_t es = bf ? 2 : 4;
+  const int Ep = bf ? pad8(E) : E;
+  const int64_t ldx = F + H;
+
+  // Every step teacher forced?  (captions given and all flags set; the flag of the
+  // last step is never consumed: its "next input" is not fed to anything.)
+  bool all_tf = captions != nullptr;
+  if (captions) {
+    MVC_CHECK(tf_flags_host, "mvc_decoder_forward: captions without tf flags");
+    for (int i = 0; i + 1 < S; ++i) all_tf = all_tf && tf_flags_host[i];
+  }
+
+  MVC_TRY(dec_prepare(d, p, audio, Fa, visual, Fv, w, !all_tf, st));
+  MVC_CUDA(cudaMemsetAsync(out_logp, 0, sizeof(float) * (size_t)B * V, st));      // sentence[0] = 0  (:96)
+  MVC_CUDA(cudaMemsetAsync(out_hid, 0, sizeof(float) * (size_t)B * H, st));       // hidden_states[0] = 0 (:98)
+  MVC_CUDA(cudaMemsetAsync(w.c, 0, sizeof(float) * (size_t)B * H, st));           // c_0 = 0 (:66-75)
+  // h_0 = 0 in slot 0's h-part (strided): clear the whole slot 0
+  MVC_CUDA(cudaMemsetAsync(w.xh, 0, es * (size_t)B * ldx, st));
+  MVC_TRY(launch_fill_i64(tokens_in, MVC_SOS, B, st));                              // first input = <SOS> (:99)
+
+  if (all_tf) {
+    // tokens_in[s] = captions[s] for s >= 1 ; hoisted embedding GEMM
+    if (S > 1)
+      MVC_CUDA(cudaMemcpyAsync(tokens_in + B, captions + B, sizeof(int64_t) * (size_t)(S - 1) * B,
+                               cudaMemcpyDeviceToDevice, st));
+    MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, (int64_t)S * B, w.xemb, Ep, bf, st));
+    MVC_TRY(gemm_nt(d->precision, S * B, 4 * H, Ep, w.xemb, Ep, bf ? w.wie : (const void*)p->w_ih, bf ? Ep : E + F, 0.f,
+                    w.gx, 4 * H, w.bsum, st));
+  }
+
+  const StepCfg cfg = dec_cfg(d, p, w, nullptr);
+  for (int s = 0; s < S; ++s) {
+    const int t = s + 1;
+    StepFwd io{};
+    io.rows = B;
+    io.xh_src = mptr(w.xh, (int64_t)s * B * ldx, es);
+    io.xh_dst = mptr(w.xh, (int64_t)(s + 1) * B * ldx, es);
+    io.wq = w.wq + (int64_t)s * B * A;
+    io.alpha = w.alpha + (int64_t)s * B * T;
+    io.act = w.act + (int64_t)s * B * 4 * H;
+    io.c_prev = w.c + (int64_t)s * B * H;
+    io.c_out = w.c + (int64_t)(s + 1) * B * H;
+    io.gx = all_tf ? w.gx + (int64_t)s * B * 4 * H : nullptr;
+    io.tokens = all_tf ? nullptr : tokens_in + (int64_t)s * B;
+    io.h_out32 = out_hid + (int64_t)t * B * H;                                      // hidden_states[t] (:107)
+    io.h_ld = H;
+    io.first = (s == 0);
+    MVC_TRY(step_forward(cfg, io, st));
+    if (!all_tf) {
+      // logits -> log-probs (+ argmax) for this step                           (:87-88, :109)
+      float* lp = out_logp + (int64_t)t * B * V;
+      MVC_TRY(gemm_nt(d->precision, B, V, H, bf ? cptr(io.xh_dst, F, es) : (const char*)io.h_out32, bf ? ldx : H,
+                      bf ? w.outw : (const void*)p->out_w, H, 0.f, lp, V, p->out_b, st));
+      const bool feed_caption = captions && tf_flags_host[s];
+      const bool last = (s + 1 == S);
+      int64_t* nxt = last ? nullptr : tokens_in + (int64_t)(s + 1) * B;
+      MVC_TRY(mvc_log_softmax_rows(lp, B, V, (last || feed_caption) ? nullptr : nxt, st));
+      if (!last && feed_caption)
+        MVC_CUDA(cudaMemcpyAsync(nxt, captions + (int64_t)t * B, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (all_tf) {
+    // all S*B rows at once: log_softmax(h . out_w^T + out_b)
+    float* lp = out_logp + (int64_t)B * V;
+    if (bf) MVC_TRY(gemm_nt(MVC_BF16, S * B, V, H, cptr(w.xh, (int64_t)B * ldx + F, es), ldx, w.outw, H, 0.f, lp, V, p->out_b, st));
+    else MVC_TRY(gemm_nt(MVC_F32, S * B, V, H, out_hid + (int64_t)B * H, H, p->out_w, H, 0.f, lp, V, p->out_b, st));
+    MVC_TRY(mvc_log_softmax_rows(lp, (int64_t)S * B, V, nullptr, st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ backward
+namespace mvc {
+struct DecBwdWs {
+  float* dlogits;   // [S*B, V]
+  float* dhall;     // [S*B, H]
+  float* dG;        // [S*B, 4H]
+  float* dxh;       // [B, F+H]
+  float* dhcar;     // [B, H] carried dh (from step s+1)
+  float* dc;        // [B, H]
+  float* dwq;       // [S*B, A]
+  float* duk;       // [B*T, A]
+  float* dwpart;    // [B, A]
+  float* dxemb;     // [S*B, E]
+  // bf16 operands
+  void* dlogits_b;  // [S*B, Vp]
+  void* outwT;      // [H, Vp]
+  void* dlogitsT;   // [V, SBp]
+  void* hallT;      // [H, SBp]
+  void* dG_b;       // [S*B, 4H]
+  void* wcatT;      // [F+H, 4H]
+  void* dGT;        // [4H, SBp]
+  void* xhT;        // [F+H, SBp]
+  void* xembT;      // [Ep, SBp]
+  void* wieT;       // [Ep, 4H]
+  void* dukT;       // [A, BTp]
+  void* featsT;     // [F, BTp]
+  void* dwqT;       // [A, SBp]
+  size_t bytes;
+};
+
+static DecBwdWs dec_bwd_layout(const MvcDecoderDims* d, void* base) {
+  const int64_t B = d->B, T = d->T, F = d->F, H = d->H, E = d->E, A = d->A, V = d->V, S = d->L - 1;
+  const bool bf = d->precision == MVC_BF16;
+  const int64_t Vp = pad8((int)V), SBp = pad8((int)(S * B)), BTp = pad8((int)(B * T)), Ep = pad8((int)E);
+  Arena ar(base);
+  DecBwdWs w{};
+  w.dlogits = ar.take<float>(S * B * V);
+  w.dhall = ar.take<float>(S * B * H);
+  w.dG = ar.take<float>(S * B * 4 * H);
+  w.dxh = ar.take<float>(B * (F + H));
+  w.dhcar = ar.take<float>(B * H);
+  w.dc = ar.take<float>(B * H);
+  w.dwq = ar.take<float>(S * B * A);
+  w.duk = ar.take<float>(B * T * A);
+  w.dwpart = ar.take<float>(B * A);
+  w.dxemb = ar.take<float>(S * B * E);
+  if (bf) {
+    w.dlogits_b = ar.take<char>(S * B * Vp * 2);
+    w.outwT = ar.take<char>(H * Vp * 2);
+    w.dlogitsT = ar.take<char>(V * SBp * 2);
+    w.hallT = ar.take<char>(H * SBp * 2);
+    w.dG_b = ar.take<char>(S * B * 4 * H * 2);
+    w.wcatT = ar.take<char>((F + H) * 4 * H * 2);
+    w.dGT = ar.take<char>(4 * H * SBp * 2);
+    w.xhT = ar.take<char>((F + H) * SBp * 2);
+    w.xembT = ar.take<char>(Ep * SBp * 2);
+    w.wieT = ar.take<char>(Ep * 4 * H * 2);
+    w.dukT = ar.take<char>(A * BTp * 2);
+    w.featsT = ar.take<char>(F * BTp * 2);
+    w.dwqT = ar.take<char>(A * SBp * 2);
+  }
+  w.bytes = ar.off + 256;
+  return w;
+}
+}  // namespace mvc
+
+extern "C" size_t mvc_decoder_bwd_workspace_bytes(const MvcDecoderDims* d) { return dec_bwd_layout(d, nullptr).bytes; }
+
+extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderParams* p, const float* out_logp,
+                                    const float* dlogp, const float* dhid, const int64_t* tokens_in,
+                                    const void* fwd_workspace, MvcDecoderGrads* g, void* bwd_workspace,
+                                    size_t bwd_workspace_bytes, void* stream) {
+  MVC_TRY(check_dims(d));
+  MVC_CHECK(p && out_logp && tokens_in && fwd_workspace && g && bwd_workspace, "mvc_decoder_backward: null argument");
+  DecWs w = dec_layout(d, const_cast<void*>(fwd_workspace));
+  DecBwdWs q = dec_bwd_layout(d, bwd_workspace);
+  MVC_CHECK(bwd_workspace_bytes >= q.bytes, "mvc_decoder_backward: workspace %zu < %zu", bwd_workspace_bytes, q.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = d->B, T = d->T, F = d->F, H = d->H, E = d->E, A = d->A, V = d->V, S = d->L - 1;
+  const bool bf = d->precision == MVC_BF16;
+  const size_t es = bf ? 2 : 4;
+  const int64_t ldx = F + H;
+  const int Vp = pad8(V), SBp = pad8(S * B), BTp = pad8(B * T), Ep = pad8(E);
+  const int SB = S * B;
+  // fp32 h_1..h_S (contiguous [S*B,H]) are not saved separately: they are the h-parts of xh slots 1..S.
+  const char* hall = cptr(w.xh, (int64_t)B * ldx + F, es);    // rows = slots 1..S, ld = ldx
+  const char* hprev = cptr(w.xh, F, es);                      // rows = slots 0..S-1
+
+  // ---- vocabulary projection backward (all steps at once)
+  if (dlogp) {
+    const float* lp = out_logp + (int64_t)B * V;
+    const float* dl = dlogp + (int64_t)B * V;
+    if (bf) {
+      MVC_CUDA(cudaMemsetAsync(q.dlogits_b, 0, (size_t)SB * Vp * 2, st));
+      MVC_TRY(mvc_log_softmax_bwd(lp, dl, SB, V, q.dlogits, q.dlogits_b, st));
+      MVC_TRY(mvc_transpose_to_bf16(p->out_w, 0, V, H, H, q.outwT, Vp, st));
+      // dhall = dlogits . out_w
+      MVC_TRY(mvc_gemm_bf16(SB, H, V, q.dlogits_b, Vp, q.outwT, Vp, 0.f, q.dhall, H, nullptr, nullptr, 0, st));
+      // dW_out = dlogits^T . hall ; db_out = colsum(dlogits) (fp32)
+      MVC_TRY(mvc_transpose_to_bf16(q.dlogits_b, 1, SB, V, Vp, q.dlogitsT, SBp, st));
+      MVC_TRY(mvc_transpose_to_bf16(hall, 1, SB, H, ldx, q.hallT, SBp, st));
+      MVC_TRY(mvc_gemm_bf16(V, H, SB, q.dlogitsT, SBp, q.hallT, SBp, 0.f, g->out_w, H, nullptr, nullptr, 0, st));
+      MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, st));
+    } else {
+      MVC_TRY(mvc_log_softmax_bwd(lp, dl, SB, V, q.dlogits, nullptr, st));
+      MVC_TRY(mvc_gemm_f32(SB, H, V, 1.f, q.dlogits, V, 1, p->out_w, 1, H, 0.f, q.dhall, H, nullptr, st));
+      MVC_TRY(mvc_gemm_f32(V, H, SB, 1.f, q.dlogits, 1, V, (const float*)hall, 1, ldx, 0.f, g->out_w, H, nullptr, st));
+      MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, st));
+    }
+  } else {
+    MVC_CUDA(cudaMemsetAsync(q.dhall, 0, sizeof(float) * (size_t)SB * H, st));
+    MVC_CUDA(cudaMemsetAsync(g->out_w, 0, sizeof(float) * (size_t)V * H, st));
+    MVC_CUDA(cudaMemsetAsync(g->out_b, 0, sizeof(float) * (size_t)V, st));
+  }
+  if (dhid) {
+    add_rows_kernel<<<gridn((int64_t)SB * H), 256, 0, st>>>(dhid + (int64_t)B * H, H, q.dhall, H, SB, H, 1);
+    MVC_LAUNCH_CHECK();
+  }
+
+  // ---- time loop
+  MVC_CUDA(cudaMemsetAsync(q.dc, 0, sizeof(float) * (size_t)B * H, st));
+  MVC_CUDA(cudaMemsetAsync(q.duk, 0, sizeof(float) * (size_t)B * T * A, st));
+  MVC_CUDA(cudaMemsetAsync(q.dwpart, 0, sizeof(float) * (size_t)B * A, st));
+  if (bf) MVC_TRY(mvc_transpose_to_bf16(w.wcat, 1, 4 * H, F + H, ldx, q.wcatT, 4 * H, st));
+  StepCfg cfg = dec_cfg(d, p, w, nullptr);
+  cfg.wcatT = q.wcatT;
+  for (int s = S - 1; s >= 0; --s) {
+    StepBwd io{};
+    io.rows = B;
+    io.act = w.act + (int64_t)s * B * 4 * H;
+    io.c_prev = w.c + (int64_t)s * B * H;
+    io.c_new = w.c + (int64_t)(s + 1) * B * H;
+    io.dh_ext = q.dhall + (int64_t)s * B * H;     // from the vocabulary projection (+ dhid)
+    io.dh_ld = H;
+    io.has_carry = (s != S - 1);
+    io.dc = q.dc;
+    io.dG = q.dG + (int64_t)s * B * 4 * H;
+    io.dG_b = bf ? mptr(q.dG_b, (int64_t)s * B * 4 * H, 2) : nullptr;
+    io.dxh = q.dxh;
+    io.wq = w.wq + (int64_t)s * B * A;
+    io.alpha = w.alpha + (int64_t)s * B * T;
+    io.dwq = q.dwq + (int64_t)s * B * A;
+    io.duk = q.duk;
+    io.dwpart = q.dwpart;
+    io.dkeys = nullptr;                           // features are inputs: no gradient
+    io.first = (s == 0);
+    MVC_TRY(step_backward(cfg, io, st));
+  }
+
+  // ---- hoisted parameter gradients
+  // attention: dW = dwq^T . h_prev ; db = colsum(dwq) ; dw = colsum(dwpart) ; dU = duk^T . feats
+  MVC_TRY(mvc_colsum(q.dwq, SB, A, A, g->att_b, st));
+  MVC_TRY(mvc_colsum(q.dwpart, B, A, A, g->att_w, st));
+  // LSTM biases
+  MVC_TRY(mvc_colsum(q.dG, SB, 4 * H, 4 * H, g->b_ih, st));
+  MVC_CUDA(cudaMemcpyAsync(g->b_hh, g->b_ih, sizeof(float) * 4 * (size_t)H, cudaMemcpyDeviceToDevice, st));
+  MVC_CUDA(cudaMemsetAsync(g->embedding, 0, sizeof(float) * (size_t)V * E, st));
+  if (!bf) {
+    const float* xh = (const float*)w.xh;
+    MVC_TRY(mvc_gemm_f32(A, H, SB, 1.f, q.dwq, 1, A, (const float*)hprev, 1, ldx, 0.f, g->att_W, H, nullptr, st));
+    MVC_TRY(mvc_gemm_f32(A, F, B * T, 1.f, q.duk, 1, A, (const float*)w.feats, 1, F, 0.f, g->att_U, F, nullptr, st));
+    // dW_ih[:, E:] = dG^T . ctx ; dW_hh = dG^T . h_prev
+    MVC_TRY(mvc_gemm_f32(4 * H, F, SB, 1.f, q.dG, 1, 4 * H, xh, 1, ldx, 0.f, g->w_ih + E, E + F, nullptr, st));
+    MVC_TRY(mvc_gemm_f32(4 * H, H, SB, 1.f, q.dG, 1, 4 * H, (const float*)hprev, 1, ldx, 0.f, g->w_hh, H, nullptr, st));
+    // embedding side: x_emb rows are gathered again (the teacher-forced path saved them, the table path did not)
+    MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, E, 0, st));
+    MVC_TRY(mvc_gemm_f32(4 * H, E, SB, 1.f, q.dG, 1, 4 * H, (const float*)w.xemb, 1, E, 0.f, g->w_ih, E + F, nullptr, st));
+    MVC_TRY(mvc_gemm_f32(SB, E, 4 * H, 1.f, q.dG, 4 * H, 1, p->w_ih, 1, E + F, 0.f, q.dxemb, E, nullptr, st));
+  } else {
+    // transposed bf16 operands (tcgen05 GEMM takes K-contiguous A[M,K], B[N,K])
+    MVC_TRY(mvc_transpose_to_bf16(q.dG_b, 1, SB, 4 * H, 4 * H, q.dGT, SBp, st));
+    MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, st));
+    MVC_TRY(mvc_transpose_to_bf16(q.dwq, 0, SB, A, A, q.dwqT, SBp, st));
+    MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * T, A, A, q.dukT, BTp, st));
+    MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
+    const char* hprevT = cptr(q.xhT, (int64_t)F * SBp, 2);
+    MVC_TRY(mvc_gemm_bf16(A, H, SB, q.dwqT, SBp, hprevT, SBp, 0.f, g->att_W, H, nullptr, nullptr, 0, st));
+    MVC_TRY(mvc_gemm_bf16(A, F, B * T, q.dukT, BTp, q.featsT, BTp, 0.f, g->att_U, F, nullptr, nullptr, 0, st));
+    MVC_TRY(mvc_gemm_bf16(4 * H, F, SB, q.dGT, SBp, q.xhT, SBp, 0.f, g->w_ih + E, E + F, nullptr, nullptr, 0, st));
+    MVC_TRY(mvc_gemm_bf16(4 * H, H, SB, q.dGT, SBp, hprevT, SBp, 0.f, g->w_hh, H, nullptr, nullptr, 0, st));
+    MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, st));
+    MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, st));
+    MVC_TRY(mvc_gemm_bf16(4 * H, E, SB, q.dGT, SBp, q.xembT, SBp, 0.f, g->w_ih, E + F, nullptr, nullptr, 0, st));
+    MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
+    MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, q.wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, st));
+  }
+  MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------ greedy ids
+namespace mvc {
+struct GreedyWs {
+  float* logits;   // [B, V]
+  int64_t* tok;    // [2, B]
+  float* c;        // [2, B, H]
+  float* wq;       // [B, A]
+  float* alpha;    // [B, T]
+  float* h32;      // [B, H]
+  size_t bytes;
+};
+static GreedyWs greedy_layout(const MvcDecoderDims* d, void* base, size_t dec_bytes) {
+  Arena ar(base);
+  ar.off = dec_bytes;
+  GreedyWs g{};
+  g.logits = ar.take<float>((int64_t)d->B * d->V);
+  g.tok = ar.take<int64_t>(2 * (int64_t)d->B);
+  g.c = ar.take<float>(2 * (int64_t)d->B * d->H);
+  g.wq = ar.take<float>((int64_t)d->B * d->A);
+  g.alpha = ar.take<float>((int64_t)d->B * d->T);
+  g.h32 = ar.take<float>((int64_t)d->B * d->H);
+  g.bytes = ar.off + 256;
+  return g;
+}
+// the step loop only needs two xh slots: shrink the layout by pretending L = 2
+static MvcDecoderDims two_slot_dims(const MvcDecoderDims* d) {
+  MvcDecoderDims e = *d;
+  e.L = 2;
+  return e;
+}
+}  // namespace mvc
+
+extern "C" size_t mvc_decoder_greedy_workspace_bytes(const MvcDecoderDims* d) {
+  MvcDecoderDims e = two_slot_dims(d);
+  return greedy_layout(d, nullptr, dec_layout(&e, nullptr).bytes).bytes;
+}
+
+extern "C" int mvc_decoder_greedy(const MvcDecoderDims* d, const MvcDecoderParams* p, const float* audio, int Fa,
+                                  const float* visual, int Fv, int64_t* ids, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  MVC_TRY(check_dims(d));
+  MVC_CHECK(p && ids && workspace, "mvc_decoder_greedy: null argument");
+  MvcDecoderDims e = two_slot_dims(d);
+  DecWs w = dec_layout(&e, workspace);
+  GreedyWs gw = greedy_layout(d, workspace, w.bytes);
+  MVC_CHECK(workspace_bytes >= gw.bytes, "mvc_decoder_greedy: workspace %zu < %zu", workspace_bytes, gw.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = d->B, F = d->F, H = d->H, V = d->V, S = d->L - 1, L = d->L;
+  const bool bf = d->precision == MVC_BF16;
+  const size_t es = bf ? 2 : 4;
+  const int64_t ldx = F + H;
+  MVC_TRY(dec_prepare(d, p, audio, Fa, visual, Fv, w, true, st));
+  MVC_CUDA(cudaMemsetAsync(w.xh, 0, es * (size_t)2 * B * ldx, st));
+  MVC_CUDA(cudaMemsetAsync(gw.c, 0, sizeof(float) * (size_t)B * H, st));
+  MVC_CUDA(cudaMemsetAsync(ids, 0, sizeof(int64_t) * (size_t)B * L, st));      // column 0 = argmax of zeros = 0
+  fill_i64_kernel<<<(unsigned)cdiv(B, 256), 256, 0, st>>>(gw.tok, MVC_SOS, B);
+  MVC_LAUNCH_CHECK();
+  const StepCfg cfg = dec_cfg(d, p, w, nullptr);
+  for (int s = 0; s < S; ++s) {
+    StepFwd io{};
+    io.rows = B;
+    io.xh_src = mptr(w.xh, (int64_t)(s & 1) * B * ldx, es);
+    io.xh_dst = mptr(w.xh, (int64_t)((s + 1) & 1) * B * ldx, es);
+    io.wq = gw.wq; io.alpha = gw.alpha; io.act = nullptr;
+    io.c_prev = gw.c + (int64_t)(s & 1) * B * H;
+    io.c_out = gw.c + (int64_t)((s + 1) & 1) * B * H;
+    io.tokens = gw.tok + (int64_t)(s & 1) * B;
+    io.h_out32 = gw.h32;
+    io.h_ld = H;
+    io.first = (s == 0);
+    MVC_TRY(step_forward(cfg, io, st));
+    MVC_TRY(gemm_nt(d->precision, B, V, H, bf ? cptr(io.xh_dst, F, es) : (const char*)gw.h32, bf ? ldx : H,
+                    bf ? w.outw : (const void*)p->out_w, H, 0.f, gw.logits, V, p->out_b, st));
+    int64_t* nxt = gw.tok + (int64_t)((s + 1) & 1) * B;
+    // argmax of the log-probs == argmax of the logits up to fp32 rounding ties; normalise anyway so that
+    // ids agree with decode(captions=None).argmax(2) (captioning.py:138-140)
+    MVC_TRY(mvc_log_softmax_rows(gw.logits, B, V, nxt, st));
+    scatter_col_i64_kernel<<<(unsigned)cdiv(B, 256), 256, 0, st>>>(nxt, ids, L, s + 1, B);
+    MVC_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ beam search
+namespace mvc {
+
+constexpr int kMaxBeam = 8;
+
+// Per row of logits: log-sum-exp and the `width` best (log-prob, token), ties -> lowest token.
+__global__ void beam_row_topk_kernel(const float* __restrict__ logits, int V, int width, float* __restrict__ cand_val,
+                                     int* __restrict__ cand_idx) {
+  __shared__ float red[32];
+  __shared__ int redi[32];
+  __shared__ float s_last_val;
+  __shared__ int s_last_idx;
+  const float* row = logits + (int64_t)blockIdx.x * V;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, row[v]);
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(row[v] - mx);
+  sum = block_sum(sum, red);
+  const float lse = mx + logf(sum);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  float last_val = INFINITY;
+  int last_idx = -1;
+  for (int k = 0; k < width; ++k) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float y = row[v] - lse;
+      const bool after = (y < last_val) || (y == last_val && v > last_idx);   // strictly after the previous pick
+      if (after && (y > best || (y == best && v < bi))) { best = y; bi = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { red[wid] = best; redi[wid] = bi; }
+    __syncthreads();
+    if (wid == 0) {
+      best = lane < nw ? red[lane] : -INFINITY;
+      bi = lane < nw ? redi[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) {
+        s_last_val = best; s_last_idx = bi;
+        cand_val[(int64_t)blockIdx.x * width + k] = best;
+        cand_idx[(int64_t)blockIdx.x * width + k] = bi;
+      }
+    }
+    __syncthreads();
+    last_val = s_last_val; last_idx = s_last_idx;
+  }
+}
+
+// One thread per batch item: merge nb*width candidates, keep `width`
+// (features_captioning.py:166-193, 201-209).  State arrays are beam-major [beam, B].
+__global__ void beam_merge_kernel(int B, int V, int nb, int width, int t, float alpha, const float* __restrict__ cand_val,
+                                  const int* __restrict__ cand_idx, const float* __restrict__ cum,
+                                  const uint8_t* __restrict__ done, const int* __restrict__ len,
+                                  float* __restrict__ cum_out, uint8_t* __restrict__ done_out, int* __restrict__ len_out,
+                                  int* __restrict__ sel_beam, int64_t* __restrict__ tok_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float sc[kMaxBeam * kMaxBeam], rk[kMaxBeam * kMaxBeam];
+  int64_t flat[kMaxBeam * kMaxBeam];
+  const int n = nb * width;
+  for (int k = 0; k < nb; ++k) {
+    const int row = k * B + b;
+    const bool fin = done[row];
+    const float clen = fin ? (float)len[row] : (float)(t + 1);                  // :171-176
+    const float norm = alpha == 0.f ? 1.f : powf(5.f + clen, alpha) / powf(6.f, alpha);   // :177
+    for (int j = 0; j < width; ++j) {
+      // finished beam: EOS_mask zeroes the step scores, so every child scores `cum`; lowest tokens win the tie
+      const float v = fin ? 0.f : cand_val[(int64_t)row * width + j];
+      const int tok = fin ? j : cand_idx[(int64_t)row * width + j];
+      const float s = v + cum[row];                                             // :166-168
+      sc[k * width + j] = s;
+      rk[k * width + j] = s / norm;
+      flat[k * width + j] = (int64_t)k * V + tok;
+    }
+  }
+  bool used[kMaxBeam * kMaxBeam];
+  for (int i = 0; i < n; ++i) used[i] = false;
+  for (int r = 0; r < width; ++r) {
+    int best = -1;
+    for (int i = 0; i < n; ++i) {
+      if (used[i]) continue;
+      if (best < 0 || rk[i] > rk[best] || (rk[i] == rk[best] && flat[i] < flat[best])) best = i;
+    }
+    used[best] = true;
+    const int kb = (int)(flat[best] / V);                                       // :192
+    const int tok = (int)(flat[best] % V);                                      // :193
+    const int src = kb * B + b, dst = r * B + b;
+    const bool was = done[src];
+    const bool now = !was && tok == MVC_EOS;
+    cum_out[dst] = sc[best];                                                    // :207 (un-normalised)
+    done_out[dst] = (was || now) ? 1 : 0;
+    len_out[dst] = was ? len[src] : (now ? t + 1 : 0);
+    sel_beam[dst] = kb;
+    tok_out[dst] = tok;
+  }
+}
+
+// Reorder beam state: h (inside xh rows), c, sequences; append the chosen token.
+template <typename XT>
+__global__ void beam_reorder_kernel(int B, int H, int F, int width, int t, int Lb, const int* __restrict__ sel_beam,
+                                    const int64_t* __restrict__ tok, const XT* __restrict__ xh_src,
+                                    XT* __restrict__ xh_dst, const float* __restrict__ c_src, float* __restrict__ c_dst,
+                                    const int* __restrict__ seq_src, int* __restrict__ seq_dst) {
+  const int dst = blockIdx.x;             // k*B + b
+  const int b = dst % B;
+  const int src = sel_beam[dst] * B + b;
+  const int64_t ldx = F + H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    xh_dst[(int64_t)dst * ldx + F + j] = xh_src[(int64_t)src * ldx + F + j];
+    c_dst[(int64_t)dst * H + j] = c_src[(int64_t)src * H + j];
+  }
+  for (int j = threadIdx.x; j < t; j += blockDim.x) seq_dst[(int64_t)dst * Lb + j] = seq_src[(int64_t)src * Lb + j];
+  if (threadIdx.x == 0) seq_dst[(int64_t)dst * Lb + t] = (int)tok[dst];
+}
+
+__global__ void beam_emit_kernel(int B, int Lb, const int* __restrict__ seq, int64_t* __restrict__ ids) {
+  const int b = blockIdx.x;
+  int64_t* o = ids + (int64_t)b * (Lb + 1);
+  if (threadIdx.x == 0) o[0] = MVC_SOS;                                          // :227
+  for (int j = threadIdx.x; j < Lb; j += blockDim.x) o[1 + j] = seq[(int64_t)b * Lb + j];   // beam 0
+}
+
+struct BeamWs {
+  float* logits;     // [W*B, V]
+  float* cand_val;   // [W*B, W]
+  int* cand_idx;     // [W*B, W]
+  float* cum[2];     // [W*B]
+  uint8_t* done[2];
+  int* len[2];
+  int* sel;          // [W*B]
+  int64_t* tok[2];   // [W*B]
+  float* c[3];       // [W*B, H]  (prev, new-unordered, reordered)
+  int* seq[2];       // [W*B, Lb]
+  float* wq;         // [W*B, A]
+  float* alpha;      // [W*B, T]
+  float* h32;        // [W*B, H]
+  float* pre;        // [W*B, 4H]
+  void* xh[3];       // [W*B, F+H]
+  size_t bytes;
+};
+static BeamWs beam_layout(const MvcDecoderDims* d, int width, void* base, size_t dec_bytes) {
+  Arena ar(base);
+  ar.off = dec_bytes;
+  const int64_t R = (int64_t)width * d->B, Lb = d->L + 1;
+  const size_t es = d->precision == MVC_BF16 ? 2 : 4;
+  BeamWs w{};
+  w.logits = ar.take<float>(R * d->V);
+  w.cand_val = ar.take<float>(R * width);
+  w.cand_idx = ar.take<int>(R * width);
+  for (int i = 0; i < 2; ++i) {
+    w.cum[i] = ar.take<float>(R);
+    w.done[i] = ar.take<uint8_t>(R);
+    w.len[i] = ar.take<int>(R);
+    w.tok[i] = ar.take<int64_t>(R);
+    w.seq[i] = ar.take<int>(R * Lb);
+  }
+  w.sel = ar.take<int>(R);
+  for (int i = 0; i < 3; ++i) {
+    w.c[i] = ar.take<float>(R * d->H);
+    w.xh[i] = ar.take<char>(R * (d->F + d->H) * es);
+  }
+  w.wq = ar.take<float>(R * d->A);
+  w.alpha = ar.take<float>(R * d->T);
+  w.h32 = ar.take<float>(R * d->H);
+  w.pre = ar.take<float>(R * 4 * d->H);
+  w.bytes = ar.off + 256;
+  return w;
+}
+static MvcDecoderDims beam_dec_dims(const MvcDecoderDims* d) {
+  MvcDecoderDims e = *d;
+  e.L = 2;          // xh slots come from BeamWs instead
+  return e;
+}
+}  // namespace mvc
+
+extern "C" size_t mvc_decoder_beam_workspace_bytes(const MvcDecoderDims* d, int width) {
+  MvcDecoderDims e = beam_dec_dims(d);
+  return beam_layout(d, width, nullptr, dec_layout(&e, nullptr).bytes).bytes;
+}
+
+extern "C" int mvc_decoder_beam(const MvcDecoderDims* d, const MvcDecoderParams* p, const float* audio, int Fa,
+                                const float* visual, int Fv, int width, float alpha, int64_t* ids, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  MVC_TRY(check_dims(d));
+  MVC_CHECK(p && ids && workspace, "mvc_decoder_beam: null argument");
+  MVC_CHECK(width >= 1 && width <= kMaxBeam, "mvc_decoder_beam: beam_width %d not in [1,%d]", width, kMaxBeam);
+  MVC_CHECK(width <= d->V, "mvc_decoder_beam: beam_width > vocab");
+  MvcDecoderDims e = beam_dec_dims(d);
+  DecWs w = dec_layout(&e, workspace);
+  BeamWs bw = beam_layout(d, width, workspace, w.bytes);
+  MVC_CHECK(workspace_bytes >= bw.bytes, "mvc_decoder_beam: workspace %zu < %zu", workspace_bytes, bw.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = d->B, F = d->F, H = d->H, V = d->V;
+  const int max_len = d->L, Lb = max_len + 1;       // max_caption_len + 1 steps (:149)
+  const bool bf = d->precision == MVC_BF16;
+  const size_t es = bf ? 2 : 4;
+  const int64_t ldx = F + H;
+  const int64_t R = (int64_t)width * B;
+  MVC_TRY(dec_prepare(d, p, audio, Fa, visual, Fv, w, true, st));
+  MVC_CUDA(cudaMemsetAsync(bw.xh[0], 0, es * (size_t)R * ldx, st));
+  MVC_CUDA(cudaMemsetAsync(bw.c[0], 0, sizeof(float) * (size_t)R * H, st));
+  MVC_CUDA(cudaMemsetAsync(bw.cum[0], 0, sizeof(float) * (size_t)R, st));       // log(1) = 0 (:144-145)
+  MVC_CUDA(cudaMemsetAsync(bw.done[0], 0, (size_t)R, st));
+  MVC_CUDA(cudaMemsetAsync(bw.len[0], 0, sizeof(int) * (size_t)R, st));
+  fill_i64_kernel<<<(unsigned)cdiv(R, 256), 256, 0, st>>>(bw.tok[0], MVC_SOS, R);
+  MVC_LAUNCH_CHECK();
+  int cur = 0;      // index of the current state buffers
+  void* xh_cur = bw.xh[0];
+  void* xh_new = bw.xh[1];
+  void* xh_nxt = bw.xh[2];
+  float* c_cur = bw.c[0];
+  float* c_new = bw.c[1];
+  float* c_nxt = bw.c[2];
+  const StepCfg cfg = dec_cfg(d, p, w, bw.pre);
+  for (int t = 0; t < Lb; ++t) {
+    const int nb = (t == 0) ? 1 : width;
+    const int rows = nb * B;
+    StepFwd io{};
+    io.rows = rows;
+    io.xh_src = xh_cur; io.xh_dst = xh_new;
+    io.wq = bw.wq; io.alpha = bw.alpha; io.act = nullptr;
+    io.c_prev = c_cur; io.c_out = c_new;
+    io.tokens = bw.tok[cur];
+    io.h_out32 = bw.h32;
+    io.h_ld = H;
+    io.first = (t == 0);
+    MVC_TRY(step_forward(cfg, io, st));
+    MVC_TRY(gemm_nt(d->precision, rows, V, H, bf ? cptr(xh_new, F, es) : (const char*)bw.h32, bf ? ldx : H,
+                    bf ? w.outw : (const void*)p->out_w, H, 0.f, bw.logits, V, p->out_b, st));
+    beam_row_topk_kernel<<<rows, 256, 0, st>>>(bw.logits, V, width, bw.cand_val, bw.cand_idx);
+    MVC_LAUNCH_CHECK();
+    const int nx = cur ^ 1;
+    beam_merge_kernel<<<(unsigned)cdiv(B, 128), 128, 0, st>>>(B, V, nb, width, t, alpha, bw.cand_val, bw.cand_idx,
+                                                             bw.cum[cur], bw.done[cur], bw.len[cur], bw.cum[nx],
+                                                             bw.done[nx], bw.len[nx], bw.sel, bw.tok[nx]);
+    MVC_LAUNCH_CHECK();
+    if (bf)
+      beam_reorder_kernel<__nv_bfloat16><<<(unsigned)R, 128, 0, st>>>(B, H, F, width, t, Lb, bw.sel, bw.tok[nx],
+                                                                     (const __nv_bfloat16*)xh_new, (__nv_bfloat16*)xh_nxt,
+                                                                     c_new, c_nxt, bw.seq[cur], bw.seq[nx]);
+    else
+      beam_reorder_kernel<float><<<(unsigned)R, 128, 0, st>>>(B, H, F, width, t, Lb, bw.sel, bw.tok[nx],
+                                                             (const float*)xh_new, (float*)xh_nxt, c_new, c_nxt,
+                                                             bw.seq[cur], bw.seq[nx]);
+    MVC_LAUNCH_CHECK();
+    // rotate: reordered state becomes current
+    void* tx = xh_cur; xh_cur = xh_nxt; xh_nxt = tx;
+    float* tc = c_cur; c_cur = c_nxt; c_nxt = tc;
+    cur = nx;
+  }
+  beam_emit_kernel<<<B, 64, 0, st>>>(B, Lb, bw.seq[cur], ids);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,472 @@
+// elementwise.cu -- HBM-bound glue kernels of the SA-LSTM path: feature
+// concat/cast, LSTM cell update and its backward, row-wise log-softmax /
+// argmax, embedding gather / scatter-add, column sums, Adam.
+#include <stdarg.h>
+
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mvc {
+
+static thread_local char g_err[512] = "";
+long long g_launches = 0;
+
+int g_prof_kid = 0, g_prof_m = -1, g_prof_n = -1, g_prof_k = -1;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+static size_t g_prof_used = 0;
+void prof_begin(cudaStream_t st) {
+  if (g_prof_used == g_prof_pool.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    g_prof_pool.emplace_back(a, b);
+  }
+  cudaEventRecord(g_prof_pool[g_prof_used].first, st);
+}
+void prof_end(cudaStream_t st) {
+  if (g_prof_used < g_prof_pool.size()) cudaEventRecord(g_prof_pool[g_prof_used++].second, st);
+}
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------- concat / cast
+template <typename OutT>
+__global__ void concat_cast_kernel(const float* __restrict__ a, int Fa, const float* __restrict__ v, int Fv,
+                                   int64_t rows, OutT* __restrict__ dst) {
+  const int F = Fa + Fv;
+  const int64_t total = rows * F;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F;
+    const int f = (int)(i - r * F);
+    const float x = (f < Fa) ? a[r * Fa + f] : v[r * Fv + (f - Fa)];
+    if constexpr (sizeof(OutT) == 2) dst[i] = __float2bfloat16(x);
+    else dst[i] = x;
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+template <typename ST>
+__global__ void transpose_bf16_kernel(const ST* __restrict__ src, int64_t R, int64_t C, int64_t lds,
+                                      __nv_bfloat16* __restrict__ dst, int64_t ldd) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = __float2bfloat16((r < R && c < C) ? ld_as_float(src + r * lds + c) : 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) dst[c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------- LSTM cell
+// gates pre-activation = pre + gx + emb_table[token] + bias, PyTorch order i,f,g,o.
+__global__ void lstm_cell_fwd_kernel(int B, int H, const float* __restrict__ pre, const float* __restrict__ gx,
+                                     int64_t gx_ld, const float* __restrict__ emb_table,
+                                     const int64_t* __restrict__ tokens, const float* __restrict__ bias,
+                                     const float* __restrict__ c_prev, float* __restrict__ act,
+                                     float* __restrict__ c_out, float* __restrict__ h_out, int64_t h_ld,
+                                     float* __restrict__ h_out2, int64_t h2_ld, __nv_bfloat16* __restrict__ h_bf16,
+                                     int64_t hb_ld) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * H) return;
+  const int b = (int)(i / H), j = (int)(i - (int64_t)b * H);
+  float g[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = q * H + j;
+    float v = pre[(int64_t)b * 4 * H + col];
+    if (gx) v += gx[b * gx_ld + col];
+    if (emb_table) v += emb_table[tokens[b] * (int64_t)(4 * H) + col];
+    if (bias) v += bias[col];
+    g[q] = v;
+  }
+  const float ig = sigmoid_f(g[0]), fg = sigmoid_f(g[1]), gg = tanhf(g[2]), og = sigmoid_f(g[3]);
+  const float cp = c_prev ? c_prev[i] : 0.f;
+  const float c = fg * cp + ig * gg;
+  const float h = og * tanhf(c);
+  if (act) {
+    float* a = act + (int64_t)b * 4 * H;
+    a[j] = ig; a[H + j] = fg; a[2 * H + j] = gg; a[3 * H + j] = og;
+  }
+  c_out[i] = c;
+  if (h_out) h_out[b * h_ld + j] = h;
+  if (h_out2) h_out2[b * h2_ld + j] = h;
+  if (h_bf16) h_bf16[b * hb_ld + j] = __float2bfloat16(h);
+}
+
+__global__ void lstm_cell_bwd_kernel(int B, int H, const float* __restrict__ act, const float* __restrict__ c_prev,
+                                     const float* __restrict__ c_new, const float* __restrict__ dh_a, int64_t dha_ld,
+                                     const float* __restrict__ dh_b, int64_t dhb_ld, float* __restrict__ dc,
+                                     float* __restrict__ dgates, __nv_bfloat16* __restrict__ dg_bf16) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * H) return;
+  const int b = (int)(i / H), j = (int)(i - (int64_t)b * H);
+  const float* a = act + (int64_t)b * 4 * H;
+  const float ig = a[j], fg = a[H + j], gg = a[2 * H + j], og = a[3 * H + j];
+  float dh = 0.f;
+  if (dh_a) dh += dh_a[b * dha_ld + j];
+  if (dh_b) dh += dh_b[b * dhb_ld + j];
+  const float tc = tanhf(c_new[i]);
+  const float dct = dc[i] + dh * og * (1.f - tc * tc);
+  const float cp = c_prev ? c_prev[i] : 0.f;
+  const float d_i = dct * gg * ig * (1.f - ig);
+  const float d_f = dct * cp * fg * (1.f - fg);
+  const float d_g = dct * ig * (1.f - gg * gg);
+  const float d_o = dh * tc * og * (1.f - og);
+  dc[i] = dct * fg;
+  float* d = dgates + (int64_t)b * 4 * H;
+  d[j] = d_i; d[H + j] = d_f; d[2 * H + j] = d_g; d[3 * H + j] = d_o;
+  if (dg_bf16) {
+    __nv_bfloat16* q = dg_bf16 + (int64_t)b * 4 * H;
+    q[j] = __float2bfloat16(d_i); q[H + j] = __float2bfloat16(d_f);
+    q[2 * H + j] = __float2bfloat16(d_g); q[3 * H + j] = __float2bfloat16(d_o);
+  }
+}
+
+// ------------------------------------------------------------- log-softmax / argmax over rows
+__global__ void log_softmax_rows_kernel(float* __restrict__ x, int V, int64_t* __restrict__ argmax) {
+  __shared__ float red[32];
+  __shared__ int redi[32];
+  float* row = x + (int64_t)blockIdx.x * V;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, row[v]);
+  mx = block_max(mx, red);
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(row[v] - mx);
+  s = block_sum(s, red);
+  const float lse = mx + logf(s);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float y = row[v] - lse;
+    row[v] = y;
+    if (y > best) { best = y; bi = v; }   // ascending v per thread: first max kept
+  }
+  if (argmax) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { red[wid] = best; redi[wid] = bi; }
+    __syncthreads();
+    if (wid == 0) {
+      best = lane < nw ? red[lane] : -INFINITY;
+      bi = lane < nw ? redi[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) argmax[blockIdx.x] = (bi == 0x7fffffff) ? 0 : bi;
+    }
+  }
+}
+
+__global__ void argmax_rows_kernel(const float* __restrict__ x, const float* __restrict__ y, int V,
+                                   int64_t* __restrict__ out) {
+  __shared__ float red[32];
+  __shared__ int redi[32];
+  const float* rx = x + (int64_t)blockIdx.x * V;
+  const float* ry = y ? y + (int64_t)blockIdx.x * V : nullptr;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float t = ry ? rx[v] + ry[v] : rx[v];
+    if (t > best) { best = t; bi = v; }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) { red[wid] = best; redi[wid] = bi; }
+  __syncthreads();
+  if (wid == 0) {
+    best = lane < nw ? red[lane] : -INFINITY;
+    bi = lane < nw ? redi[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) out[blockIdx.x] = (bi == 0x7fffffff) ? 0 : bi;
+  }
+}
+
+__global__ void log_softmax_bwd_kernel(const float* __restrict__ logp, const float* __restrict__ dlogp, int V,
+                                       float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dl_bf16, int64_t ldb) {
+  __shared__ float red[32];
+  const int64_t off = (int64_t)blockIdx.x * V;
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) s += dlogp[off + v];
+  s = block_sum(s, red);
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float d = dlogp[off + v] - expf(logp[off + v]) * s;
+    if (dlogits) dlogits[off + v] = d;
+    if (dl_bf16) dl_bf16[(int64_t)blockIdx.x * ldb + v] = __float2bfloat16(d);
+  }
+}
+
+// ------------------------------------------------------------- embedding
+template <typename OutT>
+__global__ void embedding_gather_kernel(const float* __restrict__ table, int E, const int64_t* __restrict__ idx,
+                                        OutT* __restrict__ out, int64_t out_ld, int width) {
+  const int64_t r = blockIdx.x;
+  const float* src = table + idx[r] * (int64_t)E;
+  for (int e = threadIdx.x; e < width; e += blockDim.x) {
+    const float v = e < E ? src[e] : 0.f;
+    if constexpr (sizeof(OutT) == 2) out[r * out_ld + e] = __float2bfloat16(v);
+    else out[r * out_ld + e] = v;
+  }
+}
+
+__global__ void embedding_scatter_add_kernel(const float* __restrict__ dx, int64_t dx_ld, int E,
+                                             const int64_t* __restrict__ idx, float* __restrict__ dtable) {
+  const int64_t r = blockIdx.x;
+  float* dst = dtable + idx[r] * (int64_t)E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(dst + e, dx[r * dx_ld + e]);
+}
+
+// out[n] = sum_r x[r,n]: one thread per column, fixed ascending-r order (deterministic).
+__global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int N, int64_t ld, float* __restrict__ out) {
+  // blockDim = (32, 8): 32 columns per CTA, 8 row-lanes reduced through shared memory.
+  __shared__ float part[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (n < N)
+    for (int64_t r = threadIdx.y; r < rows; r += 8) s += x[r * ld + n];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+    out[n] = t;
+  }
+}
+
+__global__ void caption_mask_kernel(const int64_t* __restrict__ cap, int64_t n, uint8_t* __restrict__ mask) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) mask[i] = (cap[i] != MVC_PAD && cap[i] != MVC_EOS) ? 1 : 0;
+}
+
+// ------------------------------------------------------------- clip + Adam(amsgrad)
+__global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, float* __restrict__ vmax, int64_t n, float lr, float b1,
+                                 float b2, float eps, float wd, float clip, float bc1, float bc2_sqrt,
+                                 float grad_scale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);       // clip_grad_value_  train.py:207-208
+    const float pi = p[i];
+    gi = fmaf(wd, pi, gi);                                      // Adam weight_decay (L2)
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float vm = fmaxf(vmax[i], vi);                        // amsgrad
+    m[i] = mi; v[i] = vi; vmax[i] = vm;
+    const float denom = sqrtf(vm) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+static inline int grid_for(int64_t n, int block = 256) {
+  int64_t g = cdiv(n, block);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace mvc
+
+using namespace mvc;
+
+extern "C" const char* mvc_last_error(void) { return mvc::g_err; }
+extern "C" int mvc_version(void) { return 100; }
+extern "C" long long mvc_launch_count(void) { return mvc::g_launches; }
+extern "C" int mvc_prof_arm(int kid, int m, int n, int k) {
+  mvc::g_prof_kid = kid; mvc::g_prof_m = m; mvc::g_prof_n = n; mvc::g_prof_k = k;
+  mvc::g_prof_used = 0;
+  return 0;
+}
+extern "C" int mvc_prof_collect(double* total_ms, long long* launches) {
+  double tot = 0.0;
+  for (size_t i = 0; i < mvc::g_prof_used; ++i) {
+    MVC_CUDA(cudaEventSynchronize(mvc::g_prof_pool[i].second));
+    float ms = 0.f;
+    MVC_CUDA(cudaEventElapsedTime(&ms, mvc::g_prof_pool[i].first, mvc::g_prof_pool[i].second));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (long long)mvc::g_prof_used;
+  mvc::g_prof_kid = 0;
+  mvc::g_prof_used = 0;
+  return 0;
+}
+extern "C" int mvc_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+extern "C" int mvc_concat_cast(const float* a, int Fa, const float* v, int Fv, int64_t rows, void* dst,
+                               int dst_bf16, void* stream) {
+  MVC_CHECK((Fa == 0 || a) && (Fv == 0 || v) && dst && Fa + Fv > 0, "mvc_concat_cast: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = rows * (Fa + Fv);
+  if (n == 0) return 0;
+  if (dst_bf16) concat_cast_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(a, Fa, v, Fv, rows, (__nv_bfloat16*)dst);
+  else concat_cast_kernel<float><<<grid_for(n), 256, 0, st>>>(a, Fa, v, Fv, rows, (float*)dst);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  cast_bf16_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_transpose_to_bf16(const void* src, int src_bf16, int64_t R, int64_t C, int64_t lds, void* dst,
+                                     int64_t ldd, void* stream) {
+  if (R == 0 || C == 0) return 0;
+  dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(R, 32)), block(32, 8);
+  if (src_bf16)
+    transpose_bf16_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, R, C, lds,
+                                                                                  (__nv_bfloat16*)dst, ldd);
+  else
+    transpose_bf16_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, R, C, lds,
+                                                                          (__nv_bfloat16*)dst, ldd);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_lstm_cell_fwd(int B, int H, const float* pre, const float* gx, int64_t gx_ld,
+                                 const float* emb_table, const int64_t* tokens, const float* bias,
+                                 const float* c_prev, float* act, float* c_out, float* h_out, int64_t h_ld,
+                                 float* h_out2, int64_t h2_ld, void* h_bf16, int64_t hb_ld, void* stream) {
+  MVC_CHECK(pre && c_out, "mvc_lstm_cell_fwd: null pre/c_out");
+  MVC_CHECK(!emb_table || tokens, "mvc_lstm_cell_fwd: emb_table without tokens");
+  const int64_t n = (int64_t)B * H;
+  if (n == 0) return 0;
+  ProfScope prof(PK_CELL_FWD, B, H, 0, (cudaStream_t)stream);
+  lstm_cell_fwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      B, H, pre, gx, gx_ld, emb_table, tokens, bias, c_prev, act, c_out, h_out, h_ld, h_out2, h2_ld,
+      (__nv_bfloat16*)h_bf16, hb_ld);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_lstm_cell_bwd(int B, int H, const float* act, const float* c_prev, const float* c_new,
+                                 const float* dh_a, int64_t dha_ld, const float* dh_b, int64_t dhb_ld, float* dc,
+                                 float* dgates, void* dg_bf16, void* stream) {
+  MVC_CHECK(act && c_new && dc && dgates, "mvc_lstm_cell_bwd: null argument");
+  const int64_t n = (int64_t)B * H;
+  if (n == 0) return 0;
+  ProfScope prof(PK_CELL_BWD, B, H, 0, (cudaStream_t)stream);
+  lstm_cell_bwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      B, H, act, c_prev, c_new, dh_a, dha_ld, dh_b, dhb_ld, dc, dgates, (__nv_bfloat16*)dg_bf16);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_log_softmax_rows(float* x, int64_t rows, int V, int64_t* argmax, void* stream) {
+  if (rows == 0) return 0;
+  MVC_CHECK(x && V > 0, "mvc_log_softmax_rows: bad arguments");
+  ProfScope prof(PK_LOGSOFTMAX, (int)rows, V, 0, (cudaStream_t)stream);
+  log_softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, V, argmax);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_argmax_rows(const float* x, const float* y, int64_t rows, int V, int64_t* out, void* stream) {
+  if (rows == 0) return 0;
+  MVC_CHECK(x && out && V > 0, "mvc_argmax_rows: bad arguments");
+  argmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, y, V, out);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_log_softmax_bwd(const float* logp, const float* dlogp, int64_t rows, int V, float* dlogits,
+                                   void* dlogits_bf16, void* stream) {
+  if (rows == 0) return 0;
+  MVC_CHECK(logp && dlogp && (dlogits || dlogits_bf16), "mvc_log_softmax_bwd: bad arguments");
+  const int64_t ldb = (V + 7) / 8 * 8;
+  log_softmax_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logp, dlogp, V, dlogits,
+                                                                        (__nv_bfloat16*)dlogits_bf16, ldb);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_embedding_gather(const float* table, int E, const int64_t* idx, int64_t rows, void* out,
+                                    int64_t out_ld, int out_bf16, void* stream) {
+  if (rows == 0) return 0;
+  MVC_CHECK(table && idx && out && out_ld >= E, "mvc_embedding_gather: bad arguments");
+  const int width = out_bf16 ? (int)out_ld : E;   // bf16 rows are zero-padded to out_ld (TMA K padding)
+  if (out_bf16) embedding_gather_kernel<__nv_bfloat16><<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(
+      table, E, idx, (__nv_bfloat16*)out, out_ld, width);
+  else embedding_gather_kernel<float><<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(table, E, idx, (float*)out,
+                                                                                     out_ld, width);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_embedding_scatter_add(const float* dx, int64_t dx_ld, int E, const int64_t* idx, int64_t rows,
+                                         float* dtable, void* stream) {
+  if (rows == 0) return 0;
+  embedding_scatter_add_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(dx, dx_ld, E, idx, dtable);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_colsum(const float* x, int64_t rows, int N, int64_t ld, float* out, void* stream) {
+  if (N == 0) return 0;
+  dim3 block(32, 8);
+  colsum_kernel<<<(unsigned)cdiv(N, 32), block, 0, (cudaStream_t)stream>>>(x, rows, N, ld, out);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_caption_mask(const int64_t* captions, int64_t n, uint8_t* mask, void* stream) {
+  if (n == 0) return 0;
+  caption_mask_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(captions, n, mask);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_clip_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                  float* max_exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                                  float weight_decay, float clip_value, int step, float grad_scale, void* stream) {
+  if (n == 0) return 0;
+  MVC_CHECK(step >= 1, "mvc_clip_adam_step: step counts from 1");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  ProfScope prof(PK_ADAM, 0, 0, 0, (cudaStream_t)stream);
+  clip_adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n,
+                                                               lr, beta1, beta2, eps, weight_decay, clip_value, bc1,
+                                                               bc2_sqrt, grad_scale);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,193 @@
+// losses.cu -- the loss bundle of src/losses.py as fused forward+gradient kernels.
+//
+//  * caption loss = F.nll_loss(ignore_index=PAD) (losses.py:112) + EntropyLoss
+//    (losses.py:12-17).  EntropyLoss applies softmax/log_softmax over dim=1 of
+//    the [L-1,B,V] log-prob tensor, i.e. over the BATCH axis; that quirk is
+//    part of the loss value and of its gradient, so it is kept: one thread owns
+//    one (step, vocab) column and walks the B batch entries (coalesced over V).
+//  * GlobalReconstructionLoss (losses.py:20-36), LocalReconstructionLoss (:39-40).
+#include "common.cuh"
+
+namespace mvc {
+
+// result[0] = mean NLL over non-PAD targets, result[2] = count; zeroes result[1].
+__global__ void nll_kernel(const float* __restrict__ logp, const int64_t* __restrict__ cap, int L, int B, int V,
+                           float* __restrict__ result) {
+  __shared__ float red[32];
+  const int64_t n = (int64_t)(L - 1) * B;
+  float s = 0.f, c = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t tok = cap[B + i];             // captions[1:]
+    if (tok != MVC_PAD) {
+      s -= logp[((int64_t)B + i) * V + tok];    // logp[1:]
+      c += 1.f;
+    }
+  }
+  s = block_sum(s, red);
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) {
+    result[0] = s / c;
+    result[1] = 0.f;
+    result[2] = c;
+  }
+}
+
+// One thread per (step s, vocab v) column of x = logp[1:].
+__global__ void entropy_kernel(const float* __restrict__ logp, const int64_t* __restrict__ cap, int L, int B, int V,
+                               float* __restrict__ result, double* __restrict__ ent_acc, float* __restrict__ dlogp,
+                               float ce_scale, float ent_scale) {
+  __shared__ float red[32];
+  const int s = blockIdx.y + 1;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = v < V;
+  const float* col = logp + (int64_t)s * B * V + v;
+  const int64_t* caps = cap + (int64_t)s * B;
+  float e_sum = 0.f;
+  if (live) {
+    float mx = -INFINITY;
+    for (int b = 0; b < B; ++b) mx = fmaxf(mx, col[(int64_t)b * V]);
+    float z = 0.f;
+    for (int b = 0; b < B; ++b) z += expf(col[(int64_t)b * V] - mx);
+    const float lse = mx + logf(z);
+    float q = 0.f;                               // sum_b m_b p_b (log p_b + 1)
+    for (int b = 0; b < B; ++b) {
+      if (caps[b] == MVC_PAD) continue;
+      const float lp = col[(int64_t)b * V] - lse;
+      const float p = expf(lp);
+      e_sum += p * lp;
+      q += p * (lp + 1.f);
+    }
+    if (dlogp) {
+      const float cnt = result[2];
+      const float es = -ent_scale / (float)B;
+      for (int b = 0; b < B; ++b) {
+        const float lp = col[(int64_t)b * V] - lse;
+        const float p = expf(lp);
+        const int64_t tok = caps[b];
+        const float m = tok != MVC_PAD ? 1.f : 0.f;
+        float g = es * p * (m * (lp + 1.f) - q);
+        if (tok != MVC_PAD && tok == v) g -= ce_scale / cnt;
+        dlogp[((int64_t)s * B + b) * V + v] = g;
+      }
+    }
+  }
+  e_sum = block_sum(e_sum, red);
+  if (threadIdx.x == 0) atomicAdd(ent_acc, (double)e_sum);
+}
+
+__global__ void entropy_finish_kernel(const double* __restrict__ ent_acc, int B, float* __restrict__ result) {
+  result[1] = (float)(-(*ent_acc) / (double)B);
+}
+
+// thread per (b, f).  acc[0] += sum (xm - xr)^2 ; optional gradient.
+__global__ void global_recon_loss_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ xrec,
+                                         int64_t r_ld, int B, int T, int L, int F, const int64_t* __restrict__ cap,
+                                         double* __restrict__ acc, float* __restrict__ dxrec, int64_t d_ld, float scale) {
+  __shared__ float red[32];
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float sq = 0.f;
+  if (i < (int64_t)B * F) {
+    const int b = (int)(i / F), f = (int)(i - (int64_t)b * F);
+    float xm = 0.f;
+    for (int t = 0; t < T; ++t) xm += x[((int64_t)b * T + t) * x_ld + f];
+    xm /= (float)T;                                                    // losses.py:25 (padding frames included)
+    float xr = 0.f, n = 0.f;
+    for (int l = 0; l < L; ++l)
+      if (cap[(int64_t)l * B + b] != MVC_PAD) {                        // keep_mask = captions != PAD (losses.py:104)
+        xr += xrec[((int64_t)b * L + l) * r_ld + f];
+        n += 1.f;
+      }
+    xr /= n;
+    const float d = xm - xr;
+    sq = d * d;
+    if (dxrec) {
+      const float g = scale * 2.f * (xr - xm) / ((float)B * (float)F) / n;
+      for (int l = 0; l < L; ++l)
+        if (cap[(int64_t)l * B + b] != MVC_PAD) dxrec[((int64_t)b * L + l) * d_ld + f] += g;
+    }
+  }
+  sq = block_sum(sq, red);
+  if (threadIdx.x == 0) atomicAdd(acc, (double)sq);
+}
+
+__global__ void local_recon_loss_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ xrec,
+                                        int64_t r_ld, int64_t rows, int F, double* __restrict__ acc,
+                                        float* __restrict__ dxrec, int64_t d_ld, float gscale) {
+  __shared__ float red[32];
+  const int64_t n = rows * F;
+  float sq = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F;
+    const int f = (int)(i - r * F);
+    const float d = xrec[r * r_ld + f] - x[r * x_ld + f];
+    sq = fmaf(d, d, sq);
+    if (dxrec) dxrec[r * d_ld + f] += gscale * d;
+  }
+  sq = block_sum(sq, red);
+  if (threadIdx.x == 0) atomicAdd(acc, (double)sq);
+}
+
+__global__ void mse_finish_kernel(const double* __restrict__ acc, double n, float* __restrict__ result) {
+  result[0] = (float)(*acc / n);
+}
+
+}  // namespace mvc
+
+using namespace mvc;
+
+extern "C" size_t mvc_caption_loss_workspace_bytes(int, int, int) { return 256; }
+
+extern "C" int mvc_caption_loss(const float* logp, const int64_t* captions, int L, int B, int V, float* result,
+                                float* dlogp, float ce_scale, float ent_scale, void* workspace, void* stream) {
+  MVC_CHECK(logp && captions && result && workspace, "mvc_caption_loss: null argument");
+  MVC_CHECK(L >= 2 && B >= 1 && V >= 1, "mvc_caption_loss: bad dims L=%d B=%d V=%d", L, B, V);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* acc = static_cast<double*>(workspace);
+  MVC_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
+  if (dlogp) MVC_CUDA(cudaMemsetAsync(dlogp, 0, sizeof(float) * (size_t)B * V, st));   // row 0 gets no gradient
+  nll_kernel<<<1, 1024, 0, st>>>(logp, captions, L, B, V, result);
+  MVC_LAUNCH_CHECK();
+  dim3 grid((unsigned)cdiv(V, 128), (unsigned)(L - 1));
+  ProfScope prof(PK_LOSS, L, B, V, st);
+  entropy_kernel<<<grid, 128, 0, st>>>(logp, captions, L, B, V, result, acc, dlogp, ce_scale, ent_scale);
+  MVC_LAUNCH_CHECK();
+  entropy_finish_kernel<<<1, 1, 0, st>>>(acc, B, result);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t mvc_global_recon_loss_workspace_bytes(int, int) { return 256; }
+
+extern "C" int mvc_global_recon_loss(const float* x, int64_t x_ld, const float* xrec, int64_t r_ld, int B, int T, int L,
+                                     int F, const int64_t* captions, float* result, float* dxrec, int64_t d_ld,
+                                     float scale, void* workspace, void* stream) {
+  MVC_CHECK(x && xrec && captions && result && workspace, "mvc_global_recon_loss: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* acc = static_cast<double*>(workspace);
+  MVC_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
+  const int64_t n = (int64_t)B * F;
+  global_recon_loss_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(x, x_ld, xrec, r_ld, B, T, L, F, captions, acc,
+                                                                   dxrec, d_ld, scale);
+  MVC_LAUNCH_CHECK();
+  mse_finish_kernel<<<1, 1, 0, st>>>(acc, (double)n, result);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_local_recon_loss(const float* x, int64_t x_ld, const float* xrec, int64_t r_ld, int64_t rows, int F,
+                                    float* result, float* dxrec, int64_t d_ld, float scale, void* workspace,
+                                    void* stream) {
+  MVC_CHECK(x && xrec && result && workspace, "mvc_local_recon_loss: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* acc = static_cast<double*>(workspace);
+  MVC_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
+  const int64_t n = rows * F;
+  int64_t g = cdiv(n, 256);
+  if (g > kNumSMs * 8) g = kNumSMs * 8;
+  local_recon_loss_kernel<<<(unsigned)g, 256, 0, st>>>(x, x_ld, xrec, r_ld, rows, F, acc, dxrec, d_ld,
+                                                       scale * 2.f / (float)n);
+  MVC_LAUNCH_CHECK();
+  mse_finish_kernel<<<1, 1, 0, st>>>(acc, (double)n, result);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}

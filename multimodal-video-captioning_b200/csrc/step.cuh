@@ -1,0 +1,142 @@
+// step.cuh -- one "soft attention -> LSTM cell" recurrence step and its backward,
+// shared by the caption decoder (features_captioning.py:77-89) and the local
+// reconstructor (reconstructor.py:67-74).  Host-side launch sequences only.
+#pragma once
+#include "common.cuh"
+
+namespace mvc {
+
+static inline int pad8(int x) { return (x + 7) / 8 * 8; }
+static inline const char* cptr(const void* p, int64_t elems, size_t es) { return (const char*)p + elems * es; }
+static inline char* mptr(void* p, int64_t elems, size_t es) { return (char*)p + elems * es; }
+
+static inline int gridn(int64_t n) {
+  int64_t g = cdiv(n, 256);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// C[M,N] = A[M,K] . B[N,K]^T (+ bias) (+ beta*C); operands K-contiguous in the compute dtype.
+static inline int gemm_nt(int prec, int M, int N, int K, const void* A, int64_t lda, const void* Bm, int64_t ldb,
+                          float beta, float* C, int64_t ldc, const float* bias, cudaStream_t st) {
+  if (prec == MVC_BF16) return mvc_gemm_bf16(M, N, K, A, lda, Bm, ldb, beta, C, ldc, bias, nullptr, 0, st);
+  return mvc_gemm_f32(M, N, K, 1.f, (const float*)A, lda, 1, (const float*)Bm, ldb, 1, beta, C, ldc, bias, st);
+}
+
+// Static description of the recurrence (constant over the time loop).
+struct StepCfg {
+  int prec;
+  int T, F, H, A;        // keys per row, key/context width, LSTM hidden, attention bottleneck
+  const float* uk;       // [keys_batch, T, A]   U.k (hoisted)
+  const void* keys;      // element (b,t,f) at keys[(b % keys_batch)*k_sb + t*k_st + f], compute dtype
+  int keys_batch;
+  int64_t k_sb, k_st;
+  const uint8_t* mask;   // optional [.,.] uint8 at mask[b*m_sb + t*m_st]
+  int64_t m_sb, m_st;
+  const void* wcat;      // [4H, F+H] = [W_ih(ctx part) | W_hh], compute dtype
+  const void* wcatT;     // [F+H, 4H] bf16 (backward, bf16 path only)
+  const void* attW;      // [A, H] attention.W in the compute dtype
+  const float* attW32;   // fp32 master copy (backward dh += dwq . W)
+  const float* att_b;    // [A]
+  const float* att_w;    // [A]
+  const float* cell_bias;  // [4H] added inside the cell (null when folded into gx / embtab)
+  const float* embtab;   // [V,4H] gathered by tokens inside the cell (or null)
+  float* pre;            // [rows, 4H] scratch
+};
+
+struct StepFwd {
+  int rows;
+  void* xh_src;          // [rows, F+H] slot: receives ctx_s, holds h_s
+  void* xh_dst;          // slot receiving h_{s+1} (may be null)
+  float* wq;             // [rows, A]
+  float* alpha;          // [rows, T]
+  float* act;            // [rows, 4H] or null
+  const float* c_prev;
+  float* c_out;
+  const float* gx;       // hoisted input projection rows [rows,4H] (ld 4H) or null
+  const int64_t* tokens; // rows of embtab to gather, or null
+  float* h_out32;        // fp32 h_{s+1} (ld h_ld), may be null
+  int64_t h_ld;
+  bool first;            // h_s == 0: skip the wq GEMM
+};
+
+static inline int step_forward(const StepCfg& c, const StepFwd& io, cudaStream_t st) {
+  const bool bf = c.prec == MVC_BF16;
+  const size_t es = bf ? 2 : 4;
+  const int64_t ldx = c.F + c.H;
+  const int R = io.rows;
+  // wq = h_s . W^T                                   (temporal_attention.py:20)
+  if (io.first) {
+    MVC_CUDA(cudaMemsetAsync(io.wq, 0, sizeof(float) * (size_t)R * c.A, st));
+  } else {
+    MVC_TRY(gemm_nt(c.prec, R, c.A, c.H, cptr(io.xh_src, c.F, es), ldx, c.attW, c.H, 0.f, io.wq, c.A, nullptr, st));
+  }
+  // ctx_s -> xh_src[:, :F]                            (temporal_attention.py:22-32)
+  MVC_TRY(mvc_soft_attention_fwd(R, c.T, c.A, c.F, io.wq, c.uk, c.att_b, c.att_w, c.keys, bf, c.keys_batch, c.k_sb,
+                                 c.k_st, c.mask, c.m_sb, c.m_st, bf ? nullptr : (float*)io.xh_src, ldx,
+                                 bf ? io.xh_src : nullptr, ldx, io.alpha, bf ? 1 : 0, st));
+  // gates = [ctx_s ; h_s] . wcat^T                    (nn.LSTM, features_captioning.py:84)
+  MVC_TRY(gemm_nt(c.prec, R, 4 * c.H, c.F + c.H, io.xh_src, ldx, c.wcat, ldx, 0.f, c.pre, 4 * c.H, nullptr, st));
+  float* h2 = nullptr;
+  void* hb = nullptr;
+  if (io.xh_dst) {
+    if (bf) hb = mptr(io.xh_dst, c.F, es);
+    else h2 = (float*)mptr(io.xh_dst, c.F, es);
+  }
+  MVC_TRY(mvc_lstm_cell_fwd(R, c.H, c.pre, io.gx, 4 * c.H, io.tokens ? c.embtab : nullptr, io.tokens, c.cell_bias,
+                            io.c_prev, io.act, io.c_out, io.h_out32, io.h_ld, h2, ldx, hb, ldx, st));
+  return 0;
+}
+
+struct StepBwd {
+  int rows;
+  const float* act;      // [rows,4H] saved activations of this step
+  const float* c_prev;
+  const float* c_new;
+  const float* dh_ext;   // external gradient w.r.t. h_{s+1} (ld dh_ld), may be null
+  int64_t dh_ld;
+  bool has_carry;        // add dxh[:, F:] (gradient carried from step s+1)
+  float* dc;             // [rows,H] in/out
+  float* dG;             // [rows,4H] out (fp32)
+  void* dG_b;            // bf16 copy (bf16 path)
+  float* dxh;            // [rows, F+H] out: d[ctx_s ; h_s]
+  const float* wq;       // saved
+  const float* alpha;    // saved
+  float* dwq;            // [rows, A] out
+  float* duk;            // [rows, T, A] accumulated
+  float* dwpart;         // [rows, A] accumulated
+  float* dkeys;          // optional accumulate, strides dk_sb/dk_st
+  int64_t dk_sb, dk_st;
+  bool first;            // s == 0: h_s is the zero initial state, skip dh_s
+};
+
+static inline int step_backward(const StepCfg& c, const StepBwd& io, cudaStream_t st) {
+  const bool bf = c.prec == MVC_BF16;
+  const int64_t ldx = c.F + c.H;
+  const int R = io.rows;
+  MVC_TRY(mvc_lstm_cell_bwd(R, c.H, io.act, io.c_prev, io.c_new, io.dh_ext, io.dh_ld,
+                            io.has_carry ? io.dxh + c.F : nullptr, ldx, io.dc, io.dG, io.dG_b, st));
+  // d[ctx_s ; h_s] = dgates . wcat
+  if (bf) MVC_TRY(mvc_gemm_bf16(R, c.F + c.H, 4 * c.H, io.dG_b, 4 * c.H, c.wcatT, 4 * c.H, 0.f, io.dxh, ldx, nullptr,
+                                nullptr, 0, st));
+  else MVC_TRY(mvc_gemm_f32(R, c.F + c.H, 4 * c.H, 1.f, io.dG, 4 * c.H, 1, (const float*)c.wcat, 1, ldx, 0.f, io.dxh,
+                            ldx, nullptr, st));
+  MVC_TRY(mvc_soft_attention_bwd(R, c.T, c.A, c.F, io.wq, c.uk, c.att_b, c.att_w, c.keys, bf, c.k_sb, c.k_st, io.alpha,
+                                 io.dxh, ldx, io.dwq, io.duk, io.dwpart, io.dkeys, io.dk_sb, io.dk_st, bf ? 1 : 0, st));
+  // dh_s += dwq . W        (wq = h_s . W^T)
+  if (!io.first)
+    MVC_TRY(mvc_gemm_f32(R, c.H, c.A, 1.f, io.dwq, c.A, 1, c.attW32, 1, c.H, 1.f, io.dxh + c.F, ldx, nullptr, st));
+  return 0;
+}
+
+// ---- small shared kernels (defined in decoder.cu) ----
+int launch_pack_wcat(const float* w_x, int64_t wx_ld, const float* w_hh, int F, int H, void* out, int out_bf16,
+                     cudaStream_t st);
+int launch_cast_pad_bf16(const float* src, int64_t rows, int C, int64_t lds, int Cp, void* out, cudaStream_t st);
+int launch_add_vec(const float* a, const float* b, float* o, int n, cudaStream_t st);
+int launch_fill_i64(int64_t* p, int64_t v, int64_t n, cudaStream_t st);
+int launch_iota_i64(int64_t* p, int64_t n, cudaStream_t st);
+int launch_add_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int C, int accumulate,
+                    cudaStream_t st);
+
+}  // namespace mvc
