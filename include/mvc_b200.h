@@ -123,6 +123,21 @@ int mvc_lstm_cell_fwd(int B, int H, const float* pre, const float* gx, int64_t g
                       const float* c_prev, float* act, float* c_out, float* h_out, int64_t h_ld,
                       float* h_out2, int64_t h2_ld, void* h_bf16, int64_t hb_ld, void* stream);
 
+/* Fused LSTM step on the tensor cores (K-C): gates = x . W^T on tcgen05 with fp32 accumulators in
+ * TMEM, and the cell update (bias / hoisted-projection addends, sigmoid/tanh, c and h) in the GEMM
+ * epilogue; K is split across CTAs and reduced deterministically.  features_captioning.py:84.
+ *   x [B,K] bf16 (ld ldx);  w_packed [4H,K] bf16 = the gate rows in TILE-INTERLEAVED order: packed
+ *   row (j/32)*128 + g*32 + j%32 is nn.LSTM row g*H + j (g = i,f,g,o) -- mvc_pack_gate_rows_bf16
+ *   builds it from an fp32 [4H,C] weight (ld ldw), zero-padding C to Cp (multiple of 8);
+ *   bias_packed [4H], gx_packed [B,4H] (optional addends) and act_packed [B,4H] (activated gates,
+ *   optional output) use the same column order; c_prev/c_out [B,H]; h_out fp32 (ld h_ld) and
+ *   h_bf16 (ld hb_ld) optional.  Requires H % 32 == 0. */
+int mvc_pack_gate_rows_bf16(const float* w, int H, int C, int64_t ldw, int Cp, void* out, void* stream);
+int mvc_lstm_gates_cell_bf16(int B, int H, int K, const void* x, int64_t ldx, const void* w_packed, int64_t ldw,
+                             const float* bias_packed, const float* gx_packed, int64_t gx_ld, const float* c_prev,
+                             float* act_packed, float* c_out, float* h_out, int64_t h_ld, void* h_bf16,
+                             int64_t hb_ld, void* stream);
+
 /* dgates (pre-activation) from dh (two optional addends dh_a [ld dha_ld], dh_b
  * [ld dhb_ld]) and the carried dc (in/out, [B,H]); dg_bf16 optional copy. */
 int mvc_lstm_cell_bwd(int B, int H, const float* act, const float* c_prev, const float* c_new,

@@ -11,7 +11,11 @@
 // T-rows split over thread groups and combined through shared memory.  Bound
 // by the read of keys [B,T,F] + uk [B,T,A]: HBM on first touch, L2 afterwards
 // (MSVD-shaped bf16 working set = 27 MB << 126 MB L2).
-#include "common.cuh"
+#include <mutex>
+#include <unordered_set>
+
+#include "ptx.cuh"
+#include "step.cuh"
 
 namespace mvc {
 
@@ -233,6 +237,247 @@ soft_attention_bwd_kernel(int T, int A, int F, const float* __restrict__ wq, con
   }
 }
 
+
+// ===================================================================== staged kernels (sm_100a fast path)
+// One CTA per (row, F-chunk).  The keys chunk [T x chunk] is pulled into shared memory by the TMA
+// engine (T 1-D bulk copies on one mbarrier) and the U.k rows are prefetched into registers; both are
+// loop invariant, so under programmatic dependent launch they are issued BEFORE griddepcontrol.wait
+// and overlap the kernel that is still producing this step's query.  Thread layout for the scores:
+// warp <-> frame t (round robin), lane <-> bottleneck unit a = lane + 32k.
+constexpr int ATT_MAXR = 8;      // frame rounds per warp held in registers (forward, 9 warps)
+constexpr int ATT_MAXR_BWD = 4;  // backward, 16 warps
+
+template <typename KT, bool FAST, int AV, int NT>
+__global__ void __launch_bounds__(NT)
+attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int NW = NT / 32;
+  constexpr int VN = VecOf<KT>::N;
+  const int T = a.T, A = AV * 32, F = a.F;
+  const int b = blockIdx.x, kb = b % a.keys_batch;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int f0 = blockIdx.y * chunk, f1 = min(F, f0 + chunk), ncols = f1 - f0;
+  const size_t stage_bytes = ((size_t)T * chunk * sizeof(KT) + 127) & ~size_t(127);
+  KT* sK = reinterpret_cast<KT*>(smem_raw);
+  float* sQ = reinterpret_cast<float*>(smem_raw + stage_bytes);
+  float* sW = sQ + A;
+  float* sE = sW + A;
+  float* sRed = sE + ((T + 3) & ~3);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sRed + 32);
+  const uint32_t bar = smem_u32(mbar);
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0 && ncols > 0) {
+    const KT* kbase = reinterpret_cast<const KT*>(a.keys) + (int64_t)kb * a.k_sb + f0;
+    const uint32_t row_bytes = (uint32_t)(ncols * sizeof(KT));
+    mbar_expect_tx(bar, row_bytes * (uint32_t)T);
+    for (int t = 0; t < T; ++t)
+      bulk_load_1d(smem_u32(sK + (size_t)t * chunk), kbase + (int64_t)t * a.k_st, row_bytes, bar);
+  }
+  // loop-invariant operands: U.k rows of this batch row -> registers, w -> smem
+  float ur[ATT_MAXR][AV];
+  const float* ukb = a.uk + (int64_t)kb * T * A;
+#pragma unroll
+  for (int r = 0; r < ATT_MAXR; ++r) {
+    const int t = wid + r * NW;
+    if (t < T) {
+#pragma unroll
+      for (int k = 0; k < AV; ++k) ur[r][k] = __ldg(ukb + (int64_t)t * A + lane + 32 * k);
+    }
+  }
+  for (int i = tid; i < A; i += NT) sW[i] = a.w[i];
+  pdl_trigger();
+  pdl_wait();                       // the query (wq) comes from the preceding kernel
+  for (int i = tid; i < A; i += NT) sQ[i] = a.wq[(int64_t)b * A + i] + a.bias[i];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < ATT_MAXR; ++r) {
+    const int t = wid + r * NW;
+    if (t < T) {
+      float e = 0.f;
+#pragma unroll
+      for (int k = 0; k < AV; ++k) e = fmaf(sW[lane + 32 * k], tanh_sel<FAST>(sQ[lane + 32 * k] + ur[r][k]), e);
+      e = warp_sum(e);
+      if (lane == 0) {
+        if (a.mask && !a.mask[b * a.m_sb + t * a.m_st]) e = -INFINITY;
+        sE[t] = e;
+      }
+    }
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int t = tid; t < T; t += NT) mx = fmaxf(mx, sE[t]);
+  mx = block_max(mx, sRed);
+  float s = 0.f;
+  for (int t = tid; t < T; t += NT) {
+    const float p = FAST ? __expf(sE[t] - mx) : expf(sE[t] - mx);
+    sE[t] = p;
+    s += p;
+  }
+  s = block_sum(s, sRed);
+  const float inv = 1.f / s;
+  for (int t = tid; t < T; t += NT) {
+    const float p = sE[t] * inv;
+    sE[t] = p;
+    if (blockIdx.y == 0) a.alpha[(int64_t)b * T + t] = p;
+  }
+  __syncthreads();
+  if (ncols <= 0) return;
+  mbar_wait(bar, 0);                // keys chunk has landed
+  const int nvec = ncols / VN;
+  for (int v = tid; v < nvec; v += NT) {
+    float acc[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {
+      const typename VecOf<KT>::Raw raw = *reinterpret_cast<const typename VecOf<KT>::Raw*>(sK + (size_t)t * chunk + v * VN);
+      float x[VN];
+      VecOf<KT>::unpack(raw, x);
+      const float p = sE[t];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] = fmaf(p, x[i], acc[i]);
+    }
+    const int f = f0 + v * VN;
+    if (a.ctx_f32) {
+      float* dst = a.ctx_f32 + b * a.ctx_ld + f;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) dst[i] = acc[i];
+    }
+    if (a.ctx_bf16) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.ctx_bf16) + b * a.ctxb_ld + f;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) dst[i] = __float2bfloat16(acc[i]);
+    }
+  }
+}
+
+// Backward, one CTA per batch row; keys row block staged by TMA bulk copies, U.k in registers.
+template <typename KT, bool FAST, int AV, int NT>
+__global__ void __launch_bounds__(NT)
+attn_bwd_staged_kernel(const AttnBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int NW = NT / 32;
+  constexpr int VN = VecOf<KT>::N;
+  const int T = a.T, A = AV * 32, F = a.F;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  size_t stage_bytes = ((size_t)T * F * sizeof(KT) + 127) & ~size_t(127);
+  if (stage_bytes < sizeof(float) * NW * 2 * A) stage_bytes = sizeof(float) * NW * 2 * A;
+  KT* sK = reinterpret_cast<KT*>(smem_raw);
+  // dctx, stored so that lane l's element (m*32*VN + l*VN + i) sits at word (m*VN + i)*32 + l: conflict-free
+  auto dpos = [](int f) { return ((f / (32 * VN)) * VN + (f % VN)) * 32 + (f % (32 * VN)) / VN; };
+  float* sD = reinterpret_cast<float*>(smem_raw + stage_bytes);       // dctx [F rounded to 32*VN]
+  float* sAl = sD + (F + 32 * VN - 1) / (32 * VN) * (32 * VN);        // alpha [T]
+  float* sDa = sAl + ((T + 3) & ~3);                                  // dalpha -> de [T]
+  float* sQ = sDa + ((T + 3) & ~3);                                   // wq + bias [A]
+  float* sW = sQ + A;                                                 // w [A]
+  float* sRed = sW + A;
+  float* sAcc = reinterpret_cast<float*>(smem_raw);                   // [NW][2][A] per-warp partials; reuses the keys
+                                                                      // stage once dalpha is done
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sRed + 32);
+  const uint32_t bar = smem_u32(mbar);
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const KT* kbase = reinterpret_cast<const KT*>(a.keys) + (int64_t)b * a.k_sb;
+    const uint32_t row_bytes = (uint32_t)(F * sizeof(KT));
+    mbar_expect_tx(bar, row_bytes * (uint32_t)T);
+    for (int t = 0; t < T; ++t) bulk_load_1d(smem_u32(sK + (size_t)t * F), kbase + (int64_t)t * a.k_st, row_bytes, bar);
+  }
+  float ur[ATT_MAXR_BWD][AV];
+  const float* ukb = a.uk + (int64_t)b * T * A;
+#pragma unroll
+  for (int r = 0; r < ATT_MAXR_BWD; ++r) {
+    const int t = wid + r * NW;
+    if (t < T) {
+#pragma unroll
+      for (int k = 0; k < AV; ++k) ur[r][k] = __ldg(ukb + (int64_t)t * A + lane + 32 * k);
+    }
+  }
+  for (int i = tid; i < A; i += NT) sW[i] = a.w[i];
+  pdl_trigger();
+  pdl_wait();
+  for (int f = tid; f < F; f += NT) sD[dpos(f)] = a.dctx[b * a.dctx_ld + f];
+  for (int t = tid; t < T; t += NT) sAl[t] = a.alpha[(int64_t)b * T + t];
+  for (int i = tid; i < A; i += NT) sQ[i] = a.wq[(int64_t)b * A + i] + a.bias[i];
+  __syncthreads();
+  mbar_wait(bar, 0);
+  // dalpha[t] = dctx . keys[t]
+  for (int t = wid; t < T; t += NW) {
+    const KT* row = sK + (size_t)t * F;
+    float d = 0.f;
+    for (int m = 0, f = lane * VN; f < F; f += 32 * VN, ++m) {
+      const typename VecOf<KT>::Raw raw = *reinterpret_cast<const typename VecOf<KT>::Raw*>(row + f);
+      float x[VN];
+      VecOf<KT>::unpack(raw, x);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) d = fmaf(sD[(m * VN + i) * 32 + lane], x[i], d);
+    }
+    d = warp_sum(d);
+    if (lane == 0) sDa[t] = d;
+  }
+  __syncthreads();                  // all reads of the staged keys are done: the stage area is free (sAcc)
+  float part = 0.f;
+  for (int t = tid; t < T; t += NT) part += sAl[t] * sDa[t];
+  const float dot = block_sum(part, sRed);
+  for (int t = tid; t < T; t += NT) sDa[t] = sAl[t] * (sDa[t] - dot);      // de[t]
+  __syncthreads();
+  // dpre[t,a] = de[t] w[a] (1 - tanh^2);  warp <-> t, lane <-> a
+  float sq[AV], sw[AV];
+#pragma unroll
+  for (int k = 0; k < AV; ++k) { sq[k] = 0.f; sw[k] = 0.f; }
+  float* dukb = a.duk ? a.duk + (int64_t)b * T * A : nullptr;
+#pragma unroll
+  for (int r = 0; r < ATT_MAXR_BWD; ++r) {
+    const int t = wid + r * NW;
+    if (t < T) {
+      const float de = sDa[t];
+#pragma unroll
+      for (int k = 0; k < AV; ++k) {
+        const int i = lane + 32 * k;
+        const float th = tanh_sel<FAST>(sQ[i] + ur[r][k]);
+        const float dpre = de * sW[i] * (1.f - th * th);
+        sq[k] += dpre;
+        sw[k] = fmaf(de, th, sw[k]);
+        if (dukb) dukb[(int64_t)t * A + i] += dpre;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < AV; ++k) {
+    sAcc[((size_t)wid * 2 + 0) * A + lane + 32 * k] = sq[k];
+    sAcc[((size_t)wid * 2 + 1) * A + lane + 32 * k] = sw[k];
+  }
+  __syncthreads();
+  for (int i = tid; i < A; i += NT) {
+    float q = 0.f, w2 = 0.f;
+#pragma unroll 4
+    for (int w = 0; w < NW; ++w) {          // fixed order: deterministic
+      q += sAcc[((size_t)w * 2 + 0) * A + i];
+      w2 += sAcc[((size_t)w * 2 + 1) * A + i];
+    }
+    a.dwq[(int64_t)b * A + i] = q;
+    if (a.dwq_bf16) reinterpret_cast<__nv_bfloat16*>(a.dwq_bf16)[(int64_t)b * A + i] = __float2bfloat16(q);
+    if (a.dw_partial) a.dw_partial[(int64_t)b * A + i] += w2;
+  }
+  if (a.dkeys) {
+    float* dkb = a.dkeys + (int64_t)b * a.dk_sb;
+    for (int64_t i = tid; i < (int64_t)T * F; i += NT) {
+      const int t = (int)(i / F), f = (int)(i - (int64_t)t * F);
+      dkb[(int64_t)t * a.dk_st + f] += sAl[t] * sD[dpos(f)];
+    }
+  }
+}
+
 template <typename T>
 static bool aligned16(const T* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -240,19 +485,95 @@ static bool aligned16(const T* p) { return (reinterpret_cast<uintptr_t>(p) & 15u
 
 using namespace mvc;
 
-extern "C" int mvc_soft_attention_fwd(int B, int T, int A, int F, const float* wq, const float* uk, const float* bias,
-                                      const float* w, const void* keys, int keys_bf16, int keys_batch, int64_t k_sb,
-                                      int64_t k_st, const uint8_t* mask, int64_t m_sb, int64_t m_st, float* ctx_f32,
-                                      int64_t ctx_ld, void* ctx_bf16, int64_t ctxb_ld, float* alpha, int fast_math,
-                                      void* stream) {
+namespace mvc {
+
+constexpr size_t kAttnMaxSmem = 220 * 1024;
+
+static int ensure_big_smem(const void* kern) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(kern)) return 0;
+  MVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnMaxSmem));
+  done.insert(kern);
+  return 0;
+}
+
+static int launch_ex(const void* kern, dim3 grid, dim3 block, size_t smem, bool pdl, void** args, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  MVC_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+  return 0;
+}
+
+template <typename KT, bool FAST>
+static const void* pick_fwd_staged(int A) {
+  switch (A) {
+    case 32: return (const void*)attn_fwd_staged_kernel<KT, FAST, 1, 288>;
+    case 64: return (const void*)attn_fwd_staged_kernel<KT, FAST, 2, 288>;
+    case 128: return (const void*)attn_fwd_staged_kernel<KT, FAST, 4, 288>;
+    case 256: return (const void*)attn_fwd_staged_kernel<KT, FAST, 8, 288>;
+    default: return nullptr;
+  }
+}
+template <typename KT, bool FAST>
+static const void* pick_bwd_staged(int A) {
+  switch (A) {
+    case 32: return (const void*)attn_bwd_staged_kernel<KT, FAST, 1, 512>;
+    case 64: return (const void*)attn_bwd_staged_kernel<KT, FAST, 2, 512>;
+    case 128: return (const void*)attn_bwd_staged_kernel<KT, FAST, 4, 512>;
+    case 256: return (const void*)attn_bwd_staged_kernel<KT, FAST, 8, 512>;
+    default: return nullptr;
+  }
+}
+
+int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
+  const int B = a.B, T = a.T, A = a.A, F = a.F;
   if (B == 0) return 0;
-  MVC_CHECK(wq && uk && bias && w && keys && alpha, "mvc_soft_attention_fwd: null argument");
-  MVC_CHECK(T > 0 && A > 0 && F > 0 && keys_batch > 0, "mvc_soft_attention_fwd: bad dims");
-  const int VN = keys_bf16 ? 8 : 4;
-  const bool vec = (F % VN == 0) && (k_sb % VN == 0) && (k_st % VN == 0) &&
-                   (reinterpret_cast<uintptr_t>(keys) % 16 == 0);
+  MVC_CHECK(a.wq && a.uk && a.bias && a.w && a.keys && a.alpha, "mvc_soft_attention_fwd: null argument");
+  MVC_CHECK(T > 0 && A > 0 && F > 0 && a.keys_batch > 0, "mvc_soft_attention_fwd: bad dims");
+  const int VN = a.keys_bf16 ? 8 : 4;
+  const size_t es = a.keys_bf16 ? 2 : 4;
+  const bool vec = (F % VN == 0) && (a.k_sb % VN == 0) && (a.k_st % VN == 0) &&
+                   (reinterpret_cast<uintptr_t>(a.keys) % 16 == 0) &&
+                   (!a.ctx_f32 || true);
+  ProfScope prof(PK_ATTN_FWD, B, T, F, st);
+  // ---- staged fast path
+  const void* kern = nullptr;
+  if (vec && T <= ATT_MAXR * 9) {
+    if (a.keys_bf16) kern = a.fast_math ? pick_fwd_staged<__nv_bfloat16, true>(A) : pick_fwd_staged<__nv_bfloat16, false>(A);
+    else kern = a.fast_math ? pick_fwd_staged<float, true>(A) : pick_fwd_staged<float, false>(A);
+  }
+  if (kern) {
+    const size_t tail = sizeof(float) * (2 * (size_t)A + ((T + 3) & ~3) + 32) + 16;
+    // fewest F-chunks whose staged keys fit in shared memory; more when the batch alone cannot fill the SMs
+    int fs = 1;
+    auto smem_for = [&](int fsplit, int* chunk_out) {
+      int chunk = (int)cdiv(cdiv(F, fsplit), VN) * VN;
+      *chunk_out = chunk;
+      return (((size_t)T * chunk * es + 127) & ~size_t(127)) + tail;
+    };
+    int chunk = F;
+    while (smem_for(fs, &chunk) > kAttnMaxSmem && fs < F / VN) ++fs;
+    while ((int64_t)B * fs < kNumSMs && fs < 8 && chunk > 64 * VN) { ++fs; smem_for(fs, &chunk); }
+    const size_t smem = smem_for(fs, &chunk);
+    fs = (int)cdiv(F, chunk);
+    if (smem <= kAttnMaxSmem) {
+      MVC_TRY(ensure_big_smem(kern));
+      AttnFwdArgs args = a;
+      void* params[] = {(void*)&args, (void*)&chunk};
+      MVC_TRY(launch_ex(kern, dim3(B, fs), dim3(288), smem, pdl, params, st));
+      MVC_LAUNCH_CHECK();
+      return 0;
+    }
+  }
+  // ---- generic path (any A / T / alignment): direct global loads
   const int vn = vec ? VN : 1;
-  // F-split: enough CTAs for ~2 waves, and at most 256 vectors per CTA
   int fs_min = (int)cdiv(F, 256 * vn);
   int fs = (int)cdiv(2 * kNumSMs, B);
   if (fs < fs_min) fs = fs_min;
@@ -260,28 +581,22 @@ extern "C" int mvc_soft_attention_fwd(int B, int T, int A, int F, const float* w
   if (fs > fs_max) fs = fs_max;
   int chunk = (int)cdiv(cdiv(F, fs), vn) * vn;
   fs = (int)cdiv(F, chunk);
-  const int nvec = chunk / vn;
-  int G = 256 / nvec;
-  if (G > T) G = T;
-  if (G < 1) G = 1;
-  (void)G; (void)nvec;
   const size_t smem = sizeof(float) * (2 * (size_t)A + T + 32 + (size_t)256 * vn);
   MVC_CHECK(smem <= 200 * 1024, "mvc_soft_attention_fwd: A=%d T=%d needs %zu B of shared memory", A, T, smem);
   dim3 grid(B, fs);
-  cudaStream_t st = (cudaStream_t)stream;
-  ProfScope prof(PK_ATTN_FWD, B, T, F, st);
 #define LAUNCH_FWD(KT, FAST, VEC)                                                                              \
   do {                                                                                                         \
-    auto kern = soft_attention_fwd_kernel<KT, FAST, VEC>;                                                      \
-    if (smem > 48 * 1024) MVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, 256, smem, st>>>(T, A, F, chunk, wq, uk, bias, w, (const KT*)keys, keys_batch, k_sb, k_st, mask, \
-                                  m_sb, m_st, ctx_f32, ctx_ld, (__nv_bfloat16*)ctx_bf16, ctxb_ld, alpha);     \
+    auto k2 = soft_attention_fwd_kernel<KT, FAST, VEC>;                                                        \
+    if (smem > 48 * 1024) MVC_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k2<<<grid, 256, smem, st>>>(T, A, F, chunk, a.wq, a.uk, a.bias, a.w, (const KT*)a.keys, a.keys_batch, a.k_sb, a.k_st, \
+                                a.mask, a.m_sb, a.m_st, a.ctx_f32, a.ctx_ld, (__nv_bfloat16*)a.ctx_bf16, a.ctxb_ld, \
+                                a.alpha);                                                                      \
   } while (0)
-  if (keys_bf16) {
-    if (fast_math) { if (vec) LAUNCH_FWD(__nv_bfloat16, true, true); else LAUNCH_FWD(__nv_bfloat16, true, false); }
+  if (a.keys_bf16) {
+    if (a.fast_math) { if (vec) LAUNCH_FWD(__nv_bfloat16, true, true); else LAUNCH_FWD(__nv_bfloat16, true, false); }
     else { if (vec) LAUNCH_FWD(__nv_bfloat16, false, true); else LAUNCH_FWD(__nv_bfloat16, false, false); }
   } else {
-    if (fast_math) { if (vec) LAUNCH_FWD(float, true, true); else LAUNCH_FWD(float, true, false); }
+    if (a.fast_math) { if (vec) LAUNCH_FWD(float, true, true); else LAUNCH_FWD(float, true, false); }
     else { if (vec) LAUNCH_FWD(float, false, true); else LAUNCH_FWD(float, false, false); }
   }
 #undef LAUNCH_FWD
@@ -289,35 +604,89 @@ extern "C" int mvc_soft_attention_fwd(int B, int T, int A, int F, const float* w
   return 0;
 }
 
+__global__ void cast_rows_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+
+int launch_attention_bwd(const AttnBwdArgs& a, bool pdl, cudaStream_t st) {
+  const int B = a.B, T = a.T, A = a.A, F = a.F;
+  if (B == 0) return 0;
+  MVC_CHECK(a.wq && a.uk && a.bias && a.w && a.keys && a.alpha && a.dctx && a.dwq, "mvc_soft_attention_bwd: null argument");
+  const int VN = a.keys_bf16 ? 8 : 4;
+  const size_t es = a.keys_bf16 ? 2 : 4;
+  const bool vec = (F % VN == 0) && (a.k_sb % VN == 0) && (a.k_st % VN == 0) &&
+                   (reinterpret_cast<uintptr_t>(a.keys) % 16 == 0);
+  ProfScope prof(PK_ATTN_BWD, B, T, F, st);
+  const void* kern = nullptr;
+  if (vec && T <= ATT_MAXR_BWD * 16) {
+    if (a.keys_bf16) kern = a.fast_math ? pick_bwd_staged<__nv_bfloat16, true>(A) : pick_bwd_staged<__nv_bfloat16, false>(A);
+    else kern = a.fast_math ? pick_bwd_staged<float, true>(A) : pick_bwd_staged<float, false>(A);
+  }
+  if (kern) {
+    size_t stage = ((size_t)T * F * es + 127) & ~size_t(127);
+    if (stage < sizeof(float) * 16 * 2 * (size_t)A) stage = sizeof(float) * 16 * 2 * (size_t)A;
+    const size_t smem = stage + sizeof(float) * ((size_t)cdiv(F, 32 * VN) * 32 * VN + 2 * (size_t)((T + 3) & ~3) +
+                                                 2 * (size_t)A + 32) + 16;
+    if (smem <= kAttnMaxSmem) {
+      MVC_TRY(ensure_big_smem(kern));
+      AttnBwdArgs args = a;
+      void* params[] = {(void*)&args};
+      MVC_TRY(launch_ex(kern, dim3(B), dim3(512), smem, pdl, params, st));
+      MVC_LAUNCH_CHECK();
+      return 0;
+    }
+  }
+  const size_t smem = sizeof(float) * ((size_t)((F + 3) & ~3) + 2 * (size_t)T + 32);
+  MVC_CHECK(smem <= 200 * 1024, "mvc_soft_attention_bwd: F=%d T=%d needs %zu B of shared memory", F, T, smem);
+#define LAUNCH_BWD(KT, FAST, VEC)                                                                              \
+  do {                                                                                                         \
+    auto k2 = soft_attention_bwd_kernel<KT, FAST, VEC>;                                                        \
+    if (smem > 48 * 1024) MVC_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k2<<<B, 512, smem, st>>>(T, A, F, a.wq, a.uk, a.bias, a.w, (const KT*)a.keys, a.k_sb, a.k_st, a.alpha, a.dctx, \
+                             a.dctx_ld, a.dwq, a.duk, a.dw_partial, a.dkeys, a.dk_sb, a.dk_st);                \
+  } while (0)
+  if (a.keys_bf16) {
+    if (a.fast_math) { if (vec) LAUNCH_BWD(__nv_bfloat16, true, true); else LAUNCH_BWD(__nv_bfloat16, true, false); }
+    else { if (vec) LAUNCH_BWD(__nv_bfloat16, false, true); else LAUNCH_BWD(__nv_bfloat16, false, false); }
+  } else {
+    if (a.fast_math) { if (vec) LAUNCH_BWD(float, true, true); else LAUNCH_BWD(float, true, false); }
+    else { if (vec) LAUNCH_BWD(float, false, true); else LAUNCH_BWD(float, false, false); }
+  }
+#undef LAUNCH_BWD
+  MVC_LAUNCH_CHECK();
+  if (a.dwq_bf16) {
+    const int64_t n = (int64_t)B * A;
+    cast_rows_bf16_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a.dwq, (__nv_bfloat16*)a.dwq_bf16, n);
+    MVC_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace mvc
+
+extern "C" int mvc_soft_attention_fwd(int B, int T, int A, int F, const float* wq, const float* uk, const float* bias,
+                                      const float* w, const void* keys, int keys_bf16, int keys_batch, int64_t k_sb,
+                                      int64_t k_st, const uint8_t* mask, int64_t m_sb, int64_t m_st, float* ctx_f32,
+                                      int64_t ctx_ld, void* ctx_bf16, int64_t ctxb_ld, float* alpha, int fast_math,
+                                      void* stream) {
+  AttnFwdArgs a{};
+  a.B = B; a.T = T; a.A = A; a.F = F; a.wq = wq; a.uk = uk; a.bias = bias; a.w = w;
+  a.keys = keys; a.keys_bf16 = keys_bf16; a.keys_batch = keys_batch; a.k_sb = k_sb; a.k_st = k_st;
+  a.mask = mask; a.m_sb = m_sb; a.m_st = m_st; a.ctx_f32 = ctx_f32; a.ctx_ld = ctx_ld; a.ctx_bf16 = ctx_bf16;
+  a.ctxb_ld = ctxb_ld; a.alpha = alpha; a.fast_math = fast_math;
+  return launch_attention_fwd(a, false, (cudaStream_t)stream);
+}
+
 extern "C" int mvc_soft_attention_bwd(int B, int T, int A, int F, const float* wq, const float* uk, const float* bias,
                                       const float* w, const void* keys, int keys_bf16, int64_t k_sb, int64_t k_st,
                                       const float* alpha, const float* dctx, int64_t dctx_ld, float* dwq, float* duk,
                                       float* dw_partial, float* dkeys, int64_t dk_sb, int64_t dk_st, int fast_math,
                                       void* stream) {
-  if (B == 0) return 0;
-  MVC_CHECK(wq && uk && bias && w && keys && alpha && dctx && dwq, "mvc_soft_attention_bwd: null argument");
-  const int VN = keys_bf16 ? 8 : 4;
-  const bool vec = (F % VN == 0) && (k_sb % VN == 0) && (k_st % VN == 0) &&
-                   (reinterpret_cast<uintptr_t>(keys) % 16 == 0);
-  const size_t smem = sizeof(float) * ((size_t)((F + 3) & ~3) + 2 * (size_t)T + 32);
-  MVC_CHECK(smem <= 200 * 1024, "mvc_soft_attention_bwd: F=%d T=%d needs %zu B of shared memory", F, T, smem);
-  cudaStream_t st = (cudaStream_t)stream;
-  ProfScope prof(PK_ATTN_BWD, B, T, F, st);
-#define LAUNCH_BWD(KT, FAST, VEC)                                                                              \
-  do {                                                                                                         \
-    auto kern = soft_attention_bwd_kernel<KT, FAST, VEC>;                                                      \
-    if (smem > 48 * 1024) MVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<B, 512, smem, st>>>(T, A, F, wq, uk, bias, w, (const KT*)keys, k_sb, k_st, alpha, dctx, dctx_ld, dwq, \
-                               duk, dw_partial, dkeys, dk_sb, dk_st);                                          \
-  } while (0)
-  if (keys_bf16) {
-    if (fast_math) { if (vec) LAUNCH_BWD(__nv_bfloat16, true, true); else LAUNCH_BWD(__nv_bfloat16, true, false); }
-    else { if (vec) LAUNCH_BWD(__nv_bfloat16, false, true); else LAUNCH_BWD(__nv_bfloat16, false, false); }
-  } else {
-    if (fast_math) { if (vec) LAUNCH_BWD(float, true, true); else LAUNCH_BWD(float, true, false); }
-    else { if (vec) LAUNCH_BWD(float, false, true); else LAUNCH_BWD(float, false, false); }
-  }
-#undef LAUNCH_BWD
-  MVC_LAUNCH_CHECK();
-  return 0;
+  AttnBwdArgs a{};
+  a.B = B; a.T = T; a.A = A; a.F = F; a.wq = wq; a.uk = uk; a.bias = bias; a.w = w;
+  a.keys = keys; a.keys_bf16 = keys_bf16; a.k_sb = k_sb; a.k_st = k_st; a.alpha = alpha; a.dctx = dctx; a.dctx_ld = dctx_ld;
+  a.dwq = dwq; a.dwq_bf16 = nullptr; a.duk = duk; a.dw_partial = dw_partial; a.dkeys = dkeys; a.dk_sb = dk_sb; a.dk_st = dk_st;
+  a.fast_math = fast_math;
+  return launch_attention_bwd(a, false, (cudaStream_t)stream);
 }

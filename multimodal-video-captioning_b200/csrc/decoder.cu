@@ -45,6 +45,9 @@ struct DecWs {
   size_t bytes;
 };
 
+// tile-interleaved gate order (fused gate-GEMM + cell epilogue): bf16 path with H a multiple of 32
+static inline int dec_perm(const MvcDecoderDims* d) { return d->precision == MVC_BF16 && d->H % 32 == 0; }
+
 static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
   const int64_t B = d->B, T = d->T, F = d->F, H = d->H, E = d->E, A = d->A, V = d->V, S = d->L - 1;
   const bool bf = d->precision == MVC_BF16;
@@ -77,13 +80,15 @@ static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
 
 // ------------------------------------------------------------------ small kernels
 // out[4H, F+H] = [w_x (4H x F, row pitch wx_ld) | w_hh (4H x H)]
+// row r of the output is gate row gate_unperm(H, r) of the weights when perm (tile-interleaved gate order)
 template <typename OutT>
 __global__ void pack_wcat_kernel(const float* __restrict__ w_x, int64_t wx_ld, const float* __restrict__ w_hh, int F,
-                                 int H, OutT* __restrict__ out) {
+                                 int H, OutT* __restrict__ out, int perm) {
   const int64_t K = F + H, total = (int64_t)4 * H * K;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / K;
-    const int k = (int)(i - r * K);
+    const int64_t ro = i / K;
+    const int k = (int)(i - ro * K);
+    const int64_t r = perm ? gate_unperm(H, (int)ro) : ro;
     const float v = k < F ? w_x[r * wx_ld + k] : w_hh[r * H + (k - F)];
     if constexpr (sizeof(OutT) == 2) out[i] = __float2bfloat16(v);
     else out[i] = v;
@@ -92,18 +97,23 @@ __global__ void pack_wcat_kernel(const float* __restrict__ w_x, int64_t wx_ld, c
 
 // out[r, 0:Cp] = bf16(src[r*lds + 0:C]) zero padded
 __global__ void cast_pad_bf16_kernel(const float* __restrict__ src, int64_t rows, int C, int64_t lds, int Cp,
-                                     __nv_bfloat16* __restrict__ out) {
+                                     __nv_bfloat16* __restrict__ out, int permH) {
   const int64_t total = rows * Cp;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / Cp;
-    const int c = (int)(i - r * Cp);
+    const int64_t ro = i / Cp;
+    const int c = (int)(i - ro * Cp);
+    const int64_t r = permH ? gate_unperm(permH, (int)ro) : ro;
     out[i] = __float2bfloat16(c < C ? src[r * lds + c] : 0.f);
   }
 }
 
-__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n) {
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n,
+                               int permH) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) o[i] = a[i] + b[i];
+  if (i < n) {
+    const int j = permH ? gate_unperm(permH, i) : i;
+    o[i] = a[j] + b[j];
+  }
 }
 
 __global__ void fill_i64_kernel(int64_t* __restrict__ p, int64_t v, int64_t n) {
@@ -137,21 +147,22 @@ __global__ void iota_i64_kernel(int64_t* __restrict__ p, int64_t n) {
   if (i < n) p[i] = i;
 }
 
-int launch_pack_wcat(const float* w_x, int64_t wx_ld, const float* w_hh, int F, int H, void* out, int out_bf16,
+int launch_pack_wcat(const float* w_x, int64_t wx_ld, const float* w_hh, int F, int H, void* out, int out_bf16, int perm,
                      cudaStream_t st) {
   const int64_t n = (int64_t)4 * H * (F + H);
-  if (out_bf16) pack_wcat_kernel<__nv_bfloat16><<<gridn(n), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H, (__nv_bfloat16*)out);
-  else pack_wcat_kernel<float><<<gridn(n), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H, (float*)out);
+  if (out_bf16) pack_wcat_kernel<__nv_bfloat16><<<gridn(n), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H, (__nv_bfloat16*)out, perm);
+  else pack_wcat_kernel<float><<<gridn(n), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H, (float*)out, perm);
   MVC_LAUNCH_CHECK();
   return 0;
 }
-int launch_cast_pad_bf16(const float* src, int64_t rows, int C, int64_t lds, int Cp, void* out, cudaStream_t st) {
-  cast_pad_bf16_kernel<<<gridn(rows * Cp), 256, 0, st>>>(src, rows, C, lds, Cp, (__nv_bfloat16*)out);
+int launch_cast_pad_bf16(const float* src, int64_t rows, int C, int64_t lds, int Cp, void* out, int permH,
+                         cudaStream_t st) {
+  cast_pad_bf16_kernel<<<gridn(rows * Cp), 256, 0, st>>>(src, rows, C, lds, Cp, (__nv_bfloat16*)out, permH);
   MVC_LAUNCH_CHECK();
   return 0;
 }
-int launch_add_vec(const float* a, const float* b, float* o, int n, cudaStream_t st) {
-  add_vec_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a, b, o, n);
+int launch_add_vec(const float* a, const float* b, float* o, int n, int permH, cudaStream_t st) {
+  add_vec_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a, b, o, n, permH);
   MVC_LAUNCH_CHECK();
   return 0;
 }
@@ -178,16 +189,17 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
   const int B = d->B, T = d->T, F = d->F, H = d->H, E = d->E, A = d->A, V = d->V;
   const bool bf = d->precision == MVC_BF16;
   const int Ep = bf ? pad8(E) : E;
+  const int perm = dec_perm(d);
   MVC_CHECK(Fa + Fv == F, "decoder: Fa (%d) + Fv (%d) != in_feature_size (%d)", Fa, Fv, F);
   MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, bf, st));
-  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, st));
-  MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, bf, st));
+  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, perm ? H : 0, st));
+  MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, bf, perm, st));
   if (bf) {
-    MVC_TRY(launch_cast_pad_bf16(p->w_ih, 4 * H, E, E + F, Ep, w.wie, st));
+    MVC_TRY(launch_cast_pad_bf16(p->w_ih, 4 * H, E, E + F, Ep, w.wie, perm ? H : 0, st));
     MVC_TRY(mvc_cast_bf16(p->att_U, w.U, (int64_t)A * F, st));
     MVC_TRY(mvc_cast_bf16(p->att_W, w.W, (int64_t)A * H, st));
     MVC_TRY(mvc_cast_bf16(p->out_w, w.outw, (int64_t)V * H, st));
-    if (need_embtab) MVC_TRY(launch_cast_pad_bf16(p->embedding, V, E, E, Ep, w.embb, st));
+    if (need_embtab) MVC_TRY(launch_cast_pad_bf16(p->embedding, V, E, E, Ep, w.embb, 0, st));
   }
   // uk = feats . U^T      (temporal_attention.py:21, hoisted)
   MVC_TRY(gemm_nt(d->precision, B * T, A, F, w.feats, F, bf ? w.U : (const void*)p->att_U, F, 0.f, w.uk, A, nullptr, st));
@@ -204,6 +216,7 @@ static StepCfg dec_cfg(const MvcDecoderDims* d, const MvcDecoderParams* p, const
   StepCfg c{};
   c.prec = d->precision;
   c.T = d->T; c.F = d->F; c.H = d->H; c.A = d->A;
+  c.perm = dec_perm(d);
   c.uk = w.uk;
   c.keys = w.feats; c.keys_batch = d->B; c.k_sb = (int64_t)d->T * d->F; c.k_st = d->F;
   c.mask = nullptr; c.m_sb = 0; c.m_st = 0;                 // decoder attention is unmasked
@@ -220,6 +233,28 @@ static StepCfg dec_cfg(const MvcDecoderDims* d, const MvcDecoderParams* p, const
 }  // namespace mvc
 
 using namespace mvc;
+
+extern "C" int mvc_pack_gate_rows_bf16(const float* w, int H, int C, int64_t ldw, int Cp, void* out, void* stream) {
+  MVC_CHECK(w && out && H > 0 && H % 32 == 0 && C > 0 && Cp >= C && Cp % 8 == 0,
+            "mvc_pack_gate_rows_bf16: need H %% 32 == 0 and Cp %% 8 == 0 (H=%d C=%d Cp=%d)", H, C, Cp);
+  return launch_cast_pad_bf16(w, 4 * (int64_t)H, C, ldw, Cp, out, H, (cudaStream_t)stream);
+}
+
+extern "C" int mvc_lstm_gates_cell_bf16(int B, int H, int K, const void* x, int64_t ldx, const void* w_packed, int64_t ldw,
+                                        const float* bias_packed, const float* gx_packed, int64_t gx_ld,
+                                        const float* c_prev, float* act_packed, float* c_out, float* h_out, int64_t h_ld,
+                                        void* h_bf16, int64_t hb_ld, void* stream) {
+  MVC_CHECK(x && w_packed && c_out && H % 32 == 0, "mvc_lstm_gates_cell_bf16: bad arguments (H=%d)", H);
+  TcEpilogue ep{};
+  ep.mode = TC_MODE_CELL;
+  ep.H = H;
+  ep.bias = bias_packed;
+  ep.gx = gx_packed; ep.gx_ld = gx_ld;
+  ep.c_prev = c_prev; ep.act = act_packed; ep.c_out = c_out;
+  ep.h32 = h_out; ep.h_ld = h_ld;
+  ep.hb = (__nv_bfloat16*)h_bf16; ep.hb_ld = hb_ld;
+  return tc_gemm(B, 4 * H, K, x, ldx, w_packed, ldw, ep, 0, (cudaStream_t)stream);
+}
 
 extern "C" size_t mvc_decoder_fwd_workspace_bytes(const MvcDecoderDims* d, int) { return dec_layout(d, nullptr).bytes; }
 
@@ -344,6 +379,8 @@ struct DecBwdWs {
   void* dukT;       // [A, BTp]
   void* featsT;     // [F, BTp]
   void* dwqT;       // [A, SBp]
+  void* dwq_b;      // [S*B, A]
+  void* attWT;      // [H, A]
   size_t bytes;
 };
 
@@ -377,6 +414,8 @@ static DecBwdWs dec_bwd_layout(const MvcDecoderDims* d, void* base) {
     w.dukT = ar.take<char>(A * BTp * 2);
     w.featsT = ar.take<char>(F * BTp * 2);
     w.dwqT = ar.take<char>(A * SBp * 2);
+    w.dwq_b = ar.take<char>(S * B * A * 2);
+    w.attWT = ar.take<char>(H * A * 2);
   }
   w.bytes = ar.off + 256;
   return w;
@@ -440,9 +479,14 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   MVC_CUDA(cudaMemsetAsync(q.dc, 0, sizeof(float) * (size_t)B * H, st));
   MVC_CUDA(cudaMemsetAsync(q.duk, 0, sizeof(float) * (size_t)B * T * A, st));
   MVC_CUDA(cudaMemsetAsync(q.dwpart, 0, sizeof(float) * (size_t)B * A, st));
-  if (bf) MVC_TRY(mvc_transpose_to_bf16(w.wcat, 1, 4 * H, F + H, ldx, q.wcatT, 4 * H, st));
+  if (bf) {
+    MVC_TRY(mvc_transpose_to_bf16(w.wcat, 1, 4 * H, F + H, ldx, q.wcatT, 4 * H, st));
+    MVC_TRY(mvc_transpose_to_bf16(w.W, 1, A, H, H, q.attWT, A, st));
+  }
   StepCfg cfg = dec_cfg(d, p, w, nullptr);
   cfg.wcatT = q.wcatT;
+  cfg.attWT = q.attWT;
+  const int permH = cfg.perm ? H : 0;
   for (int s = S - 1; s >= 0; --s) {
     StepBwd io{};
     io.rows = B;
@@ -459,6 +503,7 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     io.wq = w.wq + (int64_t)s * B * A;
     io.alpha = w.alpha + (int64_t)s * B * T;
     io.dwq = q.dwq + (int64_t)s * B * A;
+    io.dwq_b = bf ? mptr(q.dwq_b, (int64_t)s * B * A, 2) : nullptr;
     io.duk = q.duk;
     io.dwpart = q.dwpart;
     io.dkeys = nullptr;                           // features are inputs: no gradient
@@ -471,7 +516,7 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   MVC_TRY(mvc_colsum(q.dwq, SB, A, A, g->att_b, st));
   MVC_TRY(mvc_colsum(q.dwpart, B, A, A, g->att_w, st));
   // LSTM biases
-  MVC_TRY(mvc_colsum(q.dG, SB, 4 * H, 4 * H, g->b_ih, st));
+  MVC_TRY(launch_colsum(q.dG, SB, 4 * H, 4 * H, g->b_ih, permH, st));
   MVC_CUDA(cudaMemcpyAsync(g->b_hh, g->b_ih, sizeof(float) * 4 * (size_t)H, cudaMemcpyDeviceToDevice, st));
   MVC_CUDA(cudaMemsetAsync(g->embedding, 0, sizeof(float) * (size_t)V * E, st));
   if (!bf) {
@@ -487,9 +532,9 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     MVC_TRY(mvc_gemm_f32(SB, E, 4 * H, 1.f, q.dG, 4 * H, 1, p->w_ih, 1, E + F, 0.f, q.dxemb, E, nullptr, st));
   } else {
     // transposed bf16 operands (tcgen05 GEMM takes K-contiguous A[M,K], B[N,K])
-    MVC_TRY(mvc_transpose_to_bf16(q.dG_b, 1, SB, 4 * H, 4 * H, q.dGT, SBp, st));
+    MVC_TRY(launch_transpose_bf16(q.dG_b, 1, SB, 4 * H, 4 * H, q.dGT, SBp, permH, st));   // natural gate rows
     MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, st));
-    MVC_TRY(mvc_transpose_to_bf16(q.dwq, 0, SB, A, A, q.dwqT, SBp, st));
+    MVC_TRY(mvc_transpose_to_bf16(q.dwq_b, 1, SB, A, A, q.dwqT, SBp, st));
     MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * T, A, A, q.dukT, BTp, st));
     MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
     const char* hprevT = cptr(q.xhT, (int64_t)F * SBp, 2);

@@ -6,7 +6,7 @@
 #include <utility>
 #include <vector>
 
-#include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace mvc {
 
@@ -57,7 +57,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 
 template <typename ST>
 __global__ void transpose_bf16_kernel(const ST* __restrict__ src, int64_t R, int64_t C, int64_t lds,
-                                      __nv_bfloat16* __restrict__ dst, int64_t ldd) {
+                                      __nv_bfloat16* __restrict__ dst, int64_t ldd, int permH) {
   __shared__ __nv_bfloat16 tile[32][33];
   const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -67,7 +67,7 @@ __global__ void transpose_bf16_kernel(const ST* __restrict__ src, int64_t R, int
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int64_t c = c0 + i, r = r0 + threadIdx.x;
-    if (c < C && r < R) dst[c * ldd + r] = tile[threadIdx.x][i];
+    if (c < C && r < R) dst[(permH ? (int64_t)gate_unperm(permH, (int)c) : c) * ldd + r] = tile[threadIdx.x][i];
   }
 }
 
@@ -110,12 +110,14 @@ __global__ void lstm_cell_fwd_kernel(int B, int H, const float* __restrict__ pre
 __global__ void lstm_cell_bwd_kernel(int B, int H, const float* __restrict__ act, const float* __restrict__ c_prev,
                                      const float* __restrict__ c_new, const float* __restrict__ dh_a, int64_t dha_ld,
                                      const float* __restrict__ dh_b, int64_t dhb_ld, float* __restrict__ dc,
-                                     float* __restrict__ dgates, __nv_bfloat16* __restrict__ dg_bf16) {
+                                     float* __restrict__ dgates, __nv_bfloat16* __restrict__ dg_bf16, int perm) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * H) return;
   const int b = (int)(i / H), j = (int)(i - (int64_t)b * H);
   const float* a = act + (int64_t)b * 4 * H;
-  const float ig = a[j], fg = a[H + j], gg = a[2 * H + j], og = a[3 * H + j];
+  const int ci = gate_col(perm, H, 0, j), cf = gate_col(perm, H, 1, j), cg = gate_col(perm, H, 2, j),
+            co = gate_col(perm, H, 3, j);
+  const float ig = a[ci], fg = a[cf], gg = a[cg], og = a[co];
   float dh = 0.f;
   if (dh_a) dh += dh_a[b * dha_ld + j];
   if (dh_b) dh += dh_b[b * dhb_ld + j];
@@ -128,11 +130,11 @@ __global__ void lstm_cell_bwd_kernel(int B, int H, const float* __restrict__ act
   const float d_o = dh * tc * og * (1.f - og);
   dc[i] = dct * fg;
   float* d = dgates + (int64_t)b * 4 * H;
-  d[j] = d_i; d[H + j] = d_f; d[2 * H + j] = d_g; d[3 * H + j] = d_o;
+  d[ci] = d_i; d[cf] = d_f; d[cg] = d_g; d[co] = d_o;
   if (dg_bf16) {
     __nv_bfloat16* q = dg_bf16 + (int64_t)b * 4 * H;
-    q[j] = __float2bfloat16(d_i); q[H + j] = __float2bfloat16(d_f);
-    q[2 * H + j] = __float2bfloat16(d_g); q[3 * H + j] = __float2bfloat16(d_o);
+    q[ci] = __float2bfloat16(d_i); q[cf] = __float2bfloat16(d_f);
+    q[cg] = __float2bfloat16(d_g); q[co] = __float2bfloat16(d_o);
   }
 }
 
@@ -249,7 +251,8 @@ __global__ void embedding_scatter_add_kernel(const float* __restrict__ dx, int64
 }
 
 // out[n] = sum_r x[r,n]: one thread per column, fixed ascending-r order (deterministic).
-__global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int N, int64_t ld, float* __restrict__ out) {
+__global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int N, int64_t ld, float* __restrict__ out,
+                              int permH) {
   // blockDim = (32, 8): 32 columns per CTA, 8 row-lanes reduced through shared memory.
   __shared__ float part[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
@@ -262,7 +265,7 @@ __global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int N, 
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
-    out[n] = t;
+    out[permH ? gate_unperm(permH, n) : n] = t;
   }
 }
 
@@ -349,18 +352,42 @@ extern "C" int mvc_cast_bf16(const float* src, void* dst, int64_t n, void* strea
   return 0;
 }
 
-extern "C" int mvc_transpose_to_bf16(const void* src, int src_bf16, int64_t R, int64_t C, int64_t lds, void* dst,
-                                     int64_t ldd, void* stream) {
+namespace mvc {
+int launch_transpose_bf16(const void* src, int src_bf16, int64_t R, int64_t C, int64_t lds, void* dst, int64_t ldd,
+                          int permH, cudaStream_t st) {
   if (R == 0 || C == 0) return 0;
   dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(R, 32)), block(32, 8);
   if (src_bf16)
-    transpose_bf16_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, R, C, lds,
-                                                                                  (__nv_bfloat16*)dst, ldd);
+    transpose_bf16_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)src, R, C, lds, (__nv_bfloat16*)dst,
+                                                                ldd, permH);
   else
-    transpose_bf16_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, R, C, lds,
-                                                                          (__nv_bfloat16*)dst, ldd);
+    transpose_bf16_kernel<float><<<grid, block, 0, st>>>((const float*)src, R, C, lds, (__nv_bfloat16*)dst, ldd, permH);
   MVC_LAUNCH_CHECK();
   return 0;
+}
+int launch_cell_bwd(int B, int H, const float* act, const float* c_prev, const float* c_new, const float* dh_a,
+                    int64_t dha_ld, const float* dh_b, int64_t dhb_ld, float* dc, float* dgates, void* dg_bf16, int perm,
+                    cudaStream_t st) {
+  const int64_t n = (int64_t)B * H;
+  if (n == 0) return 0;
+  ProfScope prof(PK_CELL_BWD, B, H, 0, st);
+  lstm_cell_bwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(B, H, act, c_prev, c_new, dh_a, dha_ld, dh_b, dhb_ld, dc,
+                                                              dgates, (__nv_bfloat16*)dg_bf16, perm);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_colsum(const float* x, int64_t rows, int N, int64_t ld, float* out, int permH, cudaStream_t st) {
+  if (N == 0) return 0;
+  dim3 block(32, 8);
+  colsum_kernel<<<(unsigned)cdiv(N, 32), block, 0, st>>>(x, rows, N, ld, out, permH);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace mvc
+
+extern "C" int mvc_transpose_to_bf16(const void* src, int src_bf16, int64_t R, int64_t C, int64_t lds, void* dst,
+                                     int64_t ldd, void* stream) {
+  return launch_transpose_bf16(src, src_bf16, R, C, lds, dst, ldd, 0, (cudaStream_t)stream);
 }
 
 extern "C" int mvc_lstm_cell_fwd(int B, int H, const float* pre, const float* gx, int64_t gx_ld,
@@ -383,13 +410,8 @@ extern "C" int mvc_lstm_cell_bwd(int B, int H, const float* act, const float* c_
                                  const float* dh_a, int64_t dha_ld, const float* dh_b, int64_t dhb_ld, float* dc,
                                  float* dgates, void* dg_bf16, void* stream) {
   MVC_CHECK(act && c_new && dc && dgates, "mvc_lstm_cell_bwd: null argument");
-  const int64_t n = (int64_t)B * H;
-  if (n == 0) return 0;
-  ProfScope prof(PK_CELL_BWD, B, H, 0, (cudaStream_t)stream);
-  lstm_cell_bwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      B, H, act, c_prev, c_new, dh_a, dha_ld, dh_b, dhb_ld, dc, dgates, (__nv_bfloat16*)dg_bf16);
-  MVC_LAUNCH_CHECK();
-  return 0;
+  return launch_cell_bwd(B, H, act, c_prev, c_new, dh_a, dha_ld, dh_b, dhb_ld, dc, dgates, dg_bf16, 0,
+                         (cudaStream_t)stream);
 }
 
 extern "C" int mvc_log_softmax_rows(float* x, int64_t rows, int V, int64_t* argmax, void* stream) {
@@ -442,11 +464,7 @@ extern "C" int mvc_embedding_scatter_add(const float* dx, int64_t dx_ld, int E, 
 }
 
 extern "C" int mvc_colsum(const float* x, int64_t rows, int N, int64_t ld, float* out, void* stream) {
-  if (N == 0) return 0;
-  dim3 block(32, 8);
-  colsum_kernel<<<(unsigned)cdiv(N, 32), block, 0, (cudaStream_t)stream>>>(x, rows, N, ld, out);
-  MVC_LAUNCH_CHECK();
-  return 0;
+  return launch_colsum(x, rows, N, ld, out, 0, (cudaStream_t)stream);
 }
 
 extern "C" int mvc_caption_mask(const int64_t* captions, int64_t n, uint8_t* mask, void* stream) {

@@ -1,101 +1,52 @@
-// gemm_tc.cu -- bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (sm_100a).
+// gemm_tc.cu -- bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (sm_100a), with
+// deterministic split-K and an optional fused LSTM-cell epilogue.
 //
 //   C[M,N] = sum_k A[m,k] * B[n,k]  (+ beta*C) (+ bias[n])
 //
-// A [M,K] and B [N,K] are bf16, K-contiguous (the layout every nn.Linear /
-// nn.LSTM weight of the reference already has: weight[out,in], and the layout
-// of every activation matrix [rows, features]).  This is the tensor-core form
-// of the LSTM gate contraction (features_captioning.py:84), the attention
-// projections (temporal_attention.py:20-21), the vocabulary projection
-// (features_captioning.py:87) and all their backward GEMMs.
+// A [M,K] and B [N,K] are bf16, K-contiguous (the layout every nn.Linear / nn.LSTM weight of
+// the reference already has: weight[out,in], and the layout of every activation matrix
+// [rows, features]).  This is the tensor-core form of the LSTM gate contraction
+// (features_captioning.py:84), the attention projections (temporal_attention.py:20-21), the
+// vocabulary projection (features_captioning.py:87) and all their backward GEMMs.
 //
-// Kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d tiles of A (128x64) and
-//               B (BNx64) into a STAGES-deep shared-memory ring, 128B swizzle,
-//               completion on mbarriers (expect_tx);
-//   warp 1      allocates TMEM, then one lane issues tcgen05.mma
-//               (cta_group::1, kind::f16, M=128, N=BN, K=16) four times per
-//               stage, accumulating in TMEM; tcgen05.commit releases the stage
-//               back to the producer and finally signals the epilogue;
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, add
-//               bias / beta*C, store fp32 (and optionally bf16) to global.
+// Kernel anatomy (one 128 x BN output tile x one K-range per CTA, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d tiles of A (128x64) and B (BNx64) into a
+//               STAGES-deep shared-memory ring, 128B swizzle, completion on mbarriers (expect_tx);
+//   warp 1      allocates TMEM, then one lane issues tcgen05.mma (cta_group::1, kind::f16,
+//               M=128, N=BN, K=16) four times per stage, accumulating in TMEM; tcgen05.commit
+//               releases the stage back to the producer and finally signals the epilogue;
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time.
 // Out-of-range rows / K tails are zero-filled by TMA; stores are predicated.
+//
+// Split-K (the recurrence GEMMs have M = batch = one row tile, so N tiles alone cannot fill
+// 148 SMs): blockIdx.z owns a contiguous range of 64-wide K blocks.  Every split writes its fp32
+// partial tile to a workspace, takes a ticket on the tile's counter, and the LAST CTA to arrive
+// sums the partials in split order 0..S-1 (its own straight from TMEM) -- so the result does not
+// depend on arrival order -- and runs the epilogue.
+//
+// Epilogues:
+//   plain : + bias, + beta*C, fp32 store, optional bf16 copy;
+//   cell  : BN = 128 and the weight rows are permuted so that one tile holds gates i,f,g,o of 32
+//           hidden units (col = (j/32)*128 + gate*32 + j%32): the epilogue adds the hoisted input
+//           projection / embedding-table row / bias, applies sigmoid/tanh, updates c and h and
+//           writes h in fp32 and bf16 -- the LSTM step never materialises pre-activations.
+//
+// Programmatic dependent launch: when launched with the PDL attribute the producer prefetches
+// the loop-invariant operand B (weights) before griddepcontrol.wait, so the weight traffic of
+// step s+1 overlaps the tail of the kernel that produces its activations.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
 
-#include "common.cuh"
+#include "ptx.cuh"
+#include "tc_gemm.cuh"
 
 namespace mvc {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;   // 64 bf16 = 128 bytes = one swizzle-128B row
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mvc gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 128 B, 8-row
 // swizzle atoms 1024 B apart (SBO), LBO unused (=1), descriptor version 1 (sm_100).
@@ -123,11 +74,12 @@ struct TcSmem {
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
 };
 
-template <int BN, int STAGES>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
-                    int K, float beta, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
-                    __nv_bfloat16* __restrict__ Cb, int64_t ldcb) {
+                    int K, const __grid_constant__ TcEpilogue ep) {
   using S = TcSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -137,10 +89,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR_OFF + 8 * (2 * STAGES + 1));
+  uint32_t* ticket_slot = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int nkb = (K + TC_BK - 1) / TC_BK;
+  const int nkb_all = (K + TC_BK - 1) / TC_BK;
+  const int splits = gridDim.z, z = blockIdx.z;
+  const int kb0 = (int)((long long)nkb_all * z / splits), kb1 = (int)((long long)nkb_all * (z + 1) / splits);
+  const int nkb = kb1 - kb0;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 
   if (warp == 0 && lane == 0) {
@@ -163,23 +119,34 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();     // every CTA of this grid is resident by the time the dependent grid may start
 
   if (warp == 0) {
     if (lane == 0) {
+      // B (weights) does not depend on the preceding kernel: fill the ring's B halves before the
+      // grid dependency resolves, then stream A.
+      const int pre = ep.b_const ? (nkb < STAGES ? nkb : STAGES) : 0;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(full_bar(kb), S::STAGE_BYTES);
+        tma_load_2d(smem_base + kb * S::STAGE_BYTES + S::A_BYTES, &map_b, full_bar(kb), (kb0 + kb) * TC_BK, n0);
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
         const uint32_t a_dst = smem_base + stage * S::STAGE_BYTES;
-        tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TC_BK, m0);
-        tma_load_2d(a_dst + S::A_BYTES, &map_b, full_bar(stage), kb * TC_BK, n0);
+        if (kb >= pre) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
+          tma_load_2d(a_dst + S::A_BYTES, &map_b, full_bar(stage), (kb0 + kb) * TC_BK, n0);
+        }
+        tma_load_2d(a_dst, &map_a, full_bar(stage), (kb0 + kb) * TC_BK, m0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && nkb > 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -205,51 +172,162 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int64_t gm = (int64_t)m0 + row;
+    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    pdl_wait();                                   // C / partials / cell state may still be in use upstream
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    bool last = true;
+    if (splits > 1) {
+      // partial tile, transposed ([col][row]) so that a warp's stores are contiguous
+      float* mine = ep.ws + ((size_t)tile_id * splits + z) * (size_t)(BN * TC_BM);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      if (gm < M) {
-        const int gn0 = n0 + c * 32;
-        float* crow = C ? C + gm * ldc : nullptr;
-        __nv_bfloat16* brow = Cb ? Cb + gm * ldcb : nullptr;
-        const bool vec_ok = crow && (gn0 + 31 < N) && ((reinterpret_cast<uintptr_t>(crow + gn0) & 15u) == 0);
-        if (vec_ok) {
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(trow + (uint32_t)(c * 32), v);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
-            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
-            if (bias) {
-              o.x += bias[gn0 + j]; o.y += bias[gn0 + j + 1]; o.z += bias[gn0 + j + 2]; o.w += bias[gn0 + j + 3];
-            }
-            float4* dst = reinterpret_cast<float4*>(crow + gn0 + j);
-            if (beta != 0.f) {
-              const float4 old = *dst;
-              o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
-            }
-            *dst = o;
-            if (brow) {
-              brow[gn0 + j] = __float2bfloat16(o.x); brow[gn0 + j + 1] = __float2bfloat16(o.y);
-              brow[gn0 + j + 2] = __float2bfloat16(o.z); brow[gn0 + j + 3] = __float2bfloat16(o.w);
-            }
-          }
+        for (int j = 0; j < 32; ++j) __stcg(mine + (c * 32 + j) * TC_BM + row, __uint_as_float(v[j]));
+      }
+      __threadfence();
+      epi_bar_sync();
+      if (row == 0) *ticket_slot = atomicAdd(ep.counters + tile_id, 1u);
+      epi_bar_sync();
+      last = (*ticket_slot == (uint32_t)(splits - 1));
+      if (last) __threadfence();
+    }
+    if (last) {
+      const float* part = ep.ws + (size_t)tile_id * splits * (size_t)(BN * TC_BM);
+      // sum of the S partials of chunk c in split order (own partial straight from TMEM)
+      auto chunk_sum = [&](int c, float* o) {
+        uint32_t v[32];
+        tmem_ld32(trow + (uint32_t)(c * 32), v);
+        if (splits == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
         } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = 0.f;
 #pragma unroll 1
-          for (int j = 0; j < 32; ++j) {
-            const int gn = gn0 + j;
-            if (gn >= N) break;
-            float o = __uint_as_float(v[j]);
-            if (bias) o += bias[gn];
-            if (crow) {
-              if (beta != 0.f) o += beta * crow[gn];
-              crow[gn] = o;
+          for (int s = 0; s < splits; ++s) {
+            if (s == z) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] += __uint_as_float(v[j]);
+            } else {
+              const float* p = part + (size_t)s * (BN * TC_BM) + (size_t)(c * 32) * TC_BM + row;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] += __ldcg(p + j * TC_BM);
             }
-            if (brow) brow[gn] = __float2bfloat16(o);
           }
         }
+      };
+      if constexpr (MODE == TC_MODE_PLAIN) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float o[32];
+          chunk_sum(c, o);
+          if (gm < M) {
+            const int gn0 = n0 + c * 32;
+            float* crow = ep.C ? ep.C + gm * ep.ldc : nullptr;
+            __nv_bfloat16* brow = ep.Cb ? ep.Cb + gm * ep.ldcb : nullptr;
+            const bool vec_ok = crow && (gn0 + 31 < N) && ((reinterpret_cast<uintptr_t>(crow + gn0) & 15u) == 0);
+            if (vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 r = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                if (ep.bias) {
+                  r.x += ep.bias[gn0 + j]; r.y += ep.bias[gn0 + j + 1]; r.z += ep.bias[gn0 + j + 2]; r.w += ep.bias[gn0 + j + 3];
+                }
+                float4* dst = reinterpret_cast<float4*>(crow + gn0 + j);
+                if (ep.beta != 0.f) {
+                  const float4 old = *dst;
+                  r.x += ep.beta * old.x; r.y += ep.beta * old.y; r.z += ep.beta * old.z; r.w += ep.beta * old.w;
+                }
+                *dst = r;
+                if (brow) {
+                  brow[gn0 + j] = __float2bfloat16(r.x); brow[gn0 + j + 1] = __float2bfloat16(r.y);
+                  brow[gn0 + j + 2] = __float2bfloat16(r.z); brow[gn0 + j + 3] = __float2bfloat16(r.w);
+                }
+              }
+            } else {
+#pragma unroll 1
+              for (int j = 0; j < 32; ++j) {
+                const int gn = gn0 + j;
+                if (gn >= N) break;
+                float r = o[j];
+                if (ep.bias) r += ep.bias[gn];
+                if (crow) {
+                  if (ep.beta != 0.f) r += ep.beta * crow[gn];
+                  crow[gn] = r;
+                }
+                if (brow) brow[gn] = __float2bfloat16(r);
+              }
+            }
+          }
+        }
+      } else {
+        // fused LSTM cell: this tile = gates (i,f,g,o) x 32 hidden units [u0, u0+32) of row gm
+        static_assert(MODE != TC_MODE_CELL || BN == 128, "cell epilogue needs a 128-wide tile");
+        float g4[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) chunk_sum(c, g4[c]);
+        if (gm < M) {
+          const int H = ep.H, u0 = blockIdx.x * 32;
+          const float* gxr = ep.gx ? ep.gx + gm * ep.gx_ld + n0 : nullptr;
+          const float* etr = ep.embtab ? ep.embtab + ep.tokens[gm] * (int64_t)(4 * H) + n0 : nullptr;
+          const float* br = ep.bias ? ep.bias + n0 : nullptr;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (gxr) { const float4 t = *reinterpret_cast<const float4*>(gxr + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+              if (etr) { const float4 t = *reinterpret_cast<const float4*>(etr + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+              if (br) { const float4 t = *reinterpret_cast<const float4*>(br + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+              g4[c][j] += a.x; g4[c][j + 1] += a.y; g4[c][j + 2] += a.z; g4[c][j + 3] += a.w;
+            }
+          }
+          const float* cp = ep.c_prev ? ep.c_prev + gm * H + u0 : nullptr;
+          float* co = ep.c_out + gm * H + u0;
+          float* actr = ep.act ? ep.act + gm * (int64_t)(4 * H) + n0 : nullptr;
+          float* h1 = ep.h32 ? ep.h32 + gm * ep.h_ld + u0 : nullptr;
+          float* h2 = ep.h32b ? ep.h32b + gm * ep.h2_ld + u0 : nullptr;
+          __nv_bfloat16* hb = ep.hb ? ep.hb + gm * ep.hb_ld + u0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 cprev = cp ? *reinterpret_cast<const float4*>(cp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float cpv[4] = {cprev.x, cprev.y, cprev.z, cprev.w};
+            float cn[4], hn[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float ig = sigmoid_f(g4[0][j + e]), fg = sigmoid_f(g4[1][j + e]);
+              const float gg = tanhf(g4[2][j + e]), og = sigmoid_f(g4[3][j + e]);
+              g4[0][j + e] = ig; g4[1][j + e] = fg; g4[2][j + e] = gg; g4[3][j + e] = og;
+              cn[e] = fg * cpv[e] + ig * gg;
+              hn[e] = og * tanhf(cn[e]);
+            }
+            *reinterpret_cast<float4*>(co + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            if (h1) *reinterpret_cast<float4*>(h1 + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            if (h2) *reinterpret_cast<float4*>(h2 + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            if (hb) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(hn[0], hn[1]), p1 = __floats2bfloat162_rn(hn[2], hn[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&p0);
+              pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              *reinterpret_cast<uint2*>(hb + j) = pk;
+            }
+          }
+          if (actr) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(actr + c * 32 + j) = make_float4(g4[c][j], g4[c][j + 1], g4[c][j + 2], g4[c][j + 3]);
+          }
+        }
+      }
+      if (splits > 1) {
+        epi_bar_sync();
+        if (row == 0) ep.counters[tile_id] = 0u;   // ready for the next launch on this stream
       }
     }
     tc_fence_before();
@@ -328,24 +406,113 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
   return 0;
 }
 
-template <int BN, int STAGES>
-static int launch_tc(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, float beta, float* C,
-                     int64_t ldc, const float* bias, void* Cb, int64_t ldcb, cudaStream_t st) {
+// ------------------------------------------------------------------ host: split-K scratch (per device x stream)
+constexpr size_t kSplitWsBytes = 48u << 20;
+constexpr int kSplitCounters = 4096;
+struct SplitScratch {
+  float* ws;
+  unsigned* counters;
+};
+static int get_split_scratch(cudaStream_t st, SplitScratch* out) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, SplitScratch> pool;
+  int dev = 0;
+  MVC_CUDA(cudaGetDevice(&dev));
+  const uint64_t key = (reinterpret_cast<uint64_t>(st) << 8) ^ (uint64_t)dev;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = pool.find(key);
+  if (it == pool.end()) {
+    SplitScratch s{};
+    MVC_CUDA(cudaMalloc(&s.ws, kSplitWsBytes));
+    MVC_CUDA(cudaMalloc(&s.counters, sizeof(unsigned) * kSplitCounters));
+    MVC_CUDA(cudaMemset(s.counters, 0, sizeof(unsigned) * kSplitCounters));
+    it = pool.emplace(key, s).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
+template <int BN, int STAGES, int MODE>
+static int launch_tc(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, TcEpilogue ep,
+                     int splits, bool pdl, cudaStream_t st) {
   CUtensorMap ma, mb;
   MVC_TRY(get_tensor_map(A, M, K, lda, TC_BM, &ma));
   MVC_TRY(get_tensor_map(B, N, K, ldb, BN, &mb));
-  auto kern = gemm_bf16_tc_kernel<BN, STAGES>;
+  auto kern = gemm_bf16_tc_kernel<BN, STAGES, MODE>;
   constexpr int smem = TcSmem<BN, STAGES>::TOTAL;
   static bool configured = false;
   if (!configured) {
     MVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(M, TC_BM));
+  const dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(M, TC_BM), (unsigned)splits);
+  if (splits > 1) {
+    SplitScratch sc;
+    MVC_TRY(get_split_scratch(st, &sc));
+    const size_t need = (size_t)grid.x * grid.y * splits * BN * TC_BM * sizeof(float);
+    MVC_CHECK(need <= kSplitWsBytes && (size_t)grid.x * grid.y <= (size_t)kSplitCounters,
+              "tcgen05 GEMM split-K scratch too small for %dx%dx%d", M, N, K);
+    ep.ws = sc.ws;
+    ep.counters = sc.counters;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   ProfScope prof(PK_GEMM_TC, M, N, K, st);
-  kern<<<grid, 192, smem, st>>>(ma, mb, M, N, K, beta, C, ldc, bias, (__nv_bfloat16*)Cb, ldcb);
+  MVC_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, ep));
   MVC_LAUNCH_CHECK();
   return 0;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MVC_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const TcEpilogue& ep_in,
+            int flags, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  TcEpilogue ep = ep_in;
+  MVC_CHECK(A && B, "tcgen05 GEMM: null operand");
+  MVC_CHECK(K > 0, "tcgen05 GEMM: K must be positive");
+  MVC_CHECK(lda % 8 == 0 && ldb % 8 == 0, "tcgen05 GEMM: lda (%lld) / ldb (%lld) must be multiples of 8",
+            (long long)lda, (long long)ldb);
+  MVC_CHECK((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(B) & 15u) == 0,
+            "tcgen05 GEMM: operands must be 16-byte aligned");
+  const bool pdl = (flags & TC_FLAG_PDL) && pdl_enabled();
+  ep.b_const = (flags & TC_FLAG_B_CONST) ? 1 : 0;
+  const int64_t mt = cdiv(M, TC_BM);
+  const int nkb = (int)cdiv(K, TC_BK);
+  const bool can_split = !(flags & TC_FLAG_NO_SPLIT);
+  auto splits_for = [&](int64_t tiles) {
+    if (!can_split || tiles >= 112) return 1;
+    int s = (int)(kNumSMs / tiles);
+    if (s > 8) s = 8;
+    if (s > nkb) s = nkb;
+    return s < 1 ? 1 : s;
+  };
+  if (ep.mode == TC_MODE_CELL) {
+    MVC_CHECK(N % 128 == 0 && N == 4 * ep.H, "fused LSTM-cell epilogue needs N == 4H with H %% 32 == 0 (N=%d H=%d)", N, ep.H);
+    const int s = splits_for(mt * (N / 128));
+    return launch_tc<128, 4, TC_MODE_CELL>(M, N, K, A, lda, B, ldb, ep, s, pdl, st);
+  }
+  const int64_t t128 = mt * cdiv(N, 128), t64 = mt * cdiv(N, 64), t32 = mt * cdiv(N, 32);
+  // widest tile whose CTA count (tiles x K-splits) covers most of the 148 SMs
+  const int s128 = splits_for(t128), s64 = splits_for(t64), s32 = splits_for(t32);
+  if (t128 * s128 >= 96) return launch_tc<128, 4, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s128, pdl, st);
+  if (t64 * s64 >= 96) return launch_tc<64, 6, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s64, pdl, st);
+  return launch_tc<32, 8, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s32, pdl, st);
 }
 
 }  // namespace mvc
@@ -356,14 +523,8 @@ extern "C" int mvc_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, co
                              float* C, int64_t ldc, const float* bias, void* Cb, int64_t ldcb, void* stream) {
   if (M <= 0 || N <= 0) return 0;
   MVC_CHECK(A && B && (C || Cb), "mvc_gemm_bf16: null operand");
-  MVC_CHECK(K > 0, "mvc_gemm_bf16: K must be positive");
-  MVC_CHECK(lda % 8 == 0 && ldb % 8 == 0, "mvc_gemm_bf16: lda (%lld) / ldb (%lld) must be multiples of 8",
-            (long long)lda, (long long)ldb);
-  MVC_CHECK((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(B) & 15u) == 0,
-            "mvc_gemm_bf16: operands must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t mt = cdiv(M, TC_BM);
-  if (mt * cdiv(N, 128) >= kNumSMs) return launch_tc<128, 4>(M, N, K, A, lda, B, ldb, beta, C, ldc, bias, Cb, ldcb, st);
-  if (mt * cdiv(N, 64) >= kNumSMs) return launch_tc<64, 6>(M, N, K, A, lda, B, ldb, beta, C, ldc, bias, Cb, ldcb, st);
-  return launch_tc<32, 8>(M, N, K, A, lda, B, ldb, beta, C, ldc, bias, Cb, ldcb, st);
+  TcEpilogue ep{};
+  ep.mode = TC_MODE_PLAIN;
+  ep.beta = beta; ep.C = C; ep.ldc = ldc; ep.bias = bias; ep.Cb = (__nv_bfloat16*)Cb; ep.ldcb = ldcb;
+  return tc_gemm(M, N, K, A, lda, B, ldb, ep, 0, (cudaStream_t)stream);
 }

@@ -160,6 +160,9 @@ static GlobBwdWs glob_bwd_layout(const MvcReconDims* d, void* base) {
   return w;
 }
 
+// tile-interleaved gate order (fused gate GEMM + cell epilogue): bf16 path, reconstructor hidden % 32 == 0
+static inline int rec_perm(const MvcReconDims* d) { return d->precision == MVC_BF16 && d->Fr % 32 == 0; }
+
 static int check_recon_dims(const MvcReconDims* d, bool local) {
   MVC_CHECK(d, "reconstructor: null dims");
   MVC_CHECK(d->B > 0 && d->L >= 2 && d->H > 0 && d->Fr > 0, "reconstructor: bad dims B=%d L=%d H=%d Fr=%d", d->B, d->L,
@@ -194,14 +197,15 @@ extern "C" int mvc_global_recon_forward(const MvcReconDims* d, const MvcReconPar
 
   masked_mean_kernel<<<(unsigned)cdiv((int64_t)B * H, 256), 256, 0, st>>>(hid, mask, L, B, H, w.pooled);
   MVC_LAUNCH_CHECK();
-  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * Fr, st));
+  const int perm = rec_perm(d), permH = perm ? Fr : 0;
+  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * Fr, permH, st));
   MVC_TRY(launch_iota_i64(w.iota, B, st));
   const float* hid1 = hid + (int64_t)B * H;                       // decoder_hiddens[1:]
   if (bf) {
     MVC_TRY(mvc_cast_bf16(hid1, w.hid_b, (int64_t)S * B * H, st));
     MVC_TRY(mvc_cast_bf16(w.pooled, w.pooled_b, (int64_t)B * H, st));
-    MVC_TRY(mvc_cast_bf16(p->w_ih, w.wih_b, G4 * 2 * H, st));
-    MVC_TRY(mvc_cast_bf16(p->w_hh, w.whh_b, G4 * Fr, st));
+    MVC_TRY(launch_cast_pad_bf16(p->w_ih, G4, 2 * H, 2 * H, 2 * H, w.wih_b, permH, st));
+    MVC_TRY(launch_cast_pad_bf16(p->w_hh, G4, Fr, Fr, Fr, w.whh_b, permH, st));
     MVC_TRY(mvc_gemm_bf16(S * B, 4 * Fr, H, w.hid_b, H, w.wih_b, 2 * H, 0.f, w.gx, G4, nullptr, nullptr, 0, st));
     MVC_TRY(mvc_gemm_bf16(B, 4 * Fr, H, w.pooled_b, H, cptr(w.wih_b, H, 2), 2 * H, 0.f, w.gp, G4, w.bsum, nullptr, 0, st));
   } else {
@@ -213,6 +217,20 @@ extern "C" int mvc_global_recon_forward(const MvcReconDims* d, const MvcReconPar
   MVC_CUDA(cudaMemsetAsync(w.hs, 0, es * (size_t)B * Fr, st));
   for (int s = 0; s < S; ++s) {
     const int t = s + 1;
+    if (perm) {
+      // gates = h_rec_s . W_hh^T + Gx[s] + Gp[b] -> cell, one tcgen05 launch (Gp rides on the row-gather addend)
+      TcEpilogue ep{};
+      ep.mode = TC_MODE_CELL;
+      ep.H = Fr;
+      ep.gx = w.gx + (int64_t)s * B * G4; ep.gx_ld = G4;
+      ep.embtab = w.gp; ep.tokens = w.iota;
+      ep.c_prev = w.c + (int64_t)s * B * Fr; ep.act = w.act + (int64_t)s * B * G4; ep.c_out = w.c + (int64_t)(s + 1) * B * Fr;
+      ep.h32 = rec + (int64_t)t * Fr; ep.h_ld = (int64_t)L * Fr;                                  // feats_recons[t] (:183)
+      ep.hb = (__nv_bfloat16*)mptr(w.hs, (int64_t)(s + 1) * B * Fr, es); ep.hb_ld = Fr;
+      MVC_TRY(tc_gemm(B, 4 * Fr, Fr, cptr(w.hs, (int64_t)s * B * Fr, es), Fr, w.whh_b, Fr, ep,
+                      (s > 0 ? TC_FLAG_PDL : 0) | TC_FLAG_B_CONST, st));
+      continue;
+    }
     if (s == 0) {
       MVC_CUDA(cudaMemsetAsync(w.pre, 0, sizeof(float) * (size_t)B * G4, st));
     } else {
@@ -247,23 +265,24 @@ extern "C" int mvc_global_recon_backward(const MvcReconDims* d, const MvcReconPa
   const int SBp = pad8(SB), Bp = pad8(B);
   const float* hid1 = hid + (int64_t)B * H;
 
+  const int perm = rec_perm(d), permH = perm ? Fr : 0;
   MVC_CUDA(cudaMemsetAsync(q.dc, 0, sizeof(float) * (size_t)B * Fr, st));
   if (bf) MVC_TRY(mvc_transpose_to_bf16(w.whh_b, 1, G4, Fr, Fr, q.whhT, G4, st));
   for (int s = S - 1; s >= 0; --s) {
     const int t = s + 1;
     float* dG = q.dG + (int64_t)s * B * G4;
     void* dGb = bf ? mptr(q.dG_b, (int64_t)s * B * G4, 2) : nullptr;
-    MVC_TRY(mvc_lstm_cell_bwd(B, Fr, w.act + (int64_t)s * B * G4, w.c + (int64_t)s * B * Fr,
-                              w.c + (int64_t)(s + 1) * B * Fr, drec + (int64_t)t * Fr, (int64_t)L * Fr,
-                              s == S - 1 ? nullptr : q.dhcar, Fr, q.dc, dG, dGb, st));
+    MVC_TRY(launch_cell_bwd(B, Fr, w.act + (int64_t)s * B * G4, w.c + (int64_t)s * B * Fr,
+                            w.c + (int64_t)(s + 1) * B * Fr, drec + (int64_t)t * Fr, (int64_t)L * Fr,
+                            s == S - 1 ? nullptr : q.dhcar, Fr, q.dc, dG, dGb, perm, st));
     if (s > 0) {   // dh_rec_s = dgates . W_hh
-      if (bf) MVC_TRY(mvc_gemm_bf16(B, Fr, G4, dGb, G4, q.whhT, G4, 0.f, q.dhcar, Fr, nullptr, nullptr, 0, st));
+      if (bf) MVC_TRY(gemm_tc_chain(B, Fr, G4, dGb, G4, q.whhT, G4, 0.f, q.dhcar, Fr, nullptr, 0, true, st));
       else MVC_TRY(mvc_gemm_f32(B, Fr, G4, 1.f, dG, G4, 1, p->w_hh, 1, Fr, 0.f, q.dhcar, Fr, nullptr, st));
     }
   }
   sum_over_steps_kernel<<<gridn((int64_t)B * G4), 256, 0, st>>>(q.dG, S, (int64_t)B * G4, q.dGsum);
   MVC_LAUNCH_CHECK();
-  MVC_TRY(mvc_colsum(q.dGsum, B, G4, G4, g->b_ih, st));
+  MVC_TRY(launch_colsum(q.dGsum, B, G4, G4, g->b_ih, permH, st));
   MVC_CUDA(cudaMemcpyAsync(g->b_hh, g->b_ih, sizeof(float) * (size_t)G4, cudaMemcpyDeviceToDevice, st));
   MVC_CUDA(cudaMemsetAsync(dhid, 0, sizeof(float) * (size_t)L * B * H, st));
   float* dhid1 = dhid + (int64_t)B * H;
@@ -275,12 +294,12 @@ extern "C" int mvc_global_recon_backward(const MvcReconDims* d, const MvcReconPa
     MVC_TRY(mvc_gemm_f32(SB, H, G4, 1.f, q.dG, G4, 1, p->w_ih, 1, 2 * H, 0.f, dhid1, H, nullptr, st));
     MVC_TRY(mvc_gemm_f32(B, H, G4, 1.f, q.dGsum, G4, 1, p->w_ih + H, 1, 2 * H, 0.f, q.dpooled, H, nullptr, st));
   } else {
-    MVC_TRY(mvc_transpose_to_bf16(q.dG_b, 1, SB, G4, G4, q.dGT, SBp, st));
+    MVC_TRY(launch_transpose_bf16(q.dG_b, 1, SB, G4, G4, q.dGT, SBp, permH, st));        // natural gate rows
     MVC_TRY(mvc_transpose_to_bf16(w.hs, 1, SB, Fr, Fr, q.hsT, SBp, st));
     MVC_TRY(mvc_transpose_to_bf16(w.hid_b, 1, SB, H, H, q.hidT, SBp, st));
     MVC_TRY(mvc_transpose_to_bf16(w.wih_b, 1, G4, 2 * H, 2 * H, q.wihT, G4, st));
     MVC_TRY(mvc_cast_bf16(q.dGsum, q.dGsum_b, (int64_t)B * G4, st));
-    MVC_TRY(mvc_transpose_to_bf16(q.dGsum_b, 1, B, G4, G4, q.dGsumT, Bp, st));
+    MVC_TRY(launch_transpose_bf16(q.dGsum_b, 1, B, G4, G4, q.dGsumT, Bp, permH, st));
     MVC_TRY(mvc_transpose_to_bf16(w.pooled_b, 1, B, H, H, q.pooledT, Bp, st));
     MVC_TRY(mvc_gemm_bf16(G4, Fr, SB, q.dGT, SBp, q.hsT, SBp, 0.f, g->w_hh, Fr, nullptr, nullptr, 0, st));
     MVC_TRY(mvc_gemm_bf16(G4, H, SB, q.dGT, SBp, q.hidT, SBp, 0.f, g->w_ih, 2 * H, nullptr, nullptr, 0, st));
@@ -352,6 +371,8 @@ struct LocBwdWs {
   void* keysT;      // bf16 [H, BLp]
   void* duk_b;      // bf16 [B*L, A]
   void* UT;         // bf16 [H, A]
+  void* dwq_b;      // bf16 [T*B, A]
+  void* attWT;      // bf16 [Fr, A]
   size_t bytes;
 };
 static LocBwdWs loc_bwd_layout(const MvcReconDims* d, void* base) {
@@ -377,6 +398,8 @@ static LocBwdWs loc_bwd_layout(const MvcReconDims* d, void* base) {
     w.keysT = ar.take<char>(H * BLp * 2);
     w.duk_b = ar.take<char>(B * L * A * 2);
     w.UT = ar.take<char>(H * A * 2);
+    w.dwq_b = ar.take<char>(T * B * A * 2);
+    w.attWT = ar.take<char>(Fr * A * 2);
   }
   w.bytes = ar.off + 256;
   return w;
@@ -389,6 +412,7 @@ static StepCfg loc_cfg(const MvcReconDims* d, const MvcReconParams* p, const Loc
   c.F = d->H;            // key / context width = decoder hidden size
   c.H = d->Fr;           // LSTM hidden = reconstructed feature size
   c.A = d->A;
+  c.perm = rec_perm(d);
   c.uk = w.uk;
   c.keys = w.keys; c.keys_batch = d->B; c.k_sb = (int64_t)d->L * d->H; c.k_st = d->H;
   c.mask = mask; c.m_sb = 1; c.m_st = d->B;           // caption_masks is [L,B]; transposed view (reconstructor.py:69)
@@ -424,8 +448,9 @@ extern "C" int mvc_local_recon_forward(const MvcReconDims* d, const MvcReconPara
   if (bf) permute_lbh_kernel<__nv_bfloat16><<<gridn((int64_t)L * B * H), 256, 0, st>>>(hid, L, B, H, (__nv_bfloat16*)w.keys);
   else permute_lbh_kernel<float><<<gridn((int64_t)L * B * H), 256, 0, st>>>(hid, L, B, H, (float*)w.keys);
   MVC_LAUNCH_CHECK();
-  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * Fr, st));
-  MVC_TRY(launch_pack_wcat(p->w_ih, H, p->w_hh, H, Fr, w.wcat, bf, st));
+  const int perm = rec_perm(d);
+  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * Fr, perm ? Fr : 0, st));
+  MVC_TRY(launch_pack_wcat(p->w_ih, H, p->w_hh, H, Fr, w.wcat, bf, perm, st));
   if (bf) {
     MVC_TRY(mvc_cast_bf16(p->att_U, w.U, (int64_t)A * H, st));
     MVC_TRY(mvc_cast_bf16(p->att_W, w.W, (int64_t)A * Fr, st));
@@ -476,9 +501,12 @@ extern "C" int mvc_local_recon_backward(const MvcReconDims* d, const MvcReconPar
   MVC_CUDA(cudaMemsetAsync(q.dwpart, 0, sizeof(float) * (size_t)B * A, st));
   MVC_CUDA(cudaMemsetAsync(q.dkeys, 0, sizeof(float) * (size_t)B * L * H, st));
   StepCfg cfg = loc_cfg(d, p, w, mask);
+  const int permH = cfg.perm ? Fr : 0;
   if (bf) {
     MVC_TRY(mvc_transpose_to_bf16(w.wcat, 1, G4, H + Fr, ldx, q.wcatT, G4, st));
+    MVC_TRY(mvc_transpose_to_bf16(w.W, 1, A, Fr, Fr, q.attWT, A, st));
     cfg.wcatT = q.wcatT;
+    cfg.attWT = q.attWT;
   }
   for (int t = T - 1; t >= 0; --t) {
     StepBwd io{};
@@ -496,6 +524,7 @@ extern "C" int mvc_local_recon_backward(const MvcReconDims* d, const MvcReconPar
     io.wq = w.wq + (int64_t)t * B * A;
     io.alpha = w.alpha + (int64_t)t * B * L;
     io.dwq = q.dwq + (int64_t)t * B * A;
+    io.dwq_b = bf ? mptr(q.dwq_b, (int64_t)t * B * A, 2) : nullptr;
     io.duk = q.duk;
     io.dwpart = q.dwpart;
     io.dkeys = q.dkeys; io.dk_sb = (int64_t)L * H; io.dk_st = H;
@@ -504,7 +533,7 @@ extern "C" int mvc_local_recon_backward(const MvcReconDims* d, const MvcReconPar
   }
   MVC_TRY(mvc_colsum(q.dwq, TB, A, A, g->att_b, st));
   MVC_TRY(mvc_colsum(q.dwpart, B, A, A, g->att_w, st));
-  MVC_TRY(mvc_colsum(q.dG, TB, G4, G4, g->b_ih, st));
+  MVC_TRY(launch_colsum(q.dG, TB, G4, G4, g->b_ih, permH, st));
   MVC_CUDA(cudaMemcpyAsync(g->b_hh, g->b_ih, sizeof(float) * (size_t)G4, cudaMemcpyDeviceToDevice, st));
   const char* hprev = cptr(w.xh, H, es);          // h_rec_t for t = 0..T-1 (h-part of slots 0..T-1)
   if (!bf) {
@@ -515,9 +544,9 @@ extern "C" int mvc_local_recon_backward(const MvcReconDims* d, const MvcReconPar
     // dkeys += duk . U   (uk = keys . U^T)
     MVC_TRY(mvc_gemm_f32(B * L, H, A, 1.f, q.duk, A, 1, p->att_U, 1, H, 1.f, q.dkeys, H, nullptr, st));
   } else {
-    MVC_TRY(mvc_transpose_to_bf16(q.dG_b, 1, TB, G4, G4, q.dGT, TBp, st));
+    MVC_TRY(launch_transpose_bf16(q.dG_b, 1, TB, G4, G4, q.dGT, TBp, permH, st));        // natural gate rows
     MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, TB, H + Fr, ldx, q.xhT, TBp, st));
-    MVC_TRY(mvc_transpose_to_bf16(q.dwq, 0, TB, A, A, q.dwqT, TBp, st));
+    MVC_TRY(mvc_transpose_to_bf16(q.dwq_b, 1, TB, A, A, q.dwqT, TBp, st));
     MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * L, A, A, q.dukT, BLp, st));
     MVC_TRY(mvc_transpose_to_bf16(w.keys, 1, B * L, H, H, q.keysT, BLp, st));
     const char* hprevT = cptr(q.xhT, (int64_t)H * TBp, 2);

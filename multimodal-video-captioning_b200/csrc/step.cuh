@@ -1,8 +1,14 @@
 // step.cuh -- one "soft attention -> LSTM cell" recurrence step and its backward,
 // shared by the caption decoder (features_captioning.py:77-89) and the local
 // reconstructor (reconstructor.py:67-74).  Host-side launch sequences only.
+//
+// bf16 path (H % 32 == 0): three launches per forward step, chained with programmatic dependent
+// launch so that each kernel's loop-invariant operand (weights / keys) streams in while its
+// producer is still running:
+//     wq GEMM (tcgen05, split-K)  ->  fused soft attention  ->  gate GEMM + LSTM cell epilogue
+// fp32 path: FFMA GEMMs + separate cell kernel, fixed reduction order (the exact-ids path).
 #pragma once
-#include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace mvc {
 
@@ -23,25 +29,65 @@ static inline int gemm_nt(int prec, int M, int N, int K, const void* A, int64_t 
   return mvc_gemm_f32(M, N, K, 1.f, (const float*)A, lda, 1, (const float*)Bm, ldb, 1, beta, C, ldc, bias, st);
 }
 
+// plain tcgen05 GEMM inside a PDL chain (B operand loop invariant)
+static inline int gemm_tc_chain(int M, int N, int K, const void* A, int64_t lda, const void* Bm, int64_t ldb, float beta,
+                                float* C, int64_t ldc, void* Cb, int64_t ldcb, bool b_const, cudaStream_t st) {
+  TcEpilogue ep{};
+  ep.mode = TC_MODE_PLAIN;
+  ep.beta = beta; ep.C = C; ep.ldc = ldc; ep.Cb = (__nv_bfloat16*)Cb; ep.ldcb = ldcb;
+  return tc_gemm(M, N, K, A, lda, Bm, ldb, ep, TC_FLAG_PDL | (b_const ? TC_FLAG_B_CONST : 0), st);
+}
+
+// internal launchers with layout options (elementwise.cu / attention.cu)
+int launch_transpose_bf16(const void* src, int src_bf16, int64_t R, int64_t C, int64_t lds, void* dst, int64_t ldd,
+                          int permH, cudaStream_t st);
+int launch_cell_bwd(int B, int H, const float* act, const float* c_prev, const float* c_new, const float* dh_a,
+                    int64_t dha_ld, const float* dh_b, int64_t dhb_ld, float* dc, float* dgates, void* dg_bf16, int perm,
+                    cudaStream_t st);
+int launch_colsum(const float* x, int64_t rows, int N, int64_t ld, float* out, int permH, cudaStream_t st);
+bool pdl_enabled();
+
+struct AttnFwdArgs {
+  int B, T, A, F;
+  const float* wq; const float* uk; const float* bias; const float* w;
+  const void* keys; int keys_bf16; int keys_batch; int64_t k_sb, k_st;
+  const uint8_t* mask; int64_t m_sb, m_st;
+  float* ctx_f32; int64_t ctx_ld; void* ctx_bf16; int64_t ctxb_ld; float* alpha;
+  int fast_math;
+};
+int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st);
+
+struct AttnBwdArgs {
+  int B, T, A, F;
+  const float* wq; const float* uk; const float* bias; const float* w;
+  const void* keys; int keys_bf16; int64_t k_sb, k_st;
+  const float* alpha; const float* dctx; int64_t dctx_ld;
+  float* dwq; void* dwq_bf16; float* duk; float* dw_partial; float* dkeys; int64_t dk_sb, dk_st;
+  int fast_math;
+};
+int launch_attention_bwd(const AttnBwdArgs& a, bool pdl, cudaStream_t st);
+
 // Static description of the recurrence (constant over the time loop).
 struct StepCfg {
   int prec;
   int T, F, H, A;        // keys per row, key/context width, LSTM hidden, attention bottleneck
+  int perm;              // gate columns in the tile-interleaved order of the fused cell epilogue (bf16, H % 32 == 0)
   const float* uk;       // [keys_batch, T, A]   U.k (hoisted)
   const void* keys;      // element (b,t,f) at keys[(b % keys_batch)*k_sb + t*k_st + f], compute dtype
   int keys_batch;
   int64_t k_sb, k_st;
   const uint8_t* mask;   // optional [.,.] uint8 at mask[b*m_sb + t*m_st]
   int64_t m_sb, m_st;
-  const void* wcat;      // [4H, F+H] = [W_ih(ctx part) | W_hh], compute dtype
+  const void* wcat;      // [4H, F+H] = [W_ih(ctx part) | W_hh], compute dtype (rows permuted iff perm)
   const void* wcatT;     // [F+H, 4H] bf16 (backward, bf16 path only)
   const void* attW;      // [A, H] attention.W in the compute dtype
-  const float* attW32;   // fp32 master copy (backward dh += dwq . W)
+  const void* attWT;     // [H, A] bf16 (backward, bf16 path only)
+  const float* attW32;   // fp32 master copy (backward dh += dwq . W, fp32 path)
   const float* att_b;    // [A]
   const float* att_w;    // [A]
-  const float* cell_bias;  // [4H] added inside the cell (null when folded into gx / embtab)
-  const float* embtab;   // [V,4H] gathered by tokens inside the cell (or null)
-  float* pre;            // [rows, 4H] scratch
+  const float* cell_bias;  // [4H] added inside the cell (null when folded into gx / embtab); permuted iff perm
+  const float* embtab;   // [V,4H] gathered by tokens inside the cell (or null); columns permuted iff perm
+  float* pre;            // [rows, 4H] scratch (unfused path)
 };
 
 struct StepFwd {
@@ -68,14 +114,34 @@ static inline int step_forward(const StepCfg& c, const StepFwd& io, cudaStream_t
   // wq = h_s . W^T                                   (temporal_attention.py:20)
   if (io.first) {
     MVC_CUDA(cudaMemsetAsync(io.wq, 0, sizeof(float) * (size_t)R * c.A, st));
+  } else if (bf) {
+    MVC_TRY(gemm_tc_chain(R, c.A, c.H, cptr(io.xh_src, c.F, es), ldx, c.attW, c.H, 0.f, io.wq, c.A, nullptr, 0, true, st));
   } else {
     MVC_TRY(gemm_nt(c.prec, R, c.A, c.H, cptr(io.xh_src, c.F, es), ldx, c.attW, c.H, 0.f, io.wq, c.A, nullptr, st));
   }
   // ctx_s -> xh_src[:, :F]                            (temporal_attention.py:22-32)
-  MVC_TRY(mvc_soft_attention_fwd(R, c.T, c.A, c.F, io.wq, c.uk, c.att_b, c.att_w, c.keys, bf, c.keys_batch, c.k_sb,
-                                 c.k_st, c.mask, c.m_sb, c.m_st, bf ? nullptr : (float*)io.xh_src, ldx,
-                                 bf ? io.xh_src : nullptr, ldx, io.alpha, bf ? 1 : 0, st));
-  // gates = [ctx_s ; h_s] . wcat^T                    (nn.LSTM, features_captioning.py:84)
+  AttnFwdArgs a{};
+  a.B = R; a.T = c.T; a.A = c.A; a.F = c.F;
+  a.wq = io.wq; a.uk = c.uk; a.bias = c.att_b; a.w = c.att_w;
+  a.keys = c.keys; a.keys_bf16 = bf; a.keys_batch = c.keys_batch; a.k_sb = c.k_sb; a.k_st = c.k_st;
+  a.mask = c.mask; a.m_sb = c.m_sb; a.m_st = c.m_st;
+  a.ctx_f32 = bf ? nullptr : (float*)io.xh_src; a.ctx_ld = ldx;
+  a.ctx_bf16 = bf ? io.xh_src : nullptr; a.ctxb_ld = ldx;
+  a.alpha = io.alpha; a.fast_math = bf ? 1 : 0;
+  MVC_TRY(launch_attention_fwd(a, bf && !io.first, st));
+  // gates = [ctx_s ; h_s] . wcat^T  -> cell         (nn.LSTM, features_captioning.py:84)
+  if (bf && c.perm) {
+    TcEpilogue ep{};
+    ep.mode = TC_MODE_CELL;
+    ep.H = c.H;
+    ep.bias = c.cell_bias;
+    ep.gx = io.gx; ep.gx_ld = 4 * c.H;
+    ep.embtab = io.tokens ? c.embtab : nullptr; ep.tokens = io.tokens;
+    ep.c_prev = io.c_prev; ep.act = io.act; ep.c_out = io.c_out;
+    ep.h32 = io.h_out32; ep.h_ld = io.h_ld;
+    ep.hb = io.xh_dst ? (__nv_bfloat16*)mptr(io.xh_dst, c.F, es) : nullptr; ep.hb_ld = ldx;
+    return tc_gemm(R, 4 * c.H, c.F + c.H, io.xh_src, ldx, c.wcat, ldx, ep, TC_FLAG_PDL | TC_FLAG_B_CONST, st);
+  }
   MVC_TRY(gemm_nt(c.prec, R, 4 * c.H, c.F + c.H, io.xh_src, ldx, c.wcat, ldx, 0.f, c.pre, 4 * c.H, nullptr, st));
   float* h2 = nullptr;
   void* hb = nullptr;
@@ -103,6 +169,7 @@ struct StepBwd {
   const float* wq;       // saved
   const float* alpha;    // saved
   float* dwq;            // [rows, A] out
+  void* dwq_b;           // [rows, A] bf16 copy (bf16 path)
   float* duk;            // [rows, T, A] accumulated
   float* dwpart;         // [rows, A] accumulated
   float* dkeys;          // optional accumulate, strides dk_sb/dk_st
@@ -114,26 +181,35 @@ static inline int step_backward(const StepCfg& c, const StepBwd& io, cudaStream_
   const bool bf = c.prec == MVC_BF16;
   const int64_t ldx = c.F + c.H;
   const int R = io.rows;
-  MVC_TRY(mvc_lstm_cell_bwd(R, c.H, io.act, io.c_prev, io.c_new, io.dh_ext, io.dh_ld,
-                            io.has_carry ? io.dxh + c.F : nullptr, ldx, io.dc, io.dG, io.dG_b, st));
+  MVC_TRY(launch_cell_bwd(R, c.H, io.act, io.c_prev, io.c_new, io.dh_ext, io.dh_ld,
+                          io.has_carry ? io.dxh + c.F : nullptr, ldx, io.dc, io.dG, io.dG_b, c.perm, st));
   // d[ctx_s ; h_s] = dgates . wcat
-  if (bf) MVC_TRY(mvc_gemm_bf16(R, c.F + c.H, 4 * c.H, io.dG_b, 4 * c.H, c.wcatT, 4 * c.H, 0.f, io.dxh, ldx, nullptr,
-                                nullptr, 0, st));
+  if (bf) MVC_TRY(gemm_tc_chain(R, c.F + c.H, 4 * c.H, io.dG_b, 4 * c.H, c.wcatT, 4 * c.H, 0.f, io.dxh, ldx, nullptr, 0,
+                                true, st));
   else MVC_TRY(mvc_gemm_f32(R, c.F + c.H, 4 * c.H, 1.f, io.dG, 4 * c.H, 1, (const float*)c.wcat, 1, ldx, 0.f, io.dxh,
                             ldx, nullptr, st));
-  MVC_TRY(mvc_soft_attention_bwd(R, c.T, c.A, c.F, io.wq, c.uk, c.att_b, c.att_w, c.keys, bf, c.k_sb, c.k_st, io.alpha,
-                                 io.dxh, ldx, io.dwq, io.duk, io.dwpart, io.dkeys, io.dk_sb, io.dk_st, bf ? 1 : 0, st));
+  AttnBwdArgs a{};
+  a.B = R; a.T = c.T; a.A = c.A; a.F = c.F;
+  a.wq = io.wq; a.uk = c.uk; a.bias = c.att_b; a.w = c.att_w;
+  a.keys = c.keys; a.keys_bf16 = bf; a.k_sb = c.k_sb; a.k_st = c.k_st;
+  a.alpha = io.alpha; a.dctx = io.dxh; a.dctx_ld = ldx;
+  a.dwq = io.dwq; a.dwq_bf16 = bf ? io.dwq_b : nullptr; a.duk = io.duk; a.dw_partial = io.dwpart;
+  a.dkeys = io.dkeys; a.dk_sb = io.dk_sb; a.dk_st = io.dk_st; a.fast_math = bf ? 1 : 0;
+  MVC_TRY(launch_attention_bwd(a, bf, st));
   // dh_s += dwq . W        (wq = h_s . W^T)
-  if (!io.first)
-    MVC_TRY(mvc_gemm_f32(R, c.H, c.A, 1.f, io.dwq, c.A, 1, c.attW32, 1, c.H, 1.f, io.dxh + c.F, ldx, nullptr, st));
+  if (!io.first) {
+    if (bf) MVC_TRY(gemm_tc_chain(R, c.H, c.A, io.dwq_b, c.A, c.attWT, c.A, 1.f, io.dxh + c.F, ldx, nullptr, 0, true, st));
+    else MVC_TRY(mvc_gemm_f32(R, c.H, c.A, 1.f, io.dwq, c.A, 1, c.attW32, 1, c.H, 1.f, io.dxh + c.F, ldx, nullptr, st));
+  }
   return 0;
 }
 
 // ---- small shared kernels (defined in decoder.cu) ----
-int launch_pack_wcat(const float* w_x, int64_t wx_ld, const float* w_hh, int F, int H, void* out, int out_bf16,
+int launch_pack_wcat(const float* w_x, int64_t wx_ld, const float* w_hh, int F, int H, void* out, int out_bf16, int perm,
                      cudaStream_t st);
-int launch_cast_pad_bf16(const float* src, int64_t rows, int C, int64_t lds, int Cp, void* out, cudaStream_t st);
-int launch_add_vec(const float* a, const float* b, float* o, int n, cudaStream_t st);
+int launch_cast_pad_bf16(const float* src, int64_t rows, int C, int64_t lds, int Cp, void* out, int permH,
+                         cudaStream_t st);
+int launch_add_vec(const float* a, const float* b, float* o, int n, int permH, cudaStream_t st);
 int launch_fill_i64(int64_t* p, int64_t v, int64_t n, cudaStream_t st);
 int launch_iota_i64(int64_t* p, int64_t n, cudaStream_t st);
 int launch_add_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int C, int accumulate,

@@ -1,0 +1,57 @@
+// tc_gemm.cuh -- internal interface of the tcgen05 GEMM (gemm_tc.cu): epilogue descriptor + launch flags.
+#pragma once
+#include "common.cuh"
+
+namespace mvc {
+
+enum { TC_MODE_PLAIN = 0, TC_MODE_CELL = 1 };
+enum {
+  TC_FLAG_PDL = 1,       // launch with programmatic stream serialization (the kernel waits on griddepcontrol itself)
+  TC_FLAG_B_CONST = 2,   // operand B was complete before the previous kernel started: prefetch it before the dependency wait
+  TC_FLAG_NO_SPLIT = 4   // never split K
+};
+
+struct TcEpilogue {
+  int mode;
+  int b_const;
+  // plain: C = acc (+ bias[n]) (+ beta*C), optional bf16 copy
+  float beta;
+  float* C;
+  int64_t ldc;
+  const float* bias;          // also the (permuted) gate bias in cell mode, may be null
+  __nv_bfloat16* Cb;
+  int64_t ldcb;
+  // split-K scratch (filled in by the launcher)
+  float* ws;
+  unsigned* counters;
+  // fused LSTM cell (mode == TC_MODE_CELL): N = 4H, columns permuted (j/32)*128 + gate*32 + j%32
+  int H;
+  const float* gx;            // [M,4H] hoisted input projection (permuted columns), ld gx_ld, may be null
+  int64_t gx_ld;
+  const float* embtab;        // [V,4H] gathered by tokens[m] (permuted columns), may be null
+  const int64_t* tokens;
+  const float* c_prev;        // [M,H] (null = zeros)
+  float* act;                 // [M,4H] activated gates, permuted columns (may be null)
+  float* c_out;               // [M,H]
+  float* h32;                 // fp32 h (ld h_ld), may be null
+  int64_t h_ld;
+  float* h32b;                // second fp32 copy (ld h2_ld), may be null
+  int64_t h2_ld;
+  __nv_bfloat16* hb;          // bf16 h (ld hb_ld), may be null
+  int64_t hb_ld;
+};
+
+int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const TcEpilogue& ep, int flags,
+            cudaStream_t st);
+
+// gate column of hidden unit j in the permuted ("tile-interleaved") layout used by the fused cell epilogue
+__host__ __device__ inline int gate_col(int perm, int H, int gate, int j) {
+  return perm ? (j >> 5) * 128 + gate * 32 + (j & 31) : gate * H + j;
+}
+// inverse: natural row (gate*H + j) of permuted column c
+__host__ __device__ inline int gate_unperm(int H, int c) {
+  const int tile = c >> 7, gate = (c >> 5) & 3, u = c & 31;
+  return gate * H + tile * 32 + u;
+}
+
+}  // namespace mvc

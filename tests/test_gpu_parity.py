@@ -92,6 +92,47 @@ def test_gemm_bf16_tcgen05(dev, M, N, K):
     close(c3, (a.double() @ b.double().t()).float(), atol=2e-4 * math.sqrt(K), rtol=1e-4)
 
 
+@pytest.mark.parametrize("B,H,K", [(128, 512, 2688), (37, 64, 72), (130, 32, 512), (128, 2176, 2176), (512, 512, 2992)])
+def test_fused_gate_gemm_lstm_cell(dev, B, H, K):
+    """K-C: tcgen05 gate GEMM (split-K) with the LSTM cell in the epilogue, vs the closed-form cell in fp64."""
+    from salstm import cabi
+    lib = cabi.lib()
+    g = torch.Generator().manual_seed(B + H + K)
+    x = (torch.randn(B, K, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(4 * H, K, generator=g) / math.sqrt(K)).bfloat16().float()
+    bias = torch.randn(4 * H, generator=g) * 0.1
+    gx = torch.randn(B, 4 * H, generator=g) * 0.3
+    c0 = torch.randn(B, H, generator=g)
+    gates = x.double() @ w.double().t() + bias.double() + gx.double()
+    i, f, gg, o = gates.chunk(4, 1)
+    c1 = torch.sigmoid(f) * c0.double() + torch.sigmoid(i) * torch.tanh(gg)
+    h1 = torch.sigmoid(o) * torch.tanh(c1)
+    # natural gate row r = gate*H + j  <->  packed row (j//32)*128 + gate*32 + j%32
+    j = torch.arange(H)
+    packed_of = torch.stack([(j // 32) * 128 + q * 32 + j % 32 for q in range(4)]).reshape(-1)   # natural -> packed
+    nat_of = torch.empty(4 * H, dtype=torch.long); nat_of[packed_of] = torch.arange(4 * H)      # packed -> natural
+    Kp = K + (-K) % 8
+    wp = torch.empty(4 * H, Kp, device=dev, dtype=torch.bfloat16)
+    wd = w.to(dev)
+    cabi.check(lib.mvc_pack_gate_rows_bf16(cabi.ptr(wd), H, K, K, Kp, cabi.ptr(wp), cabi.stream_ptr()))
+    assert torch.equal(wp[:, :K].float().cpu(), w[nat_of])
+    xd = torch.zeros(B, Kp, device=dev, dtype=torch.bfloat16); xd[:, :K] = x.to(dev)
+    bias_p, gx_p = bias[nat_of].to(dev).contiguous(), gx[:, nat_of].to(dev).contiguous()
+    c0d = c0.to(dev)
+    act = torch.empty(B, 4 * H, device=dev)
+    c_out, h_out = torch.empty(B, H, device=dev), torch.empty(B, H + 8, device=dev)
+    h_b = torch.empty(B, H, device=dev, dtype=torch.bfloat16)
+    for _ in range(2):   # second run exercises the re-armed split-K tickets
+        cabi.check(lib.mvc_lstm_gates_cell_bf16(B, H, Kp, cabi.ptr(xd), Kp, cabi.ptr(wp), Kp, cabi.ptr(bias_p),
+                                                cabi.ptr(gx_p), 4 * H, cabi.ptr(c0d), cabi.ptr(act), cabi.ptr(c_out),
+                                                cabi.ptr(h_out), H + 8, cabi.ptr(h_b), H, cabi.stream_ptr()))
+        close(c_out, c1, atol=2e-5, rtol=1e-4)
+        close(h_out[:, :H], h1, atol=2e-5, rtol=1e-4)
+        close(h_b.float(), h1, atol=1e-2, rtol=1e-2)
+        ref_act = torch.cat([torch.sigmoid(i), torch.sigmoid(f), torch.tanh(gg), torch.sigmoid(o)], 1)
+        close(act.cpu()[:, packed_of], ref_act, atol=2e-5, rtol=1e-4)
+
+
 def test_gemm_bf16_rejects_bad_pitch(dev):
     from salstm import cabi
     lib = cabi.lib()
@@ -399,18 +440,25 @@ def test_full_width_wrappers_golden(dev, kind, rec_type):
 
 # --------------------------------------------------------------------------- bf16 tensor-core path
 @pytest.mark.parametrize("rec_type", ["none", "global", "local"])
-@pytest.mark.parametrize("peaky", [False, True])
-def test_bf16_path_vs_fp64_oracle(dev, rec_type, peaky):
-    """bf16 tensor-core path against the oracle run in fp64.  With the reference's default init the
-    gradient direction must agree to cosine >= 0.999; with out.weight x6 ("peaky" logits,
-    the id-equality variant) a 5e-2 logit error moves softmax probabilities by ~5 %, so the bound is 0.99."""
+@pytest.mark.parametrize("inputs", ["unit", "raw"])
+def test_bf16_path_vs_fp64_oracle(dev, rec_type, inputs):
+    """bf16 tensor-core path against the oracle run in fp64 (default init, no peaky logits).
+
+    "unit": features scaled to O(1) (audio/255, visual/10).  Gradient direction must agree to
+    cosine >= 0.999 and norms to 5 %.
+    "raw": the loader's raw magnitudes (audio up to 255, captioning.py normalize_inputs=False).  Gate
+    pre-activations are then ~+-36 with bf16 rounding error ~0.1, and tanh'/sigmoid' of the few
+    unsaturated units move by ~10-20 % -- measured cosine 0.93 on W_ih, 0.96-0.98 on the attention
+    parameters: a property of bf16 on unnormalised features, not of the kernels (the fp32 path on the same
+    inputs meets rtol 1e-3, test_full_width_wrappers_golden).  Bound: cosine >= 0.9, norms within 20 %."""
     from models import AVCaptioning
     import losses as L
     B, T, Lc, V = 6, 9, 8, 211
     p = _wrapper_params("joint", V, rec_type, 77)
-    if not peaky:
-        p["decoder.out.weight"] /= 6.0
+    p["decoder.out.weight"] /= 6.0
     audio, visual, caps = O.synth_batch(B, T, Lc, V, seed=5, min_frames=2, min_cap=4)
+    if inputs == "unit":
+        audio, visual = audio / 255.0, visual / 10.0
     model = AVCaptioning(Vocab(V), 1.0, rec_type, device=dev, precision="bf16").to(dev)
     _load(model, p)
     out, arec, vrec = model(audio.to(dev), visual.to(dev), caps.to(dev))
@@ -425,13 +473,14 @@ def test_bf16_path_vs_fp64_oracle(dev, rec_type, peaky):
     close(terms[0], o_terms[0], rtol=2e-2, atol=1e-3)
     if rec_type != "none":
         close(vrec, o_vr, atol=5e-2, rtol=5e-2)
+    cmin, ntol = (0.999, 5e-2) if inputs == "unit" else (0.9, 0.2)
     bad = []
     for k, v in model.named_parameters():
         if pd[k].grad is None:
             continue
         c = cos(v.grad, pd[k].grad)
         n1, n2 = float(v.grad.norm()), float(pd[k].grad.norm())
-        if c < (0.99 if peaky else 0.999) or abs(n1 - n2) > 5e-2 * n2 + 1e-7:
+        if c < cmin or abs(n1 - n2) > ntol * n2 + 1e-7:
             bad.append(f"{k}: cosine {c:.5f}, norm {n1:.4e} vs {n2:.4e}")
     assert not bad, "\n".join(bad)
 
