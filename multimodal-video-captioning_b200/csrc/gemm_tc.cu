@@ -19,10 +19,11 @@
 // Out-of-range rows / K tails are zero-filled by TMA; stores are predicated.
 //
 // Split-K (the recurrence GEMMs have M = batch = one row tile, so N tiles alone cannot fill
-// 148 SMs): blockIdx.z owns a contiguous range of 64-wide K blocks.  Every split writes its fp32
-// partial tile to a workspace, takes a ticket on the tile's counter, and the LAST CTA to arrive
-// sums the partials in split order 0..S-1 (its own straight from TMEM) -- so the result does not
-// depend on arrival order -- and runs the epilogue.
+// 148 SMs): blockIdx.z owns a contiguous range of 64-wide K blocks and the S splits of one output
+// tile are launched as one thread-block CLUSTER (1,1,S).  Each CTA parks its fp32 partial tile in
+// its own shared memory (the idle operand ring); after a cluster barrier CTA z reads rows
+// [z*128/S, (z+1)*128/S) of all S partials through distributed shared memory, sums them in rank
+// order (deterministic) and runs the epilogue for that row block -- no global scratch, no atomics.
 //
 // Epilogues:
 //   plain : + bias, + beta*C, fp32 store, optional bf16 copy;
@@ -74,7 +75,122 @@ struct TcSmem {
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+
+// ---- cluster / distributed shared memory
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// plain epilogue for NC (compile-time capacity; `n` live) consecutive columns of one row
+template <int NC, typename Arr>
+__device__ __forceinline__ void plain_store(const TcEpilogue& ep, int64_t gm, int gn0, int N, Arr& o, int n = NC) {
+  float* crow = ep.C ? ep.C + gm * ep.ldc : nullptr;
+  __nv_bfloat16* brow = ep.Cb ? ep.Cb + gm * ep.ldcb : nullptr;
+  const bool vec_ok = crow && (gn0 + n - 1 < N) && ((reinterpret_cast<uintptr_t>(crow + gn0) & 15u) == 0);
+  if (vec_ok) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      if (j < n) {
+        float4 r = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        if (ep.bias) {
+          r.x += ep.bias[gn0 + j]; r.y += ep.bias[gn0 + j + 1]; r.z += ep.bias[gn0 + j + 2]; r.w += ep.bias[gn0 + j + 3];
+        }
+        float4* dst = reinterpret_cast<float4*>(crow + gn0 + j);
+        if (ep.beta != 0.f) {
+          const float4 old = *dst;
+          r.x += ep.beta * old.x; r.y += ep.beta * old.y; r.z += ep.beta * old.z; r.w += ep.beta * old.w;
+        }
+        *dst = r;
+        if (brow) {
+          brow[gn0 + j] = __float2bfloat16(r.x); brow[gn0 + j + 1] = __float2bfloat16(r.y);
+          brow[gn0 + j + 2] = __float2bfloat16(r.z); brow[gn0 + j + 3] = __float2bfloat16(r.w);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int gn = gn0 + j;
+      if (j < n && gn < N) {
+        float r = o[j];
+        if (ep.bias) r += ep.bias[gn];
+        if (crow) {
+          if (ep.beta != 0.f) r += ep.beta * crow[gn];
+          crow[gn] = r;
+        }
+        if (brow) brow[gn] = __float2bfloat16(r);
+      }
+    }
+  }
+}
+
+// fused LSTM cell for NU hidden units [tile*32 + u0, +NU) of row gm; g[gate][j] = summed GEMM output
+template <int NU, typename Arr>
+__device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int tile, int u0, Arr& g) {
+  const int H = ep.H;
+  const int n0 = tile * 128, ug = tile * 32 + u0;
+  const float* gxr = ep.gx ? ep.gx + gm * ep.gx_ld + n0 + u0 : nullptr;
+  const float* etr = ep.embtab ? ep.embtab + ep.tokens[gm] * (int64_t)(4 * H) + n0 + u0 : nullptr;
+  const float* br = ep.bias ? ep.bias + n0 + u0 : nullptr;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int j = 0; j < NU; j += 4) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gxr) { const float4 t = *reinterpret_cast<const float4*>(gxr + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+      if (etr) { const float4 t = *reinterpret_cast<const float4*>(etr + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+      if (br) { const float4 t = *reinterpret_cast<const float4*>(br + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+      g[c][j] += a.x; g[c][j + 1] += a.y; g[c][j + 2] += a.z; g[c][j + 3] += a.w;
+    }
+  }
+  const float* cp = ep.c_prev ? ep.c_prev + gm * H + ug : nullptr;
+  float* co = ep.c_out + gm * H + ug;
+  float* actr = ep.act ? ep.act + gm * (int64_t)(4 * H) + n0 + u0 : nullptr;
+  float* h1 = ep.h32 ? ep.h32 + gm * ep.h_ld + ug : nullptr;
+  float* h2 = ep.h32b ? ep.h32b + gm * ep.h2_ld + ug : nullptr;
+  __nv_bfloat16* hb = ep.hb ? ep.hb + gm * ep.hb_ld + ug : nullptr;
+#pragma unroll
+  for (int j = 0; j < NU; j += 4) {
+    const float4 cprev = cp ? *reinterpret_cast<const float4*>(cp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float cpv[4] = {cprev.x, cprev.y, cprev.z, cprev.w};
+    float cn[4], hn[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ig = sigmoid_f(g[0][j + e]), fg = sigmoid_f(g[1][j + e]);
+      const float gg = tanhf(g[2][j + e]), og = sigmoid_f(g[3][j + e]);
+      g[0][j + e] = ig; g[1][j + e] = fg; g[2][j + e] = gg; g[3][j + e] = og;
+      cn[e] = fg * cpv[e] + ig * gg;
+      hn[e] = og * tanhf(cn[e]);
+    }
+    *reinterpret_cast<float4*>(co + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    if (h1) *reinterpret_cast<float4*>(h1 + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    if (h2) *reinterpret_cast<float4*>(h2 + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    if (hb) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(hn[0], hn[1]), p1 = __floats2bfloat162_rn(hn[2], hn[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(hb + j) = pk;
+    }
+  }
+  if (actr) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < NU; j += 4)
+        *reinterpret_cast<float4*>(actr + c * 32 + j) = make_float4(g[c][j], g[c][j + 1], g[c][j + 2], g[c][j + 3]);
+  }
+}
 
 template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(192, 1)
@@ -89,7 +205,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR_OFF + 8 * (2 * STAGES + 1));
-  uint32_t* ticket_slot = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -171,166 +286,118 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int64_t gm = (int64_t)m0 + row;
-    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    pdl_wait();                                   // C / partials / cell state may still be in use upstream
+    pdl_wait();                                   // C / cell state may still be in use upstream
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    bool last = true;
-    if (splits > 1) {
-      // partial tile, transposed ([col][row]) so that a warp's stores are contiguous
-      float* mine = ep.ws + ((size_t)tile_id * splits + z) * (size_t)(BN * TC_BM);
+    if (splits == 1) {
+      const int64_t gm = (int64_t)m0 + row;
+      if constexpr (MODE == TC_MODE_PLAIN) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(trow + (uint32_t)(c * 32), v);
+          if (gm < M) {
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+            plain_store<32>(ep, gm, n0 + c * 32, N, o);
+          }
+        }
+      } else {
+        float g4[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(trow + (uint32_t)(c * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) g4[c][j] = __uint_as_float(v[j]);
+        }
+        if (gm < M) cell_store<32>(ep, gm, blockIdx.x, 0, g4);
+      }
+    } else {
+      // split-K: park this CTA's partial tile in its own shared memory (the operand ring is idle now:
+      // every MMA has completed), row-major with a 4-word pad so 128-bit accesses are conflict-free
+      float* red = reinterpret_cast<float*>(smem);
+      constexpr int RS = BN + 4;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(trow + (uint32_t)(c * 32), v);
+        float4* dst = reinterpret_cast<float4*>(red + (size_t)row * RS + c * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) __stcg(mine + (c * 32 + j) * TC_BM + row, __uint_as_float(v[j]));
-      }
-      __threadfence();
-      epi_bar_sync();
-      if (row == 0) *ticket_slot = atomicAdd(ep.counters + tile_id, 1u);
-      epi_bar_sync();
-      last = (*ticket_slot == (uint32_t)(splits - 1));
-      if (last) __threadfence();
-    }
-    if (last) {
-      const float* part = ep.ws + (size_t)tile_id * splits * (size_t)(BN * TC_BM);
-      // sum of the S partials of chunk c in split order (own partial straight from TMEM)
-      auto chunk_sum = [&](int c, float* o) {
-        uint32_t v[32];
-        tmem_ld32(trow + (uint32_t)(c * 32), v);
-        if (splits == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = 0.f;
-#pragma unroll 1
-          for (int s = 0; s < splits; ++s) {
-            if (s == z) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] += __uint_as_float(v[j]);
-            } else {
-              const float* p = part + (size_t)s * (BN * TC_BM) + (size_t)(c * 32) * TC_BM + row;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] += __ldcg(p + j * TC_BM);
-            }
-          }
-        }
-      };
-      if constexpr (MODE == TC_MODE_PLAIN) {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          float o[32];
-          chunk_sum(c, o);
-          if (gm < M) {
-            const int gn0 = n0 + c * 32;
-            float* crow = ep.C ? ep.C + gm * ep.ldc : nullptr;
-            __nv_bfloat16* brow = ep.Cb ? ep.Cb + gm * ep.ldcb : nullptr;
-            const bool vec_ok = crow && (gn0 + 31 < N) && ((reinterpret_cast<uintptr_t>(crow + gn0) & 15u) == 0);
-            if (vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 r = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                if (ep.bias) {
-                  r.x += ep.bias[gn0 + j]; r.y += ep.bias[gn0 + j + 1]; r.z += ep.bias[gn0 + j + 2]; r.w += ep.bias[gn0 + j + 3];
-                }
-                float4* dst = reinterpret_cast<float4*>(crow + gn0 + j);
-                if (ep.beta != 0.f) {
-                  const float4 old = *dst;
-                  r.x += ep.beta * old.x; r.y += ep.beta * old.y; r.z += ep.beta * old.z; r.w += ep.beta * old.w;
-                }
-                *dst = r;
-                if (brow) {
-                  brow[gn0 + j] = __float2bfloat16(r.x); brow[gn0 + j + 1] = __float2bfloat16(r.y);
-                  brow[gn0 + j + 2] = __float2bfloat16(r.z); brow[gn0 + j + 3] = __float2bfloat16(r.w);
-                }
-              }
-            } else {
-#pragma unroll 1
-              for (int j = 0; j < 32; ++j) {
-                const int gn = gn0 + j;
-                if (gn >= N) break;
-                float r = o[j];
-                if (ep.bias) r += ep.bias[gn];
-                if (crow) {
-                  if (ep.beta != 0.f) r += ep.beta * crow[gn];
-                  crow[gn] = r;
-                }
-                if (brow) brow[gn] = __float2bfloat16(r);
-              }
-            }
-          }
-        }
-      } else {
-        // fused LSTM cell: this tile = gates (i,f,g,o) x 32 hidden units [u0, u0+32) of row gm
-        static_assert(MODE != TC_MODE_CELL || BN == 128, "cell epilogue needs a 128-wide tile");
-        float g4[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) chunk_sum(c, g4[c]);
-        if (gm < M) {
-          const int H = ep.H, u0 = blockIdx.x * 32;
-          const float* gxr = ep.gx ? ep.gx + gm * ep.gx_ld + n0 : nullptr;
-          const float* etr = ep.embtab ? ep.embtab + ep.tokens[gm] * (int64_t)(4 * H) + n0 : nullptr;
-          const float* br = ep.bias ? ep.bias + n0 : nullptr;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (gxr) { const float4 t = *reinterpret_cast<const float4*>(gxr + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-              if (etr) { const float4 t = *reinterpret_cast<const float4*>(etr + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-              if (br) { const float4 t = *reinterpret_cast<const float4*>(br + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-              g4[c][j] += a.x; g4[c][j + 1] += a.y; g4[c][j + 2] += a.z; g4[c][j + 3] += a.w;
-            }
-          }
-          const float* cp = ep.c_prev ? ep.c_prev + gm * H + u0 : nullptr;
-          float* co = ep.c_out + gm * H + u0;
-          float* actr = ep.act ? ep.act + gm * (int64_t)(4 * H) + n0 : nullptr;
-          float* h1 = ep.h32 ? ep.h32 + gm * ep.h_ld + u0 : nullptr;
-          float* h2 = ep.h32b ? ep.h32b + gm * ep.h2_ld + u0 : nullptr;
-          __nv_bfloat16* hb = ep.hb ? ep.hb + gm * ep.hb_ld + u0 : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 cprev = cp ? *reinterpret_cast<const float4*>(cp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float cpv[4] = {cprev.x, cprev.y, cprev.z, cprev.w};
-            float cn[4], hn[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float ig = sigmoid_f(g4[0][j + e]), fg = sigmoid_f(g4[1][j + e]);
-              const float gg = tanhf(g4[2][j + e]), og = sigmoid_f(g4[3][j + e]);
-              g4[0][j + e] = ig; g4[1][j + e] = fg; g4[2][j + e] = gg; g4[3][j + e] = og;
-              cn[e] = fg * cpv[e] + ig * gg;
-              hn[e] = og * tanhf(cn[e]);
-            }
-            *reinterpret_cast<float4*>(co + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            if (h1) *reinterpret_cast<float4*>(h1 + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            if (h2) *reinterpret_cast<float4*>(h2 + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            if (hb) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(hn[0], hn[1]), p1 = __floats2bfloat162_rn(hn[2], hn[3]);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&p0);
-              pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              *reinterpret_cast<uint2*>(hb + j) = pk;
-            }
-          }
-          if (actr) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(actr + c * 32 + j) = make_float4(g4[c][j], g4[c][j + 1], g4[c][j + 2], g4[c][j + 3]);
-          }
-        }
-      }
-      if (splits > 1) {
-        epi_bar_sync();
-        if (row == 0) ep.counters[tile_id] = 0u;   // ready for the next launch on this stream
+        for (int j = 0; j < 32; j += 4)
+          dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                    __uint_as_float(v[j + 3]));
       }
     }
     tc_fence_before();
+  }
+  if (splits > 1) {
+    // Reduce across the cluster (the S CTAs of one output tile) through distributed shared memory: CTA z owns
+    // rows [z*128/S, (z+1)*128/S) of the tile, reads that row block from all S partials in rank order
+    // (deterministic), and runs the epilogue for it.
+    cluster_arrive();
+    cluster_wait();
+    if (warp >= 2) {
+      constexpr int RS = BN + 4;
+      const int te = threadIdx.x - 64;                       // 0..127
+      const int rows_per = TC_BM / splits;
+      const int rl = te / splits, cgp = te - rl * splits;    // 128 threads = rows_per x S column groups
+      const int row = z * rows_per + rl;
+      const int64_t gm = (int64_t)m0 + row;
+      const uint32_t red_base = smem_base + (uint32_t)(row * RS) * 4u;
+      if constexpr (MODE == TC_MODE_PLAIN) {
+        constexpr int MAXC = BN / 2;                         // columns per thread at S = 2
+        const int ncol = BN / splits, c0 = cgp * ncol;
+        float o[MAXC];
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) o[j] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s >= splits) break;
+          const uint32_t src = mapa_cluster(red_base + (uint32_t)c0 * 4u, (uint32_t)s);
+#pragma unroll
+          for (int j = 0; j < MAXC; j += 4) {
+            if (j < ncol) {
+              const float4 t = ld_dsmem_v4(src + (uint32_t)j * 4u);
+              o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
+            }
+          }
+        }
+        if (gm < M) plain_store<MAXC>(ep, gm, n0 + c0, N, o, ncol);
+      } else {
+        // cell: thread owns units [u0, u0 + 32/S) of its row, all four gates
+        const int upt = 32 / splits, u0 = cgp * upt;
+        float g4[4][16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g4[g][j] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s >= splits) break;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t src = mapa_cluster(red_base + (uint32_t)(g * 32 + u0) * 4u, (uint32_t)s);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (j < upt) {
+                const float4 t = ld_dsmem_v4(src + (uint32_t)j * 4u);
+                g4[g][j] += t.x; g4[g][j + 1] += t.y; g4[g][j + 2] += t.z; g4[g][j + 3] += t.w;
+              }
+            }
+          }
+        }
+        if (gm < M) {
+          if (upt == 16) cell_store<16>(ep, gm, blockIdx.x, u0, g4);
+          else if (upt == 8) cell_store<8>(ep, gm, blockIdx.x, u0, g4);
+          else cell_store<4>(ep, gm, blockIdx.x, u0, g4);
+        }
+      }
+    }
+    cluster_arrive();                                        // nobody may leave while its partial is being read
+    cluster_wait();
   }
   __syncthreads();
   if (warp == 1) {
@@ -406,32 +473,6 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
   return 0;
 }
 
-// ------------------------------------------------------------------ host: split-K scratch (per device x stream)
-constexpr size_t kSplitWsBytes = 48u << 20;
-constexpr int kSplitCounters = 4096;
-struct SplitScratch {
-  float* ws;
-  unsigned* counters;
-};
-static int get_split_scratch(cudaStream_t st, SplitScratch* out) {
-  static std::mutex mu;
-  static std::unordered_map<uint64_t, SplitScratch> pool;
-  int dev = 0;
-  MVC_CUDA(cudaGetDevice(&dev));
-  const uint64_t key = (reinterpret_cast<uint64_t>(st) << 8) ^ (uint64_t)dev;
-  std::lock_guard<std::mutex> lk(mu);
-  auto it = pool.find(key);
-  if (it == pool.end()) {
-    SplitScratch s{};
-    MVC_CUDA(cudaMalloc(&s.ws, kSplitWsBytes));
-    MVC_CUDA(cudaMalloc(&s.counters, sizeof(unsigned) * kSplitCounters));
-    MVC_CUDA(cudaMemset(s.counters, 0, sizeof(unsigned) * kSplitCounters));
-    it = pool.emplace(key, s).first;
-  }
-  *out = it->second;
-  return 0;
-}
-
 template <int BN, int STAGES, int MODE>
 static int launch_tc(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, TcEpilogue ep,
                      int splits, bool pdl, cudaStream_t st) {
@@ -446,29 +487,59 @@ static int launch_tc(int M, int N, int K, const void* A, int64_t lda, const void
     configured = true;
   }
   const dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(M, TC_BM), (unsigned)splits);
-  if (splits > 1) {
-    SplitScratch sc;
-    MVC_TRY(get_split_scratch(st, &sc));
-    const size_t need = (size_t)grid.x * grid.y * splits * BN * TC_BM * sizeof(float);
-    MVC_CHECK(need <= kSplitWsBytes && (size_t)grid.x * grid.y <= (size_t)kSplitCounters,
-              "tcgen05 GEMM split-K scratch too small for %dx%dx%d", M, N, K);
-    ep.ws = sc.ws;
-    ep.counters = sc.counters;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (splits > 1) {           // the S K-splits of one output tile form a thread-block cluster
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = (unsigned)splits;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   ProfScope prof(PK_GEMM_TC, M, N, K, st);
   MVC_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, ep));
   MVC_LAUNCH_CHECK();
   return 0;
+}
+
+// How many clusters of `cs` CTAs of this kernel can be resident at once (GPC packing makes this less than
+// 148 / cs: e.g. 15 clusters of 8).  Cached per (kernel, cluster size).
+template <int BN, int STAGES, int MODE>
+static int max_active_clusters(int cs) {
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cs <= 1) return kNumSMs;
+  if (cache[cs] > 0) return cache[cs];
+  auto kern = gemm_bf16_tc_kernel<BN, STAGES, MODE>;
+  constexpr int smem = TcSmem<BN, STAGES>::TOTAL;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1, 1, (unsigned)cs);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)cs;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = kNumSMs / cs - 3;       // conservative guess
+  }
+  cache[cs] = n;
+  return n;
 }
 
 bool pdl_enabled() {
@@ -495,21 +566,24 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
   const int64_t mt = cdiv(M, TC_BM);
   const int nkb = (int)cdiv(K, TC_BK);
   const bool can_split = !(flags & TC_FLAG_NO_SPLIT);
-  auto splits_for = [&](int64_t tiles) {
-    if (!can_split || tiles >= 112) return 1;
-    int s = (int)(kNumSMs / tiles);
-    if (s > 8) s = 8;
-    if (s > nkb) s = nkb;
-    return s < 1 ? 1 : s;
+  // K-splits per output tile = cluster size: a power of two <= 8 (portable cluster limit), <= #K blocks,
+  // such that all clusters are resident in ONE wave (the hardware packs clusters per GPC)
+  auto splits_for = [&](int64_t tiles, auto max_clusters) {
+    if (!can_split || tiles >= 96) return 1;
+    int s = 1;
+    while (s < 8 && 2 * s <= nkb && tiles <= max_clusters(2 * s)) s *= 2;
+    return s;
   };
   if (ep.mode == TC_MODE_CELL) {
     MVC_CHECK(N % 128 == 0 && N == 4 * ep.H, "fused LSTM-cell epilogue needs N == 4H with H %% 32 == 0 (N=%d H=%d)", N, ep.H);
-    const int s = splits_for(mt * (N / 128));
+    const int s = splits_for(mt * (N / 128), max_active_clusters<128, 4, TC_MODE_CELL>);
     return launch_tc<128, 4, TC_MODE_CELL>(M, N, K, A, lda, B, ldb, ep, s, pdl, st);
   }
   const int64_t t128 = mt * cdiv(N, 128), t64 = mt * cdiv(N, 64), t32 = mt * cdiv(N, 32);
   // widest tile whose CTA count (tiles x K-splits) covers most of the 148 SMs
-  const int s128 = splits_for(t128), s64 = splits_for(t64), s32 = splits_for(t32);
+  const int s128 = splits_for(t128, max_active_clusters<128, 4, TC_MODE_PLAIN>);
+  const int s64 = splits_for(t64, max_active_clusters<64, 6, TC_MODE_PLAIN>);
+  const int s32 = splits_for(t32, max_active_clusters<32, 8, TC_MODE_PLAIN>);
   if (t128 * s128 >= 96) return launch_tc<128, 4, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s128, pdl, st);
   if (t64 * s64 >= 96) return launch_tc<64, 6, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s64, pdl, st);
   return launch_tc<32, 8, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s32, pdl, st);

@@ -21,9 +21,6 @@ struct TcEpilogue {
   const float* bias;          // also the (permuted) gate bias in cell mode, may be null
   __nv_bfloat16* Cb;
   int64_t ldcb;
-  // split-K scratch (filled in by the launcher)
-  float* ws;
-  unsigned* counters;
   // fused LSTM cell (mode == TC_MODE_CELL): N = 4H, columns permuted (j/32)*128 + gate*32 + j%32
   int H;
   const float* gx;            // [M,4H] hoisted input projection (permuted columns), ld gx_ld, may be null
