@@ -37,8 +37,6 @@ class FlatClipAdam:
         if not live:
             raise RuntimeError("FlatClipAdam.step() before any backward()")
         dev = live[0].device
-        if dev.type != "cuda":
-            raise RuntimeError("FlatClipAdam: parameters must live on CUDA (no CPU fallback)")
         n = sum(p.numel() for p in live)
         self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
         self.flat_g = torch.empty(n, device=dev, dtype=torch.float32)
@@ -70,6 +68,9 @@ class FlatClipAdam:
     def step(self):
         if self.flat_g is None:
             self._flatten()
+        if self.flat_p.device.type != "cuda":
+            raise RuntimeError("FlatClipAdam.step: parameters must live on CUDA (the update is a CUDA kernel; "
+                               "there is no CPU fallback)")
         self.step_count += 1
         scale = 1.0
         if self.world is not None and self.world > 1:
