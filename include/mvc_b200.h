@@ -51,6 +51,9 @@ long long mvc_launch_count(void);
  * 8 fused recurrence step, 9 caption loss, 10 clip+Adam. */
 int mvc_prof_arm(int kid, int m, int n, int k);
 int mvc_prof_collect(double* total_ms, long long* launches);
+/* Debug: device buffer (>= 10 int64 per loop step) that receives SM-clock timestamps of the phases of the
+ * persistent recurrence kernel (CTA 0); NULL switches it off. */
+int mvc_debug_set_recur_prof(long long* dev_buf);
 
 /* ------------------------------------------------------------------ */
 /* Building-block kernels (each is unit-tested against the oracle)     */
@@ -127,7 +130,7 @@ int mvc_lstm_cell_fwd(int B, int H, const float* pre, const float* gx, int64_t g
  * TMEM, and the cell update (bias / hoisted-projection addends, sigmoid/tanh, c and h) in the GEMM
  * epilogue; K is split across CTAs and reduced deterministically.  features_captioning.py:84.
  *   x [B,K] bf16 (ld ldx);  w_packed [4H,K] bf16 = the gate rows in TILE-INTERLEAVED order: packed
- *   row (j/32)*128 + g*32 + j%32 is nn.LSTM row g*H + j (g = i,f,g,o) -- mvc_pack_gate_rows_bf16
+ *   row (j/16)*64 + g*16 + j%16 is nn.LSTM row g*H + j (g = i,f,g,o) -- mvc_pack_gate_rows_bf16
  *   builds it from an fp32 [4H,C] weight (ld ldw), zero-padding C to Cp (multiple of 8);
  *   bias_packed [4H], gx_packed [B,4H] (optional addends) and act_packed [B,4H] (activated gates,
  *   optional output) use the same column order; c_prev/c_out [B,H]; h_out fp32 (ld h_ld) and

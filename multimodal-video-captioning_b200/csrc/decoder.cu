@@ -15,6 +15,7 @@
 //   * backward: every weight gradient is one GEMM over all S*B rows after the
 //     time loop; only d[ctx;h] = dgates.[W_ih[:,E:]|W_hh], the attention
 //     backward and dh += dwq.W stay inside the loop.
+#include "recur.cuh"
 #include "step.cuh"
 
 namespace mvc {
@@ -42,6 +43,7 @@ struct DecWs {
   float* gx;      // [S*B, 4H]
   float* embtab;  // [V, 4H]
   float* hzero;   // [B, H] zeros (c_0 / fp32 h_0)
+  unsigned* sync; // grid-barrier counter of the persistent recurrence kernel
   size_t bytes;
 };
 
@@ -74,6 +76,7 @@ static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
   w.gx = ar.take<float>(S * B * 4 * H);
   w.embtab = ar.take<float>(V * 4 * H);
   w.hzero = ar.take<float>(B * H);
+  w.sync = ar.take<unsigned>(64);
   w.bytes = ar.off + 256;
   return w;
 }
@@ -312,7 +315,19 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
   }
 
   const StepCfg cfg = dec_cfg(d, p, w, nullptr);
-  for (int s = 0; s < S; ++s) {
+  const bool persistent = cfg.perm && recur_fwd_supported(B, T, F, H, A);
+  if (persistent && all_tf) {
+    // the whole teacher-forced time loop in ONE persistent cluster-cooperative launch (recur_fwd.cu)
+    RecurFwdParams rp{};
+    rp.B = B; rp.T = T; rp.F = F; rp.H = H; rp.A = A; rp.K = F + H; rp.S = S; rp.s0 = 0; rp.s1 = S;
+    rp.feats = (const __nv_bfloat16*)w.feats; rp.uk = w.uk; rp.attW = (const __nv_bfloat16*)w.W;
+    rp.att_b = p->att_b; rp.att_w = p->att_w;
+    rp.gx = w.gx; rp.embtab = nullptr; rp.tokens = nullptr; rp.cell_bias = nullptr;
+    rp.xh = (__nv_bfloat16*)w.xh; rp.c = w.c; rp.act = w.act; rp.alpha = w.alpha; rp.wq_out = w.wq;
+    rp.out_hid = out_hid; rp.sync = w.sync;
+    MVC_TRY(recur_fwd_launch(rp, w.wcat, st));
+  }
+  for (int s = 0; s < S && !(persistent && all_tf); ++s) {
     const int t = s + 1;
     StepFwd io{};
     io.rows = B;

@@ -28,7 +28,7 @@
 // Epilogues:
 //   plain : + bias, + beta*C, fp32 store, optional bf16 copy;
 //   cell  : BN = 128 and the weight rows are permuted so that one tile holds gates i,f,g,o of 32
-//           hidden units (col = (j/32)*128 + gate*32 + j%32): the epilogue adds the hoisted input
+//           hidden units (col = (j/16)*64 + gate*16 + j%16): the epilogue adds the hoisted input
 //           projection / embedding-table row / bias, applies sigmoid/tanh, updates c and h and
 //           writes h in fp32 and bf16 -- the LSTM step never materialises pre-activations.
 //
@@ -139,23 +139,24 @@ template <int NU, typename Arr>
 __device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int tile, int u0, Arr& g) {
   const int H = ep.H;
   const int n0 = tile * 128, ug = tile * 32 + u0;
-  const float* gxr = ep.gx ? ep.gx + gm * ep.gx_ld + n0 + u0 : nullptr;
-  const float* etr = ep.embtab ? ep.embtab + ep.tokens[gm] * (int64_t)(4 * H) + n0 + u0 : nullptr;
-  const float* br = ep.bias ? ep.bias + n0 + u0 : nullptr;
+  const float* gxr = ep.gx ? ep.gx + gm * ep.gx_ld + n0 : nullptr;
+  const float* etr = ep.embtab ? ep.embtab + ep.tokens[gm] * (int64_t)(4 * H) + n0 : nullptr;
+  const float* br = ep.bias ? ep.bias + n0 : nullptr;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
 #pragma unroll
     for (int j = 0; j < NU; j += 4) {
+      const int lc = gate_lcol(c, u0 + j);          // 4 consecutive units stay inside one 16-unit block
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gxr) { const float4 t = *reinterpret_cast<const float4*>(gxr + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-      if (etr) { const float4 t = *reinterpret_cast<const float4*>(etr + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-      if (br) { const float4 t = *reinterpret_cast<const float4*>(br + c * 32 + j); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+      if (gxr) { const float4 t = *reinterpret_cast<const float4*>(gxr + lc); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+      if (etr) { const float4 t = *reinterpret_cast<const float4*>(etr + lc); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+      if (br) { const float4 t = *reinterpret_cast<const float4*>(br + lc); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
       g[c][j] += a.x; g[c][j + 1] += a.y; g[c][j + 2] += a.z; g[c][j + 3] += a.w;
     }
   }
   const float* cp = ep.c_prev ? ep.c_prev + gm * H + ug : nullptr;
   float* co = ep.c_out + gm * H + ug;
-  float* actr = ep.act ? ep.act + gm * (int64_t)(4 * H) + n0 + u0 : nullptr;
+  float* actr = ep.act ? ep.act + gm * (int64_t)(4 * H) + n0 : nullptr;
   float* h1 = ep.h32 ? ep.h32 + gm * ep.h_ld + ug : nullptr;
   float* h2 = ep.h32b ? ep.h32b + gm * ep.h2_ld + ug : nullptr;
   __nv_bfloat16* hb = ep.hb ? ep.hb + gm * ep.hb_ld + ug : nullptr;
@@ -188,7 +189,7 @@ __device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int
     for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int j = 0; j < NU; j += 4)
-        *reinterpret_cast<float4*>(actr + c * 32 + j) = make_float4(g[c][j], g[c][j + 1], g[c][j + 2], g[c][j + 3]);
+        *reinterpret_cast<float4*>(actr + gate_lcol(c, u0 + j)) = make_float4(g[c][j], g[c][j + 1], g[c][j + 2], g[c][j + 3]);
   }
 }
 
@@ -310,8 +311,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
           tmem_ld32(trow + (uint32_t)(c * 32), v);
+          // tile column c*32 + j  ->  unit block c/2, gate (c%2)*2 + j/16, unit j%16
 #pragma unroll
-          for (int j = 0; j < 32; ++j) g4[c][j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) g4[(c & 1) * 2 + (j >> 4)][(c >> 1) * 16 + (j & 15)] = __uint_as_float(v[j]);
         }
         if (gm < M) cell_store<32>(ep, gm, blockIdx.x, 0, g4);
       }
@@ -379,7 +381,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (s >= splits) break;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const uint32_t src = mapa_cluster(red_base + (uint32_t)(g * 32 + u0) * 4u, (uint32_t)s);
+            const uint32_t src = mapa_cluster(red_base + (uint32_t)gate_lcol(g, u0) * 4u, (uint32_t)s);
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               if (j < upt) {

@@ -1,0 +1,636 @@
+// recur_fwd.cu -- the SA-LSTM decoder recurrence as ONE persistent, cluster-cooperative kernel.
+//
+// Reference loop: FeaturesCaptioning.forward_sentence / forward_word (features_captioning.py:77-119):
+// per caption position  h -> attention -> [ctx ; h] . W^T -> LSTM cell -> h'.  A chain of launches
+// pays 7-10 us of launch / setup / first-load latency per kernel around <= 2 us of work (profiles/
+// bench_r1.md); here the whole time loop runs inside one launch:
+//
+//   grid   = (4H/64) clusters x 4 CTAs  (H = 512 -> 32 clusters = 128 CTAs, one per SM, all co-resident)
+//   CTA (cluster c, rank r) owns, for the whole kernel, in SHARED MEMORY:
+//       * wcat[64 gate columns of units [16c,16c+16), K-slice r]  (<= 11 x 64 K-columns, bf16, 128B-swizzled
+//         UMMA operand, loaded once by TMA)                                    -- the gate-GEMM B operand
+//       * attention.W[units [64r, 64r+64), :]                                  -- the query projection
+//     in REGISTERS the U.k rows of "its" batch row b = 4c + r, and in TENSOR MEMORY that row's keys.
+//   per step s:
+//     phase A (cluster-local, rows 4c..4c+3):
+//        wq[4 rows, 64r..64r+64) = h_s . W_slice^T on CUDA cores, scattered to the row owners through
+//        DSMEM; cluster barrier; each CTA finishes ITS row: scores (tanh.approx), softmax over T, and the
+//        context sum straight out of TENSOR MEMORY: the row's keys [T x F] bf16 (191 KB) are loop invariant
+//        and live in the 448 TMEM columns the accumulator does not use (lane L holds features
+//        [18L, 18L+18) of every frame), written once with tcgen05.st and read with tcgen05.ld every step --
+//        zero L2 / HBM traffic for the keys after the first step; ctx_s -> xh[s][b][:F] (bf16).
+//     grid barrier
+//     phase G: D[128, 64] = xh[s][:, K-slice r] . wcat_slice^T  (tcgen05.mma M=128 N=64, A streamed by TMA
+//        through a 4-stage ring, B resident, accumulator in TMEM); partial tile parked in the CTA's own
+//        (idle) ring; cluster barrier; rank r pulls rows [32r, 32r+32) of the 4 K-slice partials through
+//        DSMEM, sums them in rank order (deterministic) and applies the LSTM cell: + hoisted input projection / embedding-table row,
+//        sigma/tanh, c', h' -> c[s+1], act[s], out_hid[s+1] (fp32), xh[s+1][:, F:] (bf16).
+//     grid barrier
+// Grid barrier = one release-add + acquire-spin on a global counter per CTA (bounded: traps, never hangs).
+//
+// Supported: bf16 path, B <= 128, H % 16 == 0 and H <= 512, A == 256, T <= 48, F % 8 == 0 with
+// ceil(F/256) in {1, 8, 9} (F = 128 / 2048 / 2176), T * ceil(F/256) <= 448, F + H <= 2816.  Anything else takes the launch-chain path (step.cuh).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "ptx.cuh"
+#include "step.cuh"
+#include "recur.cuh"
+
+namespace mvc {
+
+constexpr int RF_THREADS = 320;      // warps 0-7 compute, warp 8 TMA / bulk producer, warp 9 MMA issuer
+constexpr int RF_CS = 4;             // cluster size = K splits = batch rows per cluster
+constexpr int RF_BN = 64;            // gate columns per cluster (16 units x 4 gates)
+constexpr int RF_STAGES = 4;
+constexpr int RF_STAGE_BYTES = 128 * 64 * 2;   // A stage: 128 rows x 64 bf16
+constexpr int RF_MAXKB = 11;
+constexpr int RF_B_BYTES = RF_MAXKB * RF_BN * 64 * 2;       // 90112
+constexpr int RF_RING_BYTES = RF_STAGES * RF_STAGE_BYTES;    // 65536
+constexpr int RF_KEY_COLS = 448;     // TMEM columns holding the resident keys (512 - 64 accumulator columns)
+constexpr int RF_R = 6;              // key-frame rounds per warp held in registers (T <= 48)
+constexpr int RF_PS = RF_BN + 4;     // partial tile row pitch (floats)
+
+__device__ __forceinline__ void cluster_arrive_() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_rank_() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem4_(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_dsmem4_(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_dsmem_(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  umma_bf16(tmem_d, adesc, bdesc, idesc, accum);
+}
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// All CTAs of the grid: everything written before is visible to everyone after.  `target` = arrivals expected.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v < target && clock64() - t0 > 4000000000LL) {
+        printf("mvc recur_fwd: grid barrier timed out (block %d, %u of %u)\n", blockIdx.x, v, target);
+        __trap();
+      }
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int AV, int WPL>   // AV = A / 32 bottleneck units per lane; WPL = ceil(F / 256) key words per TMEM lane per frame
+__global__ void __launch_bounds__(RF_THREADS, 1)
+recur_fwd_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ RecurFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int B = p.B, T = p.T, F = p.F, H = p.H, K = p.K;
+  constexpr int A = AV * 32;
+  constexpr int UPR = A / RF_CS;                 // query units computed per rank
+  constexpr int KCH = (RF_KEY_COLS / 64);        // TMEM key chunks of 64 columns
+  const int HP = H + 8;                          // padded pitch of the resident attention.W slice (bf16)
+
+  uint8_t* ring = smem + RF_B_BYTES;                              // A stages | partial tile
+  __nv_bfloat16* sWatt = reinterpret_cast<__nv_bfloat16*>(ring + RF_RING_BYTES);     // [UPR][HP]
+  __nv_bfloat16* sHb = sWatt + (size_t)UPR * HP;                                    // [4][HP] h rows of the cluster
+  float* sQ = reinterpret_cast<float*>(sHb + (size_t)RF_CS * HP);  // [A]  wq of my row (written by the 4 ranks)
+  float* sWv = sQ + A;                                            // [A]  attention.w
+  float* sBias = sWv + A;                                         // [A]  attention.b
+  float* sE = sBias + A;                                          // [64] scores -> alpha (zero beyond T)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + 64);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (RF_STAGES + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * RF_STAGES);
+  const uint32_t w_bar = bar0 + 8u * (2 * RF_STAGES + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RF_STAGES + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_rank_();
+  const int cl = blockIdx.x / RF_CS;
+  const int brow = blockIdx.x;                   // the batch row this CTA finishes in phase A
+  const bool has_row = brow < B;
+  const int n0 = cl * RF_BN;                     // first gate column of this cluster
+  const int nkb_all = (K + 63) / 64;
+  const int kb0 = nkb_all * rank / RF_CS, kb1 = nkb_all * (rank + 1) / RF_CS;
+  const int nkb = kb1 - kb0;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring_base = smem_base + RF_B_BYTES;
+
+  // ---------------------------------------------------------------- one-time setup
+  if (warp == 8 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < RF_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) {                               // all 512 TMEM columns: 64 accumulator + 448 resident keys
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's lane quarter
+  const uint32_t tmem_keys = tmem_lane + RF_BN;                                  // key columns start after the accumulator
+
+  if (warp == 8 && lane == 0) {                  // resident gate-weight slice, once
+    mbar_expect_tx(w_bar, (uint32_t)nkb * (RF_BN * 64 * 2));
+    for (int i = 0; i < nkb; ++i) tma_load_2d(smem_base + i * (RF_BN * 64 * 2), &map_w, w_bar, (kb0 + i) * 64, n0);
+  }
+  float ur[RF_R][AV];                            // U.k rows of my batch row: loop invariant -> registers
+  if (warp < 8) {
+    // resident attention.W slice: units [rank*UPR, +UPR), bf16, pitch HP
+    const int vec_per_row = H / 8;
+    for (int i = tid; i < UPR * vec_per_row; i += 256) {
+      const int u = i / vec_per_row, k8 = i - u * vec_per_row;
+      const uint4 v = *reinterpret_cast<const uint4*>(p.attW + (size_t)(rank * UPR + u) * H + k8 * 8);
+      *reinterpret_cast<uint4*>(sWatt + (size_t)u * HP + k8 * 8) = v;
+    }
+    for (int i = tid; i < A; i += 256) { sWv[i] = p.att_w[i]; sBias[i] = p.att_b[i]; }
+    if (tid < 64) sE[tid] = 0.f;
+    const float* ukb = p.uk + (size_t)(has_row ? brow : 0) * T * A;
+#pragma unroll
+    for (int r = 0; r < RF_R; ++r) {
+      const int t = warp + r * 8;
+#pragma unroll
+      for (int k = 0; k < AV; ++k) ur[r][k] = (t < T) ? __ldg(ukb + (size_t)t * A + lane + 32 * k) : 0.f;
+    }
+  }
+  if (warp < 4) {
+    // Keys of my batch row -> TMEM, resident for the whole kernel: lane L keeps, for every frame t, the WPL
+    // words (2*WPL bf16 features [2*WPL*L, +2*WPL)) at columns [t*WPL, +WPL).  Loop invariant across steps,
+    // so the per-step context sum never touches L2 / HBM.
+    const int L = tid;                           // TMEM lane
+    const uint32_t* krow = reinterpret_cast<const uint32_t*>(p.feats + (size_t)(has_row ? brow : 0) * T * F);
+    const int fw = F / 2;                        // 32-bit words per key row
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      if (c * 64 < T * WPL) {
+        uint32_t v[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const int w = c * 64 + j;              // compile-time
+          const int t = w / WPL, k = w % WPL;
+          const int word = L * WPL + k;
+          v[j] = (has_row && t < T && word < fw) ? __ldg(krow + (size_t)t * fw + word) : 0u;
+        }
+        tmem_st64(tmem_keys + (uint32_t)(c * 64), v);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+
+  unsigned gb = 0;                               // grid barriers passed
+  uint32_t ring_it = 0;                          // A-stage ring iterations issued / consumed (same in every role)
+  const unsigned nctas = gridDim.x;
+
+  // optional phase timestamps (SM clock) of CTA 0, 10 per step: debugging / profiles only
+  long long* prof = (p.prof && blockIdx.x == 0 && tid == 0) ? p.prof : nullptr;
+#define RF_STAMP(i) do { if (prof) prof[step_i * 10 + (i)] = clock64(); } while (0)
+  for (int s = p.s0; s < p.s1; ++s) {
+    const int step_i = s - p.s0;
+    RF_STAMP(0);
+    // ================================================================= phase A: attention
+    if (warp < 8) {
+      // A1: h_s of the cluster's four rows -> sHb (bf16, as stored); one 16-byte copy per thread
+      for (int i = tid; i < RF_CS * H / 8; i += 256) {
+        const int rr = i / (H / 8), k8 = i - rr * (H / 8);
+        const int b2 = cl * RF_CS + rr;
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (b2 < B) raw = __ldcg(reinterpret_cast<const uint4*>(p.xh + ((size_t)s * B + b2) * K + F) + k8);
+        *reinterpret_cast<uint4*>(sHb + (size_t)rr * HP + k8 * 8) = raw;
+      }
+      compute_bar();
+      // A2: wq[4 rows][rank*UPR + 8*warp + 0..7] = h . W_slice^T with mma.sync m16n8k16 (rows 4..15 of the A
+      // tile are zero): warp w owns 8 query units, 32 k-steps of one HMMA each.
+      if (warp * 8 < UPR) {
+        const int r4 = lane >> 2, kq = (lane & 3) * 2;
+        const __nv_bfloat16* arow = sHb + (size_t)(r4 & 3) * HP + kq;
+        const __nv_bfloat16* brow = sWatt + (size_t)(warp * 8 + r4) * HP + kq;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        const bool live = r4 < RF_CS;
+#pragma unroll 8
+        for (int k0 = 0; k0 < H; k0 += 16) {
+          const uint32_t a0 = live ? *reinterpret_cast<const uint32_t*>(arow + k0) : 0u;
+          const uint32_t a2 = live ? *reinterpret_cast<const uint32_t*>(arow + k0 + 8) : 0u;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + k0);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + k0 + 8);
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                       : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+        }
+        // A3: hand the values to the CTA that owns the row (lanes 0..15 hold rows 0..3)
+        if (live) {
+          const uint32_t dst = mapa_(smem_u32(sQ + rank * UPR + warp * 8 + kq), (uint32_t)r4);
+          st_dsmem_(dst, c0);
+          st_dsmem_(dst + 4u, c1);
+        }
+      }
+    }
+    cluster_arrive_();
+    cluster_wait_();                              // every rank's slice of my row's query has landed in sQ
+    RF_STAMP(1);
+    if (warp < 8) {
+      if (has_row) {
+        float* wq_out = p.wq_out + ((size_t)s * B + brow) * A;
+        for (int i = tid; i < A; i += 256) wq_out[i] = sQ[i];
+        float qb[AV], wv[AV];
+#pragma unroll
+        for (int k = 0; k < AV; ++k) { qb[k] = sQ[lane + 32 * k] + sBias[lane + 32 * k]; wv[k] = sWv[lane + 32 * k]; }
+#pragma unroll
+        for (int r = 0; r < RF_R; ++r) {
+          const int t = warp + r * 8;
+          if (t < T) {
+            float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < AV; k += 2) {
+              e0 = fmaf(wv[k], tanh_fast(qb[k] + ur[r][k]), e0);
+              if (k + 1 < AV) e1 = fmaf(wv[k + 1], tanh_fast(qb[k + 1] + ur[r][k + 1]), e1);
+            }
+            const float e = warp_sum(e0 + e1);
+            if (lane == 0) sE[t] = e;
+          }
+        }
+      }
+      compute_bar();
+      if (has_row && warp == 0) {                 // softmax over T <= 48 frames: one warp, two elements per lane
+        const float e0 = lane < T ? sE[lane] : -INFINITY, e1 = lane + 32 < T ? sE[lane + 32] : -INFINITY;
+        const float mx = warp_max(fmaxf(e0, e1));
+        const float p0 = lane < T ? __expf(e0 - mx) : 0.f, p1 = lane + 32 < T ? __expf(e1 - mx) : 0.f;
+        const float inv = 1.f / warp_sum(p0 + p1);
+        float* al = p.alpha + ((size_t)s * B + brow) * T;
+        if (lane < T) { sE[lane] = p0 * inv; al[lane] = p0 * inv; }
+        if (lane + 32 < T) { sE[lane + 32] = p1 * inv; al[lane + 32] = p1 * inv; }
+      }
+      compute_bar();
+      RF_STAMP(2);
+      {
+        // A6: ctx = sum_t alpha_t key_t straight out of TMEM: lane L owns features [2*WPL*L, +2*WPL).
+        // Warps w and w+4 share a lane quarter: even key chunks go to warps 0-3, odd ones to warps 4-7.
+        float acc[2 * WPL];
+#pragma unroll
+        for (int i = 0; i < 2 * WPL; ++i) acc[i] = 0.f;
+        const int half = warp >> 2;
+        float* sPart = reinterpret_cast<float*>(ring);            // [128][2*WPL + 1] partials of warps 4-7
+        if (has_row) {
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < KCH; ++c) {
+            if ((c & 1) == half && c * 64 < T * WPL) {
+              uint32_t v[64];
+              tmem_ld64(tmem_keys + (uint32_t)(c * 64), v);
+#pragma unroll
+              for (int j = 0; j < 64; ++j) {
+                const int w = c * 64 + j;          // compile-time
+                const int t = w / WPL, k = w % WPL;
+                if (t < 64) {
+                  const float al = sE[t];          // zero beyond T (and the TMEM words there are zero too)
+                  const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[j]));
+                  acc[2 * k] = fmaf(al, x.x, acc[2 * k]);
+                  acc[2 * k + 1] = fmaf(al, x.y, acc[2 * k + 1]);
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          if (half == 1) {
+#pragma unroll
+            for (int i = 0; i < 2 * WPL; ++i) sPart[(tid - 128) * (2 * WPL + 1) + i] = acc[i];
+          }
+        }
+        compute_bar();
+        if (has_row && half == 0) {
+          uint32_t* ctx = reinterpret_cast<uint32_t*>(p.xh + ((size_t)s * B + brow) * K);
+          const int fw = F / 2;
+#pragma unroll
+          for (int k = 0; k < WPL; ++k) {
+            const int word = tid * WPL + k;
+            if (word < fw) {
+              const float x0 = acc[2 * k] + sPart[tid * (2 * WPL + 1) + 2 * k];
+              const float x1 = acc[2 * k + 1] + sPart[tid * (2 * WPL + 1) + 2 * k + 1];
+              __nv_bfloat162 q = __floats2bfloat162_rn(x0, x1);
+              ctx[word] = *reinterpret_cast<uint32_t*>(&q);
+            }
+          }
+        }
+      }
+    }
+    RF_STAMP(3);
+    grid_barrier(p.sync, (++gb) * nctas);          // ctx of every row is in xh[s]
+    RF_STAMP(4);
+
+    // ================================================================= phase G: gate GEMM + LSTM cell
+    // reducer mapping (warps 0-3): rank r finishes rows [32r, 32r+32), thread = (row, 4 units)
+    const int rl = (tid & 127) >> 2, ug = tid & 3;
+    const int row = rank * 32 + rl;
+    const int u0 = ug * 4;
+    const size_t grow = (size_t)s * B + row;
+    float4 add4[4];                               // gate addends (hoisted projection / embedding row / bias)
+    float4 cp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 8) {
+      if (lane == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");     // ctx / h were written with generic stores by other CTAs
+        uint32_t it = ring_it;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int stage = (int)(it % RF_STAGES);
+          const uint32_t par = (it / RF_STAGES) & 1u;
+          mbar_wait(empty_bar(stage), par ^ 1u);
+          mbar_expect_tx(full_bar(stage), RF_STAGE_BYTES);
+          tma_load_2d(ring_base + stage * RF_STAGE_BYTES, &map_xh, full_bar(stage), (kb0 + i) * 64, s * B);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 9) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = idesc_bf16(128, RF_BN);
+        if (step_i == 0) mbar_wait(w_bar, 0);
+        uint32_t it = ring_it;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int stage = (int)(it % RF_STAGES);
+          const uint32_t par = (it / RF_STAGES) & 1u;
+          mbar_wait(full_bar(stage), par);
+          tc_fence_after();
+          const uint64_t adesc = sw128_desc(ring_base + stage * RF_STAGE_BYTES);
+          const uint64_t bdesc = sw128_desc(smem_base + i * (RF_BN * 64 * 2));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+        }
+        umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    } else if (warp < 4) {
+      // the cell's addends do not depend on the GEMM: fetch them while it runs
+      if (row < B) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = n0 + g * 16 + u0;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.gx) { const float4 t4 = __ldcs(reinterpret_cast<const float4*>(p.gx + grow * (size_t)(4 * H) + col)); a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w; }
+          if (p.embtab) {
+            const float4 t4 = *reinterpret_cast<const float4*>(p.embtab + (size_t)p.tokens[grow] * (4 * H) + col);
+            a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w;
+          }
+          if (p.cell_bias) { const float4 t4 = *reinterpret_cast<const float4*>(p.cell_bias + col); a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w; }
+          add4[g] = a;
+        }
+        cp4 = __ldcg(reinterpret_cast<const float4*>(p.c + grow * H + cl * 16 + u0));
+      }
+      // park the partial tile [128 x 64] (this K-slice) in this CTA's own operand ring (idle: every MMA that read
+      // it has completed), pitch 68 floats.  (Pushing rows into the finishing rank's ring instead would race with
+      // that rank's still-running TMA / MMA pipeline.)
+      mbar_wait(tmem_full_bar, (uint32_t)(step_i & 1));
+      tc_fence_after();
+      const int prow = warp * 32 + lane;
+      float* part = reinterpret_cast<float*>(ring);
+#pragma unroll
+      for (int c = 0; c < RF_BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_lane + (uint32_t)(c * 32), v);
+        float4* dst = reinterpret_cast<float4*>(part + (size_t)prow * RF_PS + c * 32);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                    __uint_as_float(v[j + 3]));
+      }
+      tc_fence_before();
+    }
+    ring_it += (uint32_t)nkb;
+    RF_STAMP(5);
+    cluster_arrive_();
+    cluster_wait_();                              // the four K-slice partials of this cluster's tile are parked
+    RF_STAMP(6);
+    if (warp < 4) {
+      float g4[4][4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g4[g][j] = 0.f;
+      const uint32_t pbase = ring_base + (uint32_t)(row * RF_PS) * 4u;
+#pragma unroll
+      for (int sr = 0; sr < RF_CS; ++sr) {          // source ranks in order: deterministic
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 t4 = ld_dsmem4_(mapa_(pbase + (uint32_t)(g * 16 + u0) * 4u, (uint32_t)sr));
+          g4[g][0] += t4.x; g4[g][1] += t4.y; g4[g][2] += t4.z; g4[g][3] += t4.w;
+        }
+      }
+      if (row < B) {
+        const int ug0 = cl * 16 + u0;             // global hidden unit
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { g4[g][0] += add4[g].x; g4[g][1] += add4[g].y; g4[g][2] += add4[g].z; g4[g][3] += add4[g].w; }
+        const float cpv[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+        float cn[4], hn[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float ig = sigmoid_f(g4[0][e]), fg = sigmoid_f(g4[1][e]), gg = tanhf(g4[2][e]), og = sigmoid_f(g4[3][e]);
+          g4[0][e] = ig; g4[1][e] = fg; g4[2][e] = gg; g4[3][e] = og;
+          cn[e] = fg * cpv[e] + ig * gg;
+          hn[e] = og * tanhf(cn[e]);
+        }
+        const size_t nrow = (size_t)(s + 1) * B + row;
+        *reinterpret_cast<float4*>(p.c + nrow * H + ug0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        if (p.out_hid) *reinterpret_cast<float4*>(p.out_hid + nrow * H + ug0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        {
+          __nv_bfloat162 q0 = __floats2bfloat162_rn(hn[0], hn[1]), q1 = __floats2bfloat162_rn(hn[2], hn[3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&q0);
+          pk.y = *reinterpret_cast<uint32_t*>(&q1);
+          *reinterpret_cast<uint2*>(p.xh + nrow * K + F + ug0) = pk;
+        }
+        if (p.act) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(p.act + grow * (size_t)(4 * H) + n0 + g * 16 + u0) =
+                make_float4(g4[g][0], g4[g][1], g4[g][2], g4[g][3]);
+        }
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");   // ring: generic accesses above, TMA writes next
+    }
+    RF_STAMP(7);
+    grid_barrier(p.sync, (++gb) * nctas);          // h_{s+1}, c_{s+1} complete; partial tiles consumed
+    RF_STAMP(8);
+  }
+#undef RF_STAMP
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn2 encode_fn2() {
+  static EncodeTiledFn2 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn2>(q);
+  });
+  return fn;
+}
+static int make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+  EncodeTiledFn2 enc = encode_fn2();
+  MVC_CHECK(enc, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MVC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+static size_t recur_fwd_smem(int H, int A) {
+  const size_t upr = (size_t)A / RF_CS;
+  return 1024 + RF_B_BYTES + RF_RING_BYTES + (upr + RF_CS) * (H + 8) * 2 + sizeof(float) * (3 * (size_t)A + 64) +
+         8 * (2 * RF_STAGES + 2) + 16;
+}
+
+static inline int key_wpl(int F) { return (F + 255) / 256; }
+static const void* recur_kernel_for(int A, int F) {
+  if (A != 256) return nullptr;
+  switch (key_wpl(F)) {
+    case 9: return (const void*)recur_fwd_kernel<8, 9>;      // F = 2176 (audio + visual)
+    case 8: return (const void*)recur_fwd_kernel<8, 8>;      // F = 2048 (visual)
+    case 1: return (const void*)recur_fwd_kernel<8, 1>;      // F <= 256 (audio)
+    default: return nullptr;
+  }
+}
+
+bool recur_fwd_supported(int B, int T, int F, int H, int A) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("MVC_B200_PERSISTENT");
+    disabled = (e && e[0] == '0') ? 1 : 0;
+  }
+  if (disabled) return false;
+  if (!(B >= 1 && B <= 128 && T >= 1 && T <= 8 * RF_R && F % 8 == 0 && H % 16 == 0 && H >= 64 && H <= 512)) return false;
+  if (!recur_kernel_for(A, F)) return false;
+  if ((F + H + 63) / 64 > RF_CS * RF_MAXKB) return false;
+  if (T * key_wpl(F) > RF_KEY_COLS) return false;              // keys must fit in the free TMEM columns
+  if (recur_fwd_smem(H, A) > 227 * 1024) return false;
+  // all clusters must be co-resident (the grid barrier spins)
+  static std::mutex mu;
+  static int max_clusters[3] = {-1, -1, -1};
+  const int ki = key_wpl(F) == 9 ? 0 : (key_wpl(F) == 8 ? 1 : 2);
+  std::lock_guard<std::mutex> lk(mu);
+  if (max_clusters[ki] < 0) {
+    const void* kern = recur_kernel_for(A, F);
+    const size_t smem = 227 * 1024;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      max_clusters[ki] = 0;
+    } else {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(RF_CS);
+      cfg.blockDim = dim3(RF_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = RF_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      max_clusters[ki] = n;
+    }
+  }
+  return max_clusters[ki] >= H / 16;
+}
+
+static long long* g_recur_prof = nullptr;
+
+int recur_fwd_launch(const RecurFwdParams& p, const void* wcat, cudaStream_t st) {
+  const void* kern = recur_kernel_for(p.A, p.F);
+  MVC_CHECK(kern && recur_fwd_supported(p.B, p.T, p.F, p.H, p.A), "persistent recurrence: unsupported dims");
+  CUtensorMap mx, mw;
+  MVC_TRY(make_map(p.xh, (int64_t)(p.S + 1) * p.B, p.K, p.K, 128, &mx));
+  MVC_TRY(make_map(wcat, (int64_t)4 * p.H, p.K, p.K, RF_BN, &mw));
+  MVC_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned), st));
+  const size_t smem = recur_fwd_smem(p.H, p.A);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(p.H / 16) * RF_CS);
+  cfg.blockDim = dim3(RF_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = RF_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RecurFwdParams pp = p;
+  pp.prof = g_recur_prof;
+  void* args[] = {(void*)&mx, (void*)&mw, (void*)&pp};
+  ProfScope prof(PK_STEP_FUSED, p.B, p.s1 - p.s0, p.K, st);
+  MVC_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mvc
+
+// debugging / profiles: device buffer of >= 10 * steps int64 receiving CTA 0's phase timestamps (null = off)
+extern "C" int mvc_debug_set_recur_prof(long long* dev_buf) {
+  mvc::g_recur_prof = dev_buf;
+  return 0;
+}

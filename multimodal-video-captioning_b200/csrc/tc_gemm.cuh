@@ -21,7 +21,7 @@ struct TcEpilogue {
   const float* bias;          // also the (permuted) gate bias in cell mode, may be null
   __nv_bfloat16* Cb;
   int64_t ldcb;
-  // fused LSTM cell (mode == TC_MODE_CELL): N = 4H, columns permuted (j/32)*128 + gate*32 + j%32
+  // fused LSTM cell (mode == TC_MODE_CELL): N = 4H, columns permuted (j/16)*64 + gate*16 + j%16
   int H;
   const float* gx;            // [M,4H] hoisted input projection (permuted columns), ld gx_ld, may be null
   int64_t gx_ld;
@@ -41,14 +41,20 @@ struct TcEpilogue {
 int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const TcEpilogue& ep, int flags,
             cudaStream_t st);
 
-// gate column of hidden unit j in the permuted ("tile-interleaved") layout used by the fused cell epilogue
+// "Tile-interleaved" gate order used by the fused cell epilogues: hidden units are grouped in blocks of 16 and
+// each block stores its four gates back to back -- column (j/16)*64 + gate*16 + j%16 is nn.LSTM row gate*H + j.
+// Any 64-aligned window of 64k columns therefore holds i,f,g,o of 16k units (64-wide tiles in the persistent
+// recurrence kernel, 128-wide tiles in the stand-alone fused GEMM).
+constexpr int kGateU = 16;
 __host__ __device__ inline int gate_col(int perm, int H, int gate, int j) {
-  return perm ? (j >> 5) * 128 + gate * 32 + (j & 31) : gate * H + j;
+  return perm ? (j >> 4) * 64 + gate * 16 + (j & 15) : gate * H + j;
 }
 // inverse: natural row (gate*H + j) of permuted column c
 __host__ __device__ inline int gate_unperm(int H, int c) {
-  const int tile = c >> 7, gate = (c >> 5) & 3, u = c & 31;
-  return gate * H + tile * 32 + u;
+  const int blk = c >> 6, gate = (c >> 4) & 3, u = c & 15;
+  return gate * H + blk * 16 + u;
 }
+// column, relative to the start of its (64k-aligned) tile, of gate `gate` of the tile's local unit j
+__host__ __device__ inline int gate_lcol(int gate, int j) { return (j >> 4) * 64 + gate * 16 + (j & 15); }
 
 }  // namespace mvc

@@ -107,9 +107,9 @@ def test_fused_gate_gemm_lstm_cell(dev, B, H, K):
     i, f, gg, o = gates.chunk(4, 1)
     c1 = torch.sigmoid(f) * c0.double() + torch.sigmoid(i) * torch.tanh(gg)
     h1 = torch.sigmoid(o) * torch.tanh(c1)
-    # natural gate row r = gate*H + j  <->  packed row (j//32)*128 + gate*32 + j%32
+    # natural gate row r = gate*H + j  <->  packed row (j//16)*64 + gate*16 + j%16
     j = torch.arange(H)
-    packed_of = torch.stack([(j // 32) * 128 + q * 32 + j % 32 for q in range(4)]).reshape(-1)   # natural -> packed
+    packed_of = torch.stack([(j // 16) * 64 + q * 16 + j % 16 for q in range(4)]).reshape(-1)   # natural -> packed
     nat_of = torch.empty(4 * H, dtype=torch.long); nat_of[packed_of] = torch.arange(4 * H)      # packed -> natural
     Kp = K + (-K) % 8
     wp = torch.empty(4 * H, Kp, device=dev, dtype=torch.bfloat16)

@@ -60,6 +60,7 @@ classes = [
     ("gemm_tc vocab fwd", (1, S * B, V, 512)),
     ("gemm_tc vocab step", (1, B, V, 512)),
     ("gemm_tc uk", (1, B * T, 256, 2176)),
+    ("persistent recurrence fwd", (8, -1, -1, -1)),
     ("attention fwd", (3, -1, -1, -1)),
     ("attention bwd", (4, -1, -1, -1)),
     ("cell fwd", (5, -1, -1, -1)),
