@@ -54,6 +54,7 @@ int mvc_prof_collect(double* total_ms, long long* launches);
 /* Debug: device buffer (>= 10 int64 per loop step) that receives SM-clock timestamps of the phases of the
  * persistent recurrence kernel (CTA 0); NULL switches it off. */
 int mvc_debug_set_recur_prof(long long* dev_buf);
+int mvc_debug_set_recur_bwd_prof(long long* dev_buf);
 
 /* ------------------------------------------------------------------ */
 /* Building-block kernels (each is unit-tested against the oracle)     */

@@ -502,7 +502,19 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   cfg.wcatT = q.wcatT;
   cfg.attWT = q.attWT;
   const int permH = cfg.perm ? H : 0;
-  for (int s = S - 1; s >= 0; --s) {
+  const bool persistent_bwd = bf && cfg.perm && recur_bwd_supported(B, T, F, H, A);
+  if (persistent_bwd) {
+    // the whole BPTT time loop in ONE persistent cluster-cooperative launch (recur_bwd.cu)
+    RecurBwdParams rp{};
+    rp.B = B; rp.T = T; rp.F = F; rp.H = H; rp.A = A; rp.K = F + H; rp.S = S;
+    rp.feats = (const __nv_bfloat16*)w.feats; rp.uk = w.uk; rp.att_b = p->att_b; rp.att_w = p->att_w;
+    rp.act = w.act; rp.c = w.c; rp.wq = w.wq; rp.alpha = w.alpha; rp.dh_ext = q.dhall;
+    rp.attWT = (const __nv_bfloat16*)q.attWT;
+    rp.dG = q.dG; rp.dG_b = (__nv_bfloat16*)q.dG_b; rp.dxh = q.dxh; rp.dwq = q.dwq; rp.dwq_b = (__nv_bfloat16*)q.dwq_b;
+    rp.duk = q.duk; rp.dwpart = q.dwpart; rp.sync = w.sync + 16;
+    MVC_TRY(recur_bwd_launch(rp, q.wcatT, st));
+  }
+  for (int s = S - 1; s >= 0 && !persistent_bwd; --s) {
     StepBwd io{};
     io.rows = B;
     io.act = w.act + (int64_t)s * B * 4 * H;
