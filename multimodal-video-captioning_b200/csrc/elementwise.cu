@@ -3,6 +3,7 @@
 // argmax, embedding gather / scatter-add, column sums, Adam.
 #include <stdarg.h>
 
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -50,6 +51,25 @@ __global__ void concat_cast_kernel(const float* __restrict__ a, int Fa, const fl
   }
 }
 
+// 8 outputs per thread: two float4 loads from the right source, one 16-byte bf16 store (Fa, Fv multiples of 8)
+__global__ void concat_cast_bf16x8_kernel(const float* __restrict__ a, int Fa, const float* __restrict__ v, int Fv,
+                                          int64_t rows, __nv_bfloat16* __restrict__ dst) {
+  const int F8 = (Fa + Fv) / 8, Fa8 = Fa / 8;
+  const int64_t total = rows * F8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F8;
+    const int g = (int)(i - r * F8);
+    const float4* src = reinterpret_cast<const float4*>(g < Fa8 ? a + r * Fa + g * 8 : v + r * Fv + (g - Fa8) * 8);
+    const float4 x0 = __ldcs(src), x1 = __ldcs(src + 1);
+    __nv_bfloat162 q0 = __floats2bfloat162_rn(x0.x, x0.y), q1 = __floats2bfloat162_rn(x0.z, x0.w);
+    __nv_bfloat162 q2 = __floats2bfloat162_rn(x1.x, x1.y), q3 = __floats2bfloat162_rn(x1.z, x1.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&q0); o.y = *reinterpret_cast<uint32_t*>(&q1);
+    o.z = *reinterpret_cast<uint32_t*>(&q2); o.w = *reinterpret_cast<uint32_t*>(&q3);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16(src[i]);
@@ -68,6 +88,42 @@ __global__ void transpose_bf16_kernel(const ST* __restrict__ src, int64_t R, int
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int64_t c = c0 + i, r = r0 + threadIdx.x;
     if (c < C && r < R) dst[(permH ? (int64_t)gate_unperm(permH, (int)c) : c) * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+
+// bf16 [R,C] -> bf16 [C,R], 64x64 tiles, 16-byte global accesses on both sides (C, lds, ldd multiples of 8).
+__global__ void __launch_bounds__(256)
+transpose_bf16_tile64_kernel(const __nv_bfloat16* __restrict__ src, int64_t R, int64_t C, int64_t lds,
+                             __nv_bfloat16* __restrict__ dst, int64_t ldd, int permH) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int64_t c0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = tid + i * 256;
+    const int r = idx >> 3, cv = idx & 7;
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (r0 + r < R && c0 + cv * 8 < C) x = *reinterpret_cast<const uint4*>(src + (r0 + r) * lds + c0 + cv * 8);
+    uint32_t* t32 = reinterpret_cast<uint32_t*>(&tile[r][cv * 8]);
+    t32[0] = x.x; t32[1] = x.y; t32[2] = x.z; t32[3] = x.w;
+  }
+  __syncthreads();
+  const int cl = tid >> 2, part = tid & 3;       // 4 lanes cover 64 consecutive r of one output row
+  const int64_t c = c0 + cl;
+  if (c >= C) return;
+  __nv_bfloat16* drow = dst + (permH ? (int64_t)gate_unperm(permH, (int)c) : c) * ldd + r0 + part * 16;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int rl = part * 16 + h * 8;
+    if (r0 + rl + 7 < R) {
+      __nv_bfloat16 e[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e[k] = tile[rl + k][cl];
+      *reinterpret_cast<uint4*>(drow + h * 8) = *reinterpret_cast<const uint4*>(e);
+    } else {
+      for (int k = 0; k < 8; ++k)
+        if (r0 + rl + k < R) drow[h * 8 + k] = tile[rl + k][cl];
+    }
   }
 }
 
@@ -269,6 +325,34 @@ __global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int N, 
   }
 }
 
+// Two-stage column sum for tall matrices: stage 1 sums row slices (grid.y of them) into partial[slice][N],
+// stage 2 adds the slices in order (deterministic).
+__global__ void __launch_bounds__(256)
+colsum_stage1_kernel(const float* __restrict__ x, int64_t rows, int N, int64_t ld, int64_t rows_per, float* __restrict__ partial) {
+  __shared__ float red[2][128];
+  const int col = blockIdx.x * 128 + (threadIdx.x & 127), rlane = threadIdx.x >> 7;
+  const int64_t ra = (int64_t)blockIdx.y * rows_per, rb = ra + rows_per < rows ? ra + rows_per : rows;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (col < N) {
+    int64_t r = ra + rlane;
+    for (; r + 6 < rb; r += 8) {
+      s0 += __ldcs(x + r * ld + col); s1 += __ldcs(x + (r + 2) * ld + col);
+      s2 += __ldcs(x + (r + 4) * ld + col); s3 += __ldcs(x + (r + 6) * ld + col);
+    }
+    for (; r < rb; r += 2) s0 += __ldcs(x + r * ld + col);
+  }
+  red[rlane][threadIdx.x & 127] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (rlane == 0 && col < N) partial[(int64_t)blockIdx.y * N + col] = red[0][threadIdx.x] + red[1][threadIdx.x];
+}
+__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int slices, int N, float* __restrict__ out, int permH) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int i = 0; i < slices; ++i) s += partial[(int64_t)i * N + n];
+  out[permH ? gate_unperm(permH, n) : n] = s;
+}
+
 __global__ void caption_mask_kernel(const int64_t* __restrict__ cap, int64_t n, uint8_t* __restrict__ mask) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) mask[i] = (cap[i] != MVC_PAD && cap[i] != MVC_EOS) ? 1 : 0;
@@ -339,7 +423,10 @@ extern "C" int mvc_concat_cast(const float* a, int Fa, const float* v, int Fv, i
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = rows * (Fa + Fv);
   if (n == 0) return 0;
-  if (dst_bf16) concat_cast_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(a, Fa, v, Fv, rows, (__nv_bfloat16*)dst);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+  if (dst_bf16 && Fa % 8 == 0 && Fv % 8 == 0 && al16)
+    concat_cast_bf16x8_kernel<<<grid_for(n / 8), 256, 0, st>>>(a, Fa, v, Fv, rows, (__nv_bfloat16*)dst);
+  else if (dst_bf16) concat_cast_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(a, Fa, v, Fv, rows, (__nv_bfloat16*)dst);
   else concat_cast_kernel<float><<<grid_for(n), 256, 0, st>>>(a, Fa, v, Fv, rows, (float*)dst);
   MVC_LAUNCH_CHECK();
   return 0;
@@ -356,6 +443,13 @@ namespace mvc {
 int launch_transpose_bf16(const void* src, int src_bf16, int64_t R, int64_t C, int64_t lds, void* dst, int64_t ldd,
                           int permH, cudaStream_t st) {
   if (R == 0 || C == 0) return 0;
+  if (src_bf16 && C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+    dim3 g64((unsigned)cdiv(C, 64), (unsigned)cdiv(R, 64));
+    transpose_bf16_tile64_kernel<<<g64, 256, 0, st>>>((const __nv_bfloat16*)src, R, C, lds, (__nv_bfloat16*)dst, ldd, permH);
+    MVC_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(R, 32)), block(32, 8);
   if (src_bf16)
     transpose_bf16_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)src, R, C, lds, (__nv_bfloat16*)dst,
@@ -376,8 +470,39 @@ int launch_cell_bwd(int B, int H, const float* act, const float* c_prev, const f
   MVC_LAUNCH_CHECK();
   return 0;
 }
+static int colsum_scratch(cudaStream_t st, float** out, size_t* cap) {
+  static std::mutex mu;
+  static std::vector<std::pair<uint64_t, float*>> pool;
+  constexpr size_t kBytes = 4u << 20;
+  int dev = 0;
+  MVC_CUDA(cudaGetDevice(&dev));
+  const uint64_t key = (reinterpret_cast<uint64_t>(st) << 8) ^ (uint64_t)dev;
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& e : pool)
+    if (e.first == key) { *out = e.second; *cap = kBytes; return 0; }
+  float* pbuf = nullptr;
+  MVC_CUDA(cudaMalloc(&pbuf, kBytes));
+  pool.emplace_back(key, pbuf);
+  *out = pbuf; *cap = kBytes;
+  return 0;
+}
+
 int launch_colsum(const float* x, int64_t rows, int N, int64_t ld, float* out, int permH, cudaStream_t st) {
   if (N == 0) return 0;
+  if (rows >= 512) {
+    float* part = nullptr;
+    size_t cap = 0;
+    MVC_TRY(colsum_scratch(st, &part, &cap));
+    int slices = (int)(rows / 64 < 64 ? rows / 64 : 64);
+    while ((size_t)slices * N * sizeof(float) > cap && slices > 1) slices /= 2;
+    const int64_t rows_per = cdiv(rows, slices);
+    dim3 g1((unsigned)cdiv(N, 128), (unsigned)slices);
+    colsum_stage1_kernel<<<g1, 256, 0, st>>>(x, rows, N, ld, rows_per, part);
+    MVC_LAUNCH_CHECK();
+    colsum_stage2_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(part, slices, N, out, permH);
+    MVC_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 block(32, 8);
   colsum_kernel<<<(unsigned)cdiv(N, 32), block, 0, st>>>(x, rows, N, ld, out, permH);
   MVC_LAUNCH_CHECK();

@@ -20,6 +20,24 @@ REC_PARAM_ORDER = ("rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0", "rn
                    "attention.W.weight", "attention.U.weight", "attention.b", "attention.w.weight")
 
 
+# Gradient arena (salstm/trainer.py::FlatClipAdam): parameter storage address -> view of the flat gradient
+# buffer.  When a parameter is registered here, the backward kernels write its gradient straight into the
+# arena view and autograd (with .grad == None) adopts that view: no zero-fill, no accumulate pass.
+_GRAD_ARENA: dict = {}
+
+
+def register_grad_arena(mapping: dict) -> None:
+    _GRAD_ARENA.clear()
+    _GRAD_ARENA.update(mapping)
+
+
+def _grad_like(t: torch.Tensor) -> torch.Tensor:
+    v = _GRAD_ARENA.get(t.data_ptr())
+    if v is not None and v.shape == t.shape and v.device == t.device:
+        return v.detach()          # a fresh alias: autograd may adopt it as .grad without cloning
+    return torch.empty_like(t)
+
+
 def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
     if t is None:
         return None
@@ -80,7 +98,7 @@ class DecoderFn(torch.autograd.Function):
         d, p = _dec_structs(dims, params)
         dout = None if dout is None else _f32c(dout, "grad")
         dhid = None if dhid is None else _f32c(dhid, "grad")
-        grads = [torch.empty_like(t) for t in params]
+        grads = [_grad_like(t) for t in params]
         g = cabi.DecoderGrads(*[C.c_void_p(t.data_ptr()) for t in grads])
         nbytes = lib.mvc_decoder_bwd_workspace_bytes(C.byref(d))
         bws = cabi.workspace(nbytes, out.device)
@@ -180,7 +198,7 @@ class _ReconFn(torch.autograd.Function):
         d, p = _rec_structs(ctx.dims, params)
         drec = _f32c(drec, "grad")
         dhid = torch.empty_like(hid3)
-        grads = [torch.empty_like(t) for t in params]
+        grads = [_grad_like(t) for t in params]
         g = cabi.ReconGrads(*([C.c_void_p(t.data_ptr()) for t in grads] + [None] * (8 - len(grads))))
         nbytes = bws_b(C.byref(d))
         bws = cabi.workspace(nbytes, hid3.device)

@@ -50,24 +50,45 @@ class FlatClipAdam:
             off += k
         self.m, self.v, self.vmax = (torch.zeros_like(self.flat_p) for _ in range(3))
         self._live = live
+        self._views = [p.grad for p in live]
+        if dev.type == "cuda":
+            # backward kernels write gradients straight into these views (functional._GRAD_ARENA)
+            Fn.register_grad_arena({p.data_ptr(): g for p, g in zip(live, self._views)})
 
     def zero_grad(self):
-        if self.flat_g is None:
+        """Before the first step: plain ``grad = None``.  Afterwards gradients live in the flat buffer; on CUDA the
+        backward kernels OVERWRITE their arena views (and autograd adopts them because ``grad is None``), so no
+        zero-fill is needed; elsewhere (CPU plumbing tests) the buffer is cleared and autograd accumulates."""
+        if self.flat_g is None or self.flat_g.device.type == "cuda":
             for p in self.params:
                 p.grad = None
         else:
             self.flat_g.zero_()
+
+    def _adopt(self):
+        """Make sure every live parameter's .grad IS its arena view (copy in anything autograd allocated itself)."""
+        for p, v in zip(self._live, self._views):
+            g = p.grad
+            if g is None:
+                v.zero_()
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+            p.grad = v
 
     def all_reduce_grads(self):
         """One NCCL all-reduce (sum) over the flat gradient buffer; averaging happens in step()."""
         import torch.distributed as dist
         if self.flat_g is None:
             self._flatten()
+        else:
+            self._adopt()
         dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
 
     def step(self):
         if self.flat_g is None:
             self._flatten()
+        else:
+            self._adopt()
         if self.flat_p.device.type != "cuda":
             raise RuntimeError("FlatClipAdam.step: parameters must live on CUDA (the update is a CUDA kernel; "
                                "there is no CPU fallback)")
