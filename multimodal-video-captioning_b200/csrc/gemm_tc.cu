@@ -408,6 +408,162 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------ persistent 128x256 kernel for the big GEMMs
+// One CTA per SM loops over output tiles (tile = blockIdx.x + i*gridDim.x).  The fp32 accumulator is DOUBLE
+// BUFFERED in TMEM (2 x 256 columns = all 512): while the four epilogue warps drain tile i, the MMA warp already
+// accumulates tile i+1 and the producer keeps the TMA ring full across tile boundaries, so neither the prologue
+// nor the epilogue of a tile is exposed.  The epilogue transposes each 32x32 chunk through shared memory so that
+// every global store instruction writes 128 contiguous bytes of one output row.
+constexpr int PG_BN = 256;
+constexpr int PG_STAGES = 4;
+constexpr int PG_A_BYTES = TC_BM * TC_BK * 2;            // 16 KB
+constexpr int PG_B_BYTES = PG_BN * TC_BK * 2;            // 32 KB
+constexpr int PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;  // 48 KB
+constexpr int PG_EPI_OFF = PG_STAGES * PG_STAGE_BYTES;   // 4 warps x [32][33] floats staging
+constexpr int PG_EPI_BYTES = 4 * 32 * 33 * 4;
+constexpr int PG_BAR_OFF = PG_EPI_OFF + PG_EPI_BYTES;
+constexpr int PG_SMEM = PG_BAR_OFF + (2 * PG_STAGES + 4) * 8 + 16 + 1024;
+
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M,
+                            int N, int K, const __grid_constant__ TcEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + PG_BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (PG_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * PG_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * PG_STAGES + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PG_BAR_OFF + 8 * (2 * PG_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + TC_BK - 1) / TC_BK;
+  const int ntn = (N + PG_BN - 1) / PG_BN, ntm = (M + TC_BM - 1) / TC_BM;
+  const int ntiles = ntn * ntm;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < PG_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);               // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * PG_BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int stage = (int)(it % PG_STAGES);
+          const uint32_t par = (it / PG_STAGES) & 1u;
+          mbar_wait(empty_bar(stage), par ^ 1u);
+          mbar_expect_tx(full_bar(stage), PG_STAGE_BYTES);
+          const uint32_t a_dst = smem_base + stage * PG_STAGE_BYTES;
+          tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TC_BK, m0);
+          tma_load_2d(a_dst + PG_A_BYTES, &map_b, full_bar(stage), kb * TC_BK, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, PG_BN);
+      uint32_t it = 0;
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(tempty_bar(buf), (((uint32_t)ti >> 1) & 1u) ^ 1u);     // epilogue has drained this buffer
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * PG_BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int stage = (int)(it % PG_STAGES);
+          const uint32_t par = (it / PG_STAGES) & 1u;
+          mbar_wait(full_bar(stage), par);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * PG_STAGE_BYTES;
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + PG_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;                       // TMEM lane quarter of this warp
+    float* stg = reinterpret_cast<float*>(smem + PG_EPI_OFF) + (warp - 2) * (32 * 33);
+    pdl_wait();
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      const int m0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * PG_BN;
+      mbar_wait(tfull_bar(buf), ((uint32_t)ti >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PG_BN);
+#pragma unroll 1
+      for (int c = 0; c < PG_BN / 32; ++c) {
+        const int gn0 = n0 + c * 32;
+        if (gn0 >= N) break;
+        uint32_t v[32];
+        tmem_ld32(trow + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int gn = gn0 + lane;
+        const float bv = (ep.bias && gn < N) ? ep.bias[gn] : 0.f;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int64_t gm = (int64_t)m0 + q * 32 + rr;
+          if (gm >= M) break;
+          if (gn < N) {
+            float r = stg[rr * 33 + lane] + bv;
+            if (ep.C) {
+              float* dst = ep.C + gm * ep.ldc + gn;
+              if (ep.beta != 0.f) r += ep.beta * (*dst);
+              *dst = r;
+            }
+            if (ep.Cb) ep.Cb[gm * ep.ldcb + gn] = __float2bfloat16(r);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -544,6 +700,33 @@ static int max_active_clusters(int cs) {
   return n;
 }
 
+static int launch_tc_persist(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, TcEpilogue ep,
+                             bool pdl, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  MVC_TRY(get_tensor_map(A, M, K, lda, TC_BM, &ma));
+  MVC_TRY(get_tensor_map(B, N, K, ldb, PG_BN, &mb));
+  static bool configured = false;
+  if (!configured) {
+    MVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+    configured = true;
+  }
+  const int64_t tiles = cdiv(M, TC_BM) * cdiv(N, PG_BN);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = PG_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  ProfScope prof(PK_GEMM_TC, M, N, K, st);
+  MVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_persist_kernel, ma, mb, M, N, K, ep));
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -581,6 +764,8 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
     const int s = splits_for(mt * (N / 128), max_active_clusters<128, 4, TC_MODE_CELL>);
     return launch_tc<128, 4, TC_MODE_CELL>(M, N, K, A, lda, B, ldb, ep, s, pdl, st);
   }
+  // big GEMMs (>= half a wave of 128x256 tiles): persistent kernel with double-buffered TMEM accumulators
+  if (mt * cdiv(N, PG_BN) >= kNumSMs / 2 && K >= 2 * TC_BK) return launch_tc_persist(M, N, K, A, lda, B, ldb, ep, pdl, st);
   const int64_t t128 = mt * cdiv(N, 128), t64 = mt * cdiv(N, 64), t32 = mt * cdiv(N, 32);
   // widest tile whose CTA count (tiles x K-splits) covers most of the 148 SMs
   const int s128 = splits_for(t128, max_active_clusters<128, 4, TC_MODE_PLAIN>);
