@@ -142,6 +142,13 @@ int mvc_lstm_gates_cell_bf16(int B, int H, int K, const void* x, int64_t ldx, co
                              float* act_packed, float* c_out, float* h_out, int64_t h_ld, void* h_bf16,
                              int64_t hb_ld, void* stream);
 
+/* Vocabulary projection fused with the row arg-max (K-E, greedy decoding: features_captioning.py:87-88,:109):
+ * ids[m] = argmax_v (h[m,:] . out_w[v,:] + out_b[v]), ties -> lowest v.  h [M,K] bf16 (ld ldh), out_w [V,K] bf16
+ * (ld ldw).  The arg-max runs in the tcgen05 epilogue (one partial per row and 256-column tile, then a tiny
+ * reduce): the [M,V] logits are never written.  workspace >= M * ceil(V/256) * 8 bytes. */
+int mvc_vocab_argmax_bf16(int M, int V, int K, const void* h, int64_t ldh, const void* out_w, int64_t ldw,
+                          const float* out_b, void* workspace, size_t workspace_bytes, int64_t* ids, void* stream);
+
 /* dgates (pre-activation) from dh (two optional addends dh_a [ld dha_ld], dh_b
  * [ld dhb_ld]) and the carried dc (in/out, [B,H]); dg_bf16 optional copy. */
 int mvc_lstm_cell_bwd(int B, int H, const float* act, const float* c_prev, const float* c_new,

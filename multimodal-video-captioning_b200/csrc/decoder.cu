@@ -650,11 +650,20 @@ extern "C" int mvc_decoder_greedy(const MvcDecoderDims* d, const MvcDecoderParam
     io.h_ld = H;
     io.first = (s == 0);
     MVC_TRY(step_forward(cfg, io, st));
-    MVC_TRY(gemm_nt(d->precision, B, V, H, bf ? cptr(io.xh_dst, F, es) : (const char*)gw.h32, bf ? ldx : H,
-                    bf ? w.outw : (const void*)p->out_w, H, 0.f, gw.logits, V, p->out_b, st));
     int64_t* nxt = gw.tok + (int64_t)((s + 1) & 1) * B;
-    // argmax of the log-probs == argmax of the logits up to fp32 rounding ties; normalise anyway so that
-    // ids agree with decode(captions=None).argmax(2) (captioning.py:138-140)
+    if (bf) {
+      // K-E: vocabulary projection with the row arg-max in the tcgen05 epilogue -- the [B,V] logits never reach
+      // memory (arg-max of the logits == arg-max of the log-probs)
+      const int ntn = tc_gemm_argmax_tiles(V);
+      float* pval = gw.logits;
+      int* pidx = reinterpret_cast<int*>(gw.logits + (size_t)B * ntn);
+      MVC_TRY(tc_gemm_argmax(B, V, H, cptr(io.xh_dst, F, es), ldx, w.outw, H, p->out_b, pval, pidx, nxt, ids + (s + 1), L,
+                             TC_FLAG_PDL | TC_FLAG_B_CONST, st));
+      continue;
+    }
+    MVC_TRY(gemm_nt(d->precision, B, V, H, (const char*)gw.h32, H, (const void*)p->out_w, H, 0.f, gw.logits, V, p->out_b, st));
+    // fp32 path: normalise before the arg-max so that ids agree bit-for-bit with decode(captions=None).argmax(2)
+    // (captioning.py:138-140)
     MVC_TRY(mvc_log_softmax_rows(gw.logits, B, V, nxt, st));
     scatter_col_i64_kernel<<<(unsigned)cdiv(B, 256), 256, 0, st>>>(nxt, ids, L, s + 1, B);
     MVC_LAUNCH_CHECK();

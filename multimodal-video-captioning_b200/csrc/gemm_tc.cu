@@ -424,6 +424,7 @@ constexpr int PG_EPI_BYTES = 4 * 32 * 33 * 4;
 constexpr int PG_BAR_OFF = PG_EPI_OFF + PG_EPI_BYTES;
 constexpr int PG_SMEM = PG_BAR_OFF + (2 * PG_STAGES + 4) * 8 + 16 + 1024;
 
+template <int MODE>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M,
                             int N, int K, const __grid_constant__ TcEpilogue ep) {
@@ -522,6 +523,32 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       mbar_wait(tfull_bar(buf), ((uint32_t)ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PG_BN);
+      if constexpr (MODE == TC_MODE_ARGMAX) {
+        // K-E: row-wise arg-max of (acc + bias) over this tile's columns; the logits never leave the SM.
+        // Thread = row; columns ascend, so a strict > keeps the lowest index on ties.
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll 1
+        for (int c = 0; c < PG_BN / 32; ++c) {
+          const int gn0 = n0 + c * 32;
+          if (gn0 >= N) break;
+          uint32_t v[32];
+          tmem_ld32(trow + (uint32_t)(c * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gn = gn0 + j;
+            if (gn < N) {
+              const float x = __uint_as_float(v[j]) + (ep.bias ? __ldg(ep.bias + gn) : 0.f);
+              if (x > best) { best = x; bi = gn; }
+            }
+          }
+        }
+        const int64_t gm = (int64_t)m0 + q * 32 + lane;
+        if (gm < M) {
+          ep.amax_val[gm * ntn + (tile % ntn)] = best;
+          ep.amax_idx[gm * ntn + (tile % ntn)] = bi;
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < PG_BN / 32; ++c) {
         const int gn0 = n0 + c * 32;
@@ -548,6 +575,7 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           }
         }
         __syncwarp();
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -700,6 +728,7 @@ static int max_active_clusters(int cs) {
   return n;
 }
 
+template <int MODE>
 static int launch_tc_persist(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, TcEpilogue ep,
                              bool pdl, cudaStream_t st) {
   CUtensorMap ma, mb;
@@ -707,7 +736,7 @@ static int launch_tc_persist(int M, int N, int K, const void* A, int64_t lda, co
   MVC_TRY(get_tensor_map(B, N, K, ldb, PG_BN, &mb));
   static bool configured = false;
   if (!configured) {
-    MVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+    MVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_persist_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
     configured = true;
   }
   const int64_t tiles = cdiv(M, TC_BM) * cdiv(N, PG_BN);
@@ -722,7 +751,7 @@ static int launch_tc_persist(int M, int N, int K, const void* A, int64_t lda, co
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   ProfScope prof(PK_GEMM_TC, M, N, K, st);
-  MVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_persist_kernel, ma, mb, M, N, K, ep));
+  MVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_persist_kernel<MODE>, ma, mb, M, N, K, ep));
   MVC_LAUNCH_CHECK();
   return 0;
 }
@@ -765,7 +794,12 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
     return launch_tc<128, 4, TC_MODE_CELL>(M, N, K, A, lda, B, ldb, ep, s, pdl, st);
   }
   // big GEMMs (>= half a wave of 128x256 tiles): persistent kernel with double-buffered TMEM accumulators
-  if (mt * cdiv(N, PG_BN) >= kNumSMs / 2 && K >= 2 * TC_BK) return launch_tc_persist(M, N, K, A, lda, B, ldb, ep, pdl, st);
+  if (ep.mode == TC_MODE_ARGMAX) {
+    MVC_CHECK(ep.amax_val && ep.amax_idx, "tcgen05 GEMM arg-max epilogue: null partial buffers");
+    return launch_tc_persist<TC_MODE_ARGMAX>(M, N, K, A, lda, B, ldb, ep, pdl, st);
+  }
+  if (mt * cdiv(N, PG_BN) >= kNumSMs / 2 && K >= 2 * TC_BK)
+    return launch_tc_persist<TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, pdl, st);
   const int64_t t128 = mt * cdiv(N, 128), t64 = mt * cdiv(N, 64), t32 = mt * cdiv(N, 32);
   // widest tile whose CTA count (tiles x K-splits) covers most of the 148 SMs
   const int s128 = splits_for(t128, max_active_clusters<128, 4, TC_MODE_PLAIN>);
@@ -776,9 +810,49 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
   return launch_tc<32, 8, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s32, pdl, st);
 }
 
+// token[m] = column of the best partial of row m (tiles ascend: strict > keeps the lowest index)
+__global__ void argmax_partials_kernel(const float* __restrict__ pval, const int* __restrict__ pidx, int M, int ntn,
+                                       int64_t* __restrict__ out, int64_t* __restrict__ out2, int64_t out2_ld) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int t = 0; t < ntn; ++t) {
+    const float v = pval[(int64_t)m * ntn + t];
+    if (v > best) { best = v; bi = pidx[(int64_t)m * ntn + t]; }
+  }
+  if (out) out[m] = bi;
+  if (out2) out2[(int64_t)m * out2_ld] = bi;
+}
+
+int tc_gemm_argmax(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
+                   float* pval, int* pidx, int64_t* out, int64_t* out2, int64_t out2_ld, int flags, cudaStream_t st) {
+  TcEpilogue ep{};
+  ep.mode = TC_MODE_ARGMAX;
+  ep.bias = bias;
+  ep.amax_val = pval;
+  ep.amax_idx = pidx;
+  MVC_TRY(tc_gemm(M, N, K, A, lda, B, ldb, ep, flags, st));
+  argmax_partials_kernel<<<(unsigned)cdiv(M, 128), 128, 0, st>>>(pval, pidx, M, (int)cdiv(N, PG_BN), out, out2, out2_ld);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+int tc_gemm_argmax_tiles(int N) { return (int)cdiv(N, PG_BN); }
+
 }  // namespace mvc
 
 using namespace mvc;
+
+extern "C" int mvc_vocab_argmax_bf16(int M, int V, int K, const void* h, int64_t ldh, const void* out_w, int64_t ldw,
+                                     const float* out_b, void* workspace, size_t workspace_bytes, int64_t* ids,
+                                     void* stream) {
+  MVC_CHECK(h && out_w && workspace && ids, "mvc_vocab_argmax_bf16: null argument");
+  const size_t need = (size_t)M * tc_gemm_argmax_tiles(V) * 8;
+  MVC_CHECK(workspace_bytes >= need, "mvc_vocab_argmax_bf16: workspace %zu < %zu", workspace_bytes, need);
+  float* pval = static_cast<float*>(workspace);
+  int* pidx = reinterpret_cast<int*>(pval + (size_t)M * tc_gemm_argmax_tiles(V));
+  return tc_gemm_argmax(M, V, K, h, ldh, out_w, ldw, out_b, pval, pidx, ids, nullptr, 0, 0, (cudaStream_t)stream);
+}
 
 extern "C" int mvc_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, float beta,
                              float* C, int64_t ldc, const float* bias, void* Cb, int64_t ldcb, void* stream) {

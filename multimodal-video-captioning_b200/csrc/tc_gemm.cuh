@@ -4,7 +4,7 @@
 
 namespace mvc {
 
-enum { TC_MODE_PLAIN = 0, TC_MODE_CELL = 1 };
+enum { TC_MODE_PLAIN = 0, TC_MODE_CELL = 1, TC_MODE_ARGMAX = 2 };
 enum {
   TC_FLAG_PDL = 1,       // launch with programmatic stream serialization (the kernel waits on griddepcontrol itself)
   TC_FLAG_B_CONST = 2,   // operand B was complete before the previous kernel started: prefetch it before the dependency wait
@@ -21,6 +21,9 @@ struct TcEpilogue {
   const float* bias;          // also the (permuted) gate bias in cell mode, may be null
   __nv_bfloat16* Cb;
   int64_t ldcb;
+  // fused row arg-max (mode == TC_MODE_ARGMAX): per (row, 256-column tile) partial maximum of acc + bias
+  float* amax_val;            // [M, ceil(N/256)]
+  int* amax_idx;              // [M, ceil(N/256)]
   // fused LSTM cell (mode == TC_MODE_CELL): N = 4H, columns permuted (j/16)*64 + gate*16 + j%16
   int H;
   const float* gx;            // [M,4H] hoisted input projection (permuted columns), ld gx_ld, may be null
@@ -40,6 +43,11 @@ struct TcEpilogue {
 
 int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const TcEpilogue& ep, int flags,
             cudaStream_t st);
+// K-E: ids[m] = argmax_n (A[m,:] . B[n,:] + bias[n]) without materialising the logits (lowest index wins ties);
+// pval / pidx: [M, tc_gemm_argmax_tiles(N)] scratch; out2 (optional) receives the same ids with stride out2_ld.
+int tc_gemm_argmax(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
+                   float* pval, int* pidx, int64_t* out, int64_t* out2, int64_t out2_ld, int flags, cudaStream_t st);
+int tc_gemm_argmax_tiles(int N);
 
 // "Tile-interleaved" gate order used by the fused cell epilogues: hidden units are grouped in blocks of 16 and
 // each block stores its four gates back to back -- column (j/16)*64 + gate*16 + j%16 is nn.LSTM row gate*H + j.

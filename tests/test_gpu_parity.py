@@ -133,6 +133,30 @@ def test_fused_gate_gemm_lstm_cell(dev, B, H, K):
         close(act.cpu()[:, packed_of], ref_act, atol=2e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("M,V,K", [(512, 10547, 512), (7, 300, 64), (130, 3201, 512)])
+def test_vocab_argmax_fused(dev, M, V, K):
+    """K-E: vocabulary projection with the arg-max in the GEMM epilogue == argmax of the explicit logits."""
+    from salstm import cabi
+    lib = cabi.lib()
+    g = torch.Generator().manual_seed(M + V)
+    h = torch.randn(M, K, generator=g).bfloat16().to(dev)
+    w = (torch.randn(V, K, generator=g) * 0.2).bfloat16().to(dev)
+    b = torch.randn(V, generator=g).to(dev)
+    logits = h.double() @ w.double().t() + b.double()
+    ws = torch.empty(M * ((V + 255) // 256) * 8, dtype=torch.uint8, device=dev)
+    ids = torch.empty(M, dtype=torch.int64, device=dev)
+    cabi.check(lib.mvc_vocab_argmax_bf16(M, V, K, cabi.ptr(h), K, cabi.ptr(w), K, cabi.ptr(b), cabi.ptr(ws), ws.numel(),
+                                         cabi.ptr(ids), cabi.stream_ptr()))
+    ref = logits.argmax(1)
+    same = ids == ref
+    # fp32 accumulation-order ties: where ids differ the two logits must be within rounding of each other
+    if not bool(same.all()):
+        r = torch.arange(M, device=dev)
+        gap = (logits[r, ref] - logits[r, ids]).abs()
+        assert float(gap[~same].max()) < 1e-4 * float(logits.abs().max())
+    assert float(same.float().mean()) > 0.99
+
+
 def test_gemm_bf16_rejects_bad_pitch(dev):
     from salstm import cabi
     lib = cabi.lib()
@@ -528,6 +552,26 @@ def test_config3_greedy_matches_decode_argmax(dev):
         ids_b = torch.tensor(model.predict_ids(audio[48:], visual[48:], 30))
         assert torch.equal(torch.cat([ids_a, ids_b]), ids)
         assert (ids[:, 0] == 0).all()
+
+
+def test_greedy_bf16_fused_argmax_matches_decode(dev):
+    """bf16 path: greedy_ids (vocab projection + arg-max fused in the tcgen05 epilogue, logits never materialised)
+    against the arg-max of the bf16 free-running log-probs.  Both run the same bf16 recurrence, so rows agree unless
+    an fp32 accumulation-order tie flips a token (and then cascades): >= 95 % of the captions must be identical."""
+    from models import AVCaptioning
+    B, T, V = 160, 30, 10547
+    torch.manual_seed(0)
+    model = AVCaptioning(Vocab(V), 0.0, "none", device=dev, precision="bf16").to(dev)
+    with torch.no_grad():
+        model.decoder.out.weight.mul_(8.0)
+    audio, visual, _ = (t.to(dev) for t in O.synth_batch(B, T, 30, V, seed=4, min_frames=10))
+    with torch.no_grad():
+        ids = torch.tensor(model.predict_ids(audio, visual, 30))
+        out, _ = model.decoder.decode((audio, visual), None, 30)
+        ref = out.argmax(2).t().cpu()
+    same_rows = (ids == ref).all(1).float().mean()
+    assert float(same_rows) >= 0.95, f"only {float(same_rows):.3f} of the captions identical"
+    assert (ids[:, 0] == 0).all()
 
 
 def test_greedy_ids_fp32_vs_oracle_full_width(dev):

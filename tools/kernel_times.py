@@ -59,6 +59,8 @@ classes = [
     ("gemm_tc dh+=dwq.W (B,H,A)", (1, B, 512, 256)),
     ("gemm_tc vocab fwd", (1, S * B, V, 512)),
     ("gemm_tc vocab step", (1, B, V, 512)),
+    ("gemm_tc embtab", (1, V, 2048, 304)),
+    ("gemm_tc gates greedy (B,4H,F+H)", (1, B, 2048, 2688)),
     ("gemm_tc uk", (1, B * T, 256, 2176)),
     ("persistent recurrence fwd", (8, -1, -1, -1)),
     ("attention fwd", (3, -1, -1, -1)),
