@@ -273,7 +273,7 @@ recur_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_consta
     const int step_i = S - 1 - s;
     RB_STAMP(0);
     // ================================================================= P2: d[ctx;h]_s = dG_s . wcat
-    const int rl = (tid & 127) >> 2, q4 = tid & 3;
+    const int rl = (tid & 255) >> 3, q8 = tid & 7;     // reducer: 8 warps, thread = (row, every 8th float4)
     const int row = rank * 32 + rl;
     if (warp == 8) {
       if (lane == 0) {
@@ -331,10 +331,10 @@ recur_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_consta
     cl_arrive();
     cl_wait();
     RB_STAMP(2);
-    if (warp < 4 && row < B) {
+    if (warp < 8 && row < B) {
       const uint32_t pbase = ring_base + (uint32_t)(row * RB_PS) * 4u;
       float* out = p.dxh + (size_t)row * K + n0;
-      for (int v4 = q4; v4 * 4 < ncol; v4 += 4) {
+      for (int v4 = q8; v4 * 4 < ncol; v4 += 8) {
         if (n0 + v4 * 4 >= K) break;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -345,7 +345,7 @@ recur_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_consta
         *reinterpret_cast<float4*>(out + v4 * 4) = acc;
       }
     }
-    if (warp < 4) asm volatile("fence.proxy.async;" ::: "memory");
+    if (warp < 8) asm volatile("fence.proxy.async;" ::: "memory");
     RB_STAMP(3);
     gbar(p.sync, (++gb) * nctas);                 // dxh of every row / column is complete
     RB_STAMP(4);

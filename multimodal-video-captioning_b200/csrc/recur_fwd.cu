@@ -69,6 +69,11 @@ __device__ __forceinline__ float4 ld_dsmem4_(uint32_t addr) {
   asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ float2 ld_dsmem2_(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_dsmem4_(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -367,13 +372,29 @@ recur_fwd_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_consta
     RF_STAMP(4);
 
     // ================================================================= phase G: gate GEMM + LSTM cell
-    // reducer mapping (warps 0-3): rank r finishes rows [32r, 32r+32), thread = (row, 4 units)
-    const int rl = (tid & 127) >> 2, ug = tid & 3;
+    // reducer mapping (warps 0-7): rank r finishes rows [32r, 32r+32), thread = (row, 2 units)
+    const int rl = (tid & 255) >> 3, ug = tid & 7;
     const int row = rank * 32 + rl;
-    const int u0 = ug * 4;
+    const int u0 = ug * 2;
     const size_t grow = (size_t)s * B + row;
-    float4 add4[4];                               // gate addends (hoisted projection / embedding row / bias)
-    float4 cp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 add2[4];                               // gate addends (hoisted projection / embedding row / bias)
+    float2 cp2 = make_float2(0.f, 0.f);
+    if (warp < 8 && row < B) {
+      // the cell's addends do not depend on the GEMM: fetch them while it runs
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = n0 + g * 16 + u0;
+        float2 a = make_float2(0.f, 0.f);
+        if (p.gx) { const float2 t2 = __ldcs(reinterpret_cast<const float2*>(p.gx + grow * (size_t)(4 * H) + col)); a.x += t2.x; a.y += t2.y; }
+        if (p.embtab) {
+          const float2 t2 = *reinterpret_cast<const float2*>(p.embtab + (size_t)p.tokens[grow] * (4 * H) + col);
+          a.x += t2.x; a.y += t2.y;
+        }
+        if (p.cell_bias) { const float2 t2 = *reinterpret_cast<const float2*>(p.cell_bias + col); a.x += t2.x; a.y += t2.y; }
+        add2[g] = a;
+      }
+      cp2 = __ldcg(reinterpret_cast<const float2*>(p.c + grow * H + cl * 16 + u0));
+    }
     if (warp == 8) {
       if (lane == 0) {
         asm volatile("fence.proxy.async;" ::: "memory");     // ctx / h were written with generic stores by other CTAs
@@ -408,22 +429,6 @@ recur_fwd_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_consta
       }
       __syncwarp();
     } else if (warp < 4) {
-      // the cell's addends do not depend on the GEMM: fetch them while it runs
-      if (row < B) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = n0 + g * 16 + u0;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.gx) { const float4 t4 = __ldcs(reinterpret_cast<const float4*>(p.gx + grow * (size_t)(4 * H) + col)); a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w; }
-          if (p.embtab) {
-            const float4 t4 = *reinterpret_cast<const float4*>(p.embtab + (size_t)p.tokens[grow] * (4 * H) + col);
-            a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w;
-          }
-          if (p.cell_bias) { const float4 t4 = *reinterpret_cast<const float4*>(p.cell_bias + col); a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w; }
-          add4[g] = a;
-        }
-        cp4 = __ldcg(reinterpret_cast<const float4*>(p.c + grow * H + cl * 16 + u0));
-      }
       // park the partial tile [128 x 64] (this K-slice) in this CTA's own operand ring (idle: every MMA that read
       // it has completed), pitch 68 floats.  (Pushing rows into the finishing rank's ring instead would race with
       // that rank's still-running TMA / MMA pipeline.)
@@ -448,49 +453,40 @@ recur_fwd_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_consta
     cluster_arrive_();
     cluster_wait_();                              // the four K-slice partials of this cluster's tile are parked
     RF_STAMP(6);
-    if (warp < 4) {
-      float g4[4][4];
+    if (warp < 8) {
+      float g2[4][2];
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) g4[g][j] = 0.f;
+      for (int g = 0; g < 4; ++g) { g2[g][0] = 0.f; g2[g][1] = 0.f; }
       const uint32_t pbase = ring_base + (uint32_t)(row * RF_PS) * 4u;
 #pragma unroll
       for (int sr = 0; sr < RF_CS; ++sr) {          // source ranks in order: deterministic
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const float4 t4 = ld_dsmem4_(mapa_(pbase + (uint32_t)(g * 16 + u0) * 4u, (uint32_t)sr));
-          g4[g][0] += t4.x; g4[g][1] += t4.y; g4[g][2] += t4.z; g4[g][3] += t4.w;
+          const float2 t2 = ld_dsmem2_(mapa_(pbase + (uint32_t)(g * 16 + u0) * 4u, (uint32_t)sr));
+          g2[g][0] += t2.x; g2[g][1] += t2.y;
         }
       }
       if (row < B) {
         const int ug0 = cl * 16 + u0;             // global hidden unit
 #pragma unroll
-        for (int g = 0; g < 4; ++g) { g4[g][0] += add4[g].x; g4[g][1] += add4[g].y; g4[g][2] += add4[g].z; g4[g][3] += add4[g].w; }
-        const float cpv[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
-        float cn[4], hn[4];
+        for (int g = 0; g < 4; ++g) { g2[g][0] += add2[g].x; g2[g][1] += add2[g].y; }
+        const float cpv[2] = {cp2.x, cp2.y};
+        float cn[2], hn[2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float ig = sigmoid_f(g4[0][e]), fg = sigmoid_f(g4[1][e]), gg = tanhf(g4[2][e]), og = sigmoid_f(g4[3][e]);
-          g4[0][e] = ig; g4[1][e] = fg; g4[2][e] = gg; g4[3][e] = og;
+        for (int e = 0; e < 2; ++e) {
+          const float ig = sigmoid_f(g2[0][e]), fg = sigmoid_f(g2[1][e]), gg = tanhf(g2[2][e]), og = sigmoid_f(g2[3][e]);
+          g2[0][e] = ig; g2[1][e] = fg; g2[2][e] = gg; g2[3][e] = og;
           cn[e] = fg * cpv[e] + ig * gg;
           hn[e] = og * tanhf(cn[e]);
         }
         const size_t nrow = (size_t)(s + 1) * B + row;
-        *reinterpret_cast<float4*>(p.c + nrow * H + ug0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-        if (p.out_hid) *reinterpret_cast<float4*>(p.out_hid + nrow * H + ug0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-        {
-          __nv_bfloat162 q0 = __floats2bfloat162_rn(hn[0], hn[1]), q1 = __floats2bfloat162_rn(hn[2], hn[3]);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&q0);
-          pk.y = *reinterpret_cast<uint32_t*>(&q1);
-          *reinterpret_cast<uint2*>(p.xh + nrow * K + F + ug0) = pk;
-        }
+        *reinterpret_cast<float2*>(p.c + nrow * H + ug0) = make_float2(cn[0], cn[1]);
+        if (p.out_hid) *reinterpret_cast<float2*>(p.out_hid + nrow * H + ug0) = make_float2(hn[0], hn[1]);
+        *reinterpret_cast<__nv_bfloat162*>(p.xh + nrow * K + F + ug0) = __floats2bfloat162_rn(hn[0], hn[1]);
         if (p.act) {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<float4*>(p.act + grow * (size_t)(4 * H) + n0 + g * 16 + u0) =
-                make_float4(g4[g][0], g4[g][1], g4[g][2], g4[g][3]);
+            *reinterpret_cast<float2*>(p.act + grow * (size_t)(4 * H) + n0 + g * 16 + u0) = make_float2(g2[g][0], g2[g][1]);
         }
       }
       asm volatile("fence.proxy.async;" ::: "memory");   // ring: generic accesses above, TMA writes next

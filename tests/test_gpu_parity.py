@@ -509,6 +509,42 @@ def test_bf16_path_vs_fp64_oracle(dev, rec_type, inputs):
     assert not bad, "\n".join(bad)
 
 
+@pytest.mark.parametrize("B,T", [(5, 7), (37, 30), (128, 44)])
+def test_bf16_dual_persistent_kernels_vs_fp64_oracle(dev, B, T):
+    """AVCaptioningDual on the bf16 path: the visual decoder (F=2048) and the audio decoder (F=128) run the other two
+    instantiations of the persistent recurrence kernels (9 / 8 / 1 key words per TMEM lane), at ragged batch sizes
+    (B < 128 leaves CTAs without a row) and both reference frame counts.  O(1) features: cosine >= 0.999."""
+    from models import AVCaptioningDual
+    import losses as L
+    Lc, V = 9, 157
+    p = _wrapper_params("dual", V, "none", 78)
+    p["v_decoder.out.weight"] /= 6.0
+    p["a_decoder.out.weight"] /= 6.0
+    audio, visual, caps = O.synth_batch(B, T, Lc, V, seed=6, min_frames=2, min_cap=4)
+    audio, visual = audio / 255.0, visual / 10.0
+    model = AVCaptioningDual(Vocab(V), 1.0, "none", device=dev, precision="bf16").to(dev)
+    _load(model, p)
+    out, _, _ = model(audio.to(dev), visual.to(dev), caps.to(dev))
+    terms = L.ModalityWiseReconstructionLoss(out, caps.to(dev), None, None, None, None, 0.0005, 0.0, 0.0, "none")
+    terms[0].backward()
+    pd = {k: v.double().requires_grad_() for k, v in p.items()}
+    o_out, _, _ = O.av_dual_forward(pd, audio.double(), visual.double(), caps, 1.0, "none", hoist=True)
+    o_terms = O.modality_wise_loss(o_out, caps, reg_lambda=0.0005)
+    o_terms[0].backward()
+    close(out, o_out, atol=5e-2, rtol=5e-2)
+    close(terms[0], o_terms[0], rtol=2e-2, atol=1e-3)
+    bad = []
+    for k, v in model.named_parameters():
+        if pd.get(k) is None or pd[k].grad is None:
+            assert v.grad is None or k.startswith("output_fc"), k
+            continue
+        c = cos(v.grad, pd[k].grad)
+        n1, n2 = float(v.grad.norm()), float(pd[k].grad.norm())
+        if c < 0.999 or abs(n1 - n2) > 5e-2 * n2 + 1e-7:
+            bad.append(f"{k}: cosine {c:.5f}, norm {n1:.4e} vs {n2:.4e}")
+    assert not bad, "\n".join(bad)
+
+
 # --------------------------------------------------------------------------- full-size properties (BASELINE configs)
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_config2_shape_properties(dev, precision):
