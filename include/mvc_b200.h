@@ -149,6 +149,15 @@ int mvc_lstm_gates_cell_bf16(int B, int H, int K, const void* x, int64_t ldx, co
 int mvc_vocab_argmax_bf16(int M, int V, int K, const void* h, int64_t ldh, const void* out_w, int64_t ldw,
                           const float* out_b, void* workspace, size_t workspace_bytes, int64_t* ids, void* stream);
 
+/* Vocabulary projection fused with log-softmax + top-k (K-E, beam search: features_captioning.py:160-189):
+ * cand_logp[m,k], cand_idx[m,k] (k < width <= 8) = the largest log_softmax(h[m,:] . out_w^T + out_b) values of row m
+ * and their tokens, best first, ties -> lowest token.  Top-8 lists and an online log-sum-exp are kept per row and
+ * 256-column tile in the tcgen05 epilogue and merged by a small kernel; logits / log-probs are never written. */
+size_t mvc_vocab_topk_workspace_bytes(int M, int V);
+int mvc_vocab_topk_bf16(int M, int V, int K, const void* h, int64_t ldh, const void* out_w, int64_t ldw,
+                        const float* out_b, int width, void* workspace, size_t workspace_bytes, float* cand_logp,
+                        int* cand_idx, void* stream);
+
 /* dgates (pre-activation) from dh (two optional addends dh_a [ld dha_ld], dh_b
  * [ld dhb_ld]) and the carried dc (in/out, [B,H]); dg_bf16 optional copy. */
 int mvc_lstm_cell_bwd(int B, int H, const float* act, const float* c_prev, const float* c_new,

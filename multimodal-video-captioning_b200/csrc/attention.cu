@@ -254,7 +254,8 @@ attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
   constexpr int NW = NT / 32;
   constexpr int VN = VecOf<KT>::N;
   const int T = a.T, A = AV * 32, F = a.F;
-  const int b = blockIdx.x, kb = b % a.keys_batch;
+  const int kb = blockIdx.x;                     // key block; rows kb, kb + keys_batch, ... (beams) share it
+  const int nq = a.B / a.keys_batch;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int f0 = blockIdx.y * chunk, f1 = min(F, f0 + chunk), ncols = f1 - f0;
   const size_t stage_bytes = ((size_t)T * chunk * sizeof(KT) + 127) & ~size_t(127);
@@ -292,6 +293,9 @@ attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
   for (int i = tid; i < A; i += NT) sW[i] = a.w[i];
   pdl_trigger();
   pdl_wait();                       // the query (wq) comes from the preceding kernel
+  for (int qi = 0; qi < nq; ++qi) {
+  const int b = qi * a.keys_batch + kb;
+  __syncthreads();                  // previous query's readers of sQ / sE are done
   for (int i = tid; i < A; i += NT) sQ[i] = a.wq[(int64_t)b * A + i] + a.bias[i];
   __syncthreads();
 #pragma unroll
@@ -326,8 +330,8 @@ attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
     if (blockIdx.y == 0) a.alpha[(int64_t)b * T + t] = p;
   }
   __syncthreads();
-  if (ncols <= 0) return;
-  mbar_wait(bar, 0);                // keys chunk has landed
+  if (ncols <= 0) continue;
+  mbar_wait(bar, 0);                // keys chunk has landed (immediate for every query after the first)
   const int nvec = ncols / VN;
   for (int v = tid; v < nvec; v += NT) {
     float acc[VN];
@@ -354,6 +358,7 @@ attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
       for (int i = 0; i < VN; ++i) dst[i] = __float2bfloat16(acc[i]);
     }
   }
+  }   // queries
 }
 
 // Backward, one CTA per batch row; keys row block staged by TMA bulk copies, U.k in registers.
@@ -545,7 +550,7 @@ int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
   ProfScope prof(PK_ATTN_FWD, B, T, F, st);
   // ---- staged fast path
   const void* kern = nullptr;
-  if (vec && T <= ATT_MAXR * 9) {
+  if (vec && T <= ATT_MAXR * 9 && B % a.keys_batch == 0) {
     if (a.keys_bf16) kern = a.fast_math ? pick_fwd_staged<__nv_bfloat16, true>(A) : pick_fwd_staged<__nv_bfloat16, false>(A);
     else kern = a.fast_math ? pick_fwd_staged<float, true>(A) : pick_fwd_staged<float, false>(A);
   }
@@ -560,14 +565,14 @@ int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
     };
     int chunk = F;
     while (smem_for(fs, &chunk) > kAttnMaxSmem && fs < F / VN) ++fs;
-    while ((int64_t)B * fs < kNumSMs && fs < 8 && chunk > 64 * VN) { ++fs; smem_for(fs, &chunk); }
+    while ((int64_t)a.keys_batch * fs < kNumSMs && fs < 8 && chunk > 64 * VN) { ++fs; smem_for(fs, &chunk); }
     const size_t smem = smem_for(fs, &chunk);
     fs = (int)cdiv(F, chunk);
     if (smem <= kAttnMaxSmem) {
       MVC_TRY(ensure_big_smem(kern));
       AttnFwdArgs args = a;
       void* params[] = {(void*)&args, (void*)&chunk};
-      MVC_TRY(launch_ex(kern, dim3(B, fs), dim3(288), smem, pdl, params, st));
+      MVC_TRY(launch_ex(kern, dim3(a.keys_batch, fs), dim3(288), smem, pdl, params, st));
       MVC_LAUNCH_CHECK();
       return 0;
     }

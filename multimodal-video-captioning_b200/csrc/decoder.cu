@@ -910,10 +910,16 @@ extern "C" int mvc_decoder_beam(const MvcDecoderDims* d, const MvcDecoderParams*
     io.h_ld = H;
     io.first = (t == 0);
     MVC_TRY(step_forward(cfg, io, st));
-    MVC_TRY(gemm_nt(d->precision, rows, V, H, bf ? cptr(xh_new, F, es) : (const char*)bw.h32, bf ? ldx : H,
-                    bf ? w.outw : (const void*)p->out_w, H, 0.f, bw.logits, V, p->out_b, st));
-    beam_row_topk_kernel<<<rows, 256, 0, st>>>(bw.logits, V, width, bw.cand_val, bw.cand_idx);
-    MVC_LAUNCH_CHECK();
+    if (bf && V >= 64) {
+      // K-E: vocabulary projection with top-k + log-sum-exp in the tcgen05 epilogue (no [rows,V] logits)
+      MVC_TRY(tc_gemm_topk(rows, V, H, cptr(xh_new, F, es), ldx, w.outw, H, p->out_b, bw.logits, width, bw.cand_val,
+                           bw.cand_idx, TC_FLAG_PDL | TC_FLAG_B_CONST, st));
+    } else {
+      MVC_TRY(gemm_nt(d->precision, rows, V, H, bf ? cptr(xh_new, F, es) : (const char*)bw.h32, bf ? ldx : H,
+                      bf ? w.outw : (const void*)p->out_w, H, 0.f, bw.logits, V, p->out_b, st));
+      beam_row_topk_kernel<<<rows, 256, 0, st>>>(bw.logits, V, width, bw.cand_val, bw.cand_idx);
+      MVC_LAUNCH_CHECK();
+    }
     const int nx = cur ^ 1;
     beam_merge_kernel<<<(unsigned)cdiv(B, 128), 128, 0, st>>>(B, V, nb, width, t, alpha, bw.cand_val, bw.cand_idx,
                                                              bw.cum[cur], bw.done[cur], bw.len[cur], bw.cum[nx],

@@ -545,8 +545,64 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         }
         const int64_t gm = (int64_t)m0 + q * 32 + lane;
         if (gm < M) {
-          ep.amax_val[gm * ntn + (tile % ntn)] = best;
-          ep.amax_idx[gm * ntn + (tile % ntn)] = bi;
+          ep.amax_val[(int64_t)(tile % ntn) * M + gm] = best;       // [tile][row]
+          ep.amax_idx[(int64_t)(tile % ntn) * M + gm] = bi;
+        }
+      } else if constexpr (MODE == TC_MODE_TOPK) {
+        // K-E (beam search): per row of this tile the 8 best (acc + bias) values with their columns (sorted, ties ->
+        // lowest column) and the (max, sum exp) pair of an online log-sum-exp; the logits never leave the SM.
+        float tv[8];
+        int tix[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { tv[i] = -INFINITY; tix[i] = 0x7fffffff; }
+        float mx = -INFINITY, sm = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < PG_BN / 32; ++c) {
+          const int gn0 = n0 + c * 32;
+          if (gn0 >= N) break;
+          uint32_t v[32];
+          tmem_ld32(trow + (uint32_t)(c * 32), v);
+          float x[32];
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gn = gn0 + j;
+            x[j] = (gn < N) ? __uint_as_float(v[j]) + (ep.bias ? __ldg(ep.bias + gn) : 0.f) : -INFINITY;
+            cmax = fmaxf(cmax, x[j]);
+          }
+          // online log-sum-exp, one rescale per 32-column chunk; the 32 exponentials are independent
+          const float nmx = fmaxf(mx, cmax);
+          float part = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part += __expf(x[j] - nmx);
+          sm = sm * __expf(mx - nmx) + part;
+          mx = nmx;
+          if (cmax > tv[7]) {                    // some element of this chunk enters the top-8
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (x[j] > tv[7]) {
+                tv[7] = x[j]; tix[7] = gn0 + j;
+#pragma unroll
+                for (int i = 7; i > 0; --i) {
+                  if (tv[i] > tv[i - 1]) {       // strict: an equal value stays behind the earlier (lower) column
+                    const float tf = tv[i]; tv[i] = tv[i - 1]; tv[i - 1] = tf;
+                    const int tn = tix[i]; tix[i] = tix[i - 1]; tix[i - 1] = tn;
+                  }
+                }
+              }
+            }
+          }
+        }
+        const int64_t gm = (int64_t)m0 + q * 32 + lane;
+        if (gm < M) {
+          const int64_t tn = tile % ntn;           // partials are [tile][k][row]: coalesced here and in the merge
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            ep.topk_val[(tn * 8 + i) * M + gm] = tv[i];
+            ep.topk_idx[(tn * 8 + i) * M + gm] = tix[i];
+          }
+          ep.lse_max[tn * M + gm] = mx;
+          ep.lse_sum[tn * M + gm] = sm;
         }
       } else {
 #pragma unroll 1
@@ -798,6 +854,10 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
     MVC_CHECK(ep.amax_val && ep.amax_idx, "tcgen05 GEMM arg-max epilogue: null partial buffers");
     return launch_tc_persist<TC_MODE_ARGMAX>(M, N, K, A, lda, B, ldb, ep, pdl, st);
   }
+  if (ep.mode == TC_MODE_TOPK) {
+    MVC_CHECK(ep.topk_val && ep.topk_idx && ep.lse_max && ep.lse_sum, "tcgen05 GEMM top-k epilogue: null partial buffers");
+    return launch_tc_persist<TC_MODE_TOPK>(M, N, K, A, lda, B, ldb, ep, pdl, st);
+  }
   if (mt * cdiv(N, PG_BN) >= kNumSMs / 2 && K >= 2 * TC_BK)
     return launch_tc_persist<TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, pdl, st);
   const int64_t t128 = mt * cdiv(N, 128), t64 = mt * cdiv(N, 64), t32 = mt * cdiv(N, 32);
@@ -818,8 +878,8 @@ __global__ void argmax_partials_kernel(const float* __restrict__ pval, const int
   float best = -INFINITY;
   int bi = 0;
   for (int t = 0; t < ntn; ++t) {
-    const float v = pval[(int64_t)m * ntn + t];
-    if (v > best) { best = v; bi = pidx[(int64_t)m * ntn + t]; }
+    const float v = pval[(int64_t)t * M + m];
+    if (v > best) { best = v; bi = pidx[(int64_t)t * M + m]; }
   }
   if (out) out[m] = bi;
   if (out2) out2[(int64_t)m * out2_ld] = bi;
@@ -839,6 +899,62 @@ int tc_gemm_argmax(int M, int N, int K, const void* A, int64_t lda, const void* 
 }
 int tc_gemm_argmax_tiles(int N) { return (int)cdiv(N, PG_BN); }
 
+// per row: log-sum-exp from the per-tile (max, sum) pairs and the `width` best log-probs from the per-tile top-8
+// lists (tiles ascend, lists are sorted: a strict > keeps the lowest token on ties)
+__global__ void topk_partials_kernel(const float* __restrict__ tval, const int* __restrict__ tidx,
+                                     const float* __restrict__ lmax, const float* __restrict__ lsum, int M, int ntn,
+                                     int width, float* __restrict__ cand_val, int* __restrict__ cand_idx) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float mx = -INFINITY;
+  for (int t = 0; t < ntn; ++t) mx = fmaxf(mx, lmax[(int64_t)t * M + m]);
+  float sm = 0.f;
+  for (int t = 0; t < ntn; ++t) sm += lsum[(int64_t)t * M + m] * expf(lmax[(int64_t)t * M + m] - mx);
+  const float lse = mx + logf(sm);
+  float bv[8];
+  int bi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { bv[i] = -INFINITY; bi[i] = 0x7fffffff; }
+  for (int t = 0; t < ntn; ++t) {
+    for (int k = 0; k < 8; ++k) {
+      const float x = tval[((int64_t)t * 8 + k) * M + m];
+      if (!(x > bv[7])) break;                  // the list is sorted: nothing better follows in this tile
+      bv[7] = x; bi[7] = tidx[((int64_t)t * 8 + k) * M + m];
+#pragma unroll
+      for (int i = 7; i > 0; --i) {
+        if (bv[i] > bv[i - 1]) {
+          const float tf = bv[i]; bv[i] = bv[i - 1]; bv[i - 1] = tf;
+          const int tn = bi[i]; bi[i] = bi[i - 1]; bi[i - 1] = tn;
+        }
+      }
+    }
+  }
+  for (int k = 0; k < width; ++k) {
+    cand_val[(int64_t)m * width + k] = bv[k] - lse;
+    cand_idx[(int64_t)m * width + k] = bi[k];
+  }
+}
+
+size_t tc_gemm_topk_scratch_bytes(int M, int N) { return (size_t)M * cdiv(N, PG_BN) * (8 + 8 + 2) * 4; }
+
+int tc_gemm_topk(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
+                 void* scratch, int width, float* cand_val, int* cand_idx, int flags, cudaStream_t st) {
+  MVC_CHECK(width >= 1 && width <= 8, "fused top-k: width %d not in [1,8]", width);
+  const int ntn = (int)cdiv(N, PG_BN);
+  float* tval = static_cast<float*>(scratch);
+  int* tidx = reinterpret_cast<int*>(tval + (size_t)M * ntn * 8);
+  float* lmax = reinterpret_cast<float*>(tidx + (size_t)M * ntn * 8);
+  float* lsum = lmax + (size_t)M * ntn;
+  TcEpilogue ep{};
+  ep.mode = TC_MODE_TOPK;
+  ep.bias = bias;
+  ep.topk_val = tval; ep.topk_idx = tidx; ep.lse_max = lmax; ep.lse_sum = lsum;
+  MVC_TRY(tc_gemm(M, N, K, A, lda, B, ldb, ep, flags, st));
+  topk_partials_kernel<<<(unsigned)cdiv(M, 128), 128, 0, st>>>(tval, tidx, lmax, lsum, M, ntn, width, cand_val, cand_idx);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace mvc
 
 using namespace mvc;
@@ -852,6 +968,17 @@ extern "C" int mvc_vocab_argmax_bf16(int M, int V, int K, const void* h, int64_t
   float* pval = static_cast<float*>(workspace);
   int* pidx = reinterpret_cast<int*>(pval + (size_t)M * tc_gemm_argmax_tiles(V));
   return tc_gemm_argmax(M, V, K, h, ldh, out_w, ldw, out_b, pval, pidx, ids, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+extern "C" size_t mvc_vocab_topk_workspace_bytes(int M, int V) { return tc_gemm_topk_scratch_bytes(M, V); }
+
+extern "C" int mvc_vocab_topk_bf16(int M, int V, int K, const void* h, int64_t ldh, const void* out_w, int64_t ldw,
+                                   const float* out_b, int width, void* workspace, size_t workspace_bytes,
+                                   float* cand_logp, int* cand_idx, void* stream) {
+  MVC_CHECK(h && out_w && workspace && cand_logp && cand_idx, "mvc_vocab_topk_bf16: null argument");
+  MVC_CHECK(workspace_bytes >= tc_gemm_topk_scratch_bytes(M, V), "mvc_vocab_topk_bf16: workspace %zu < %zu",
+            workspace_bytes, tc_gemm_topk_scratch_bytes(M, V));
+  return tc_gemm_topk(M, V, K, h, ldh, out_w, ldw, out_b, workspace, width, cand_logp, cand_idx, 0, (cudaStream_t)stream);
 }
 
 extern "C" int mvc_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, float beta,

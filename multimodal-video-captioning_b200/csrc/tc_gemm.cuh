@@ -4,7 +4,7 @@
 
 namespace mvc {
 
-enum { TC_MODE_PLAIN = 0, TC_MODE_CELL = 1, TC_MODE_ARGMAX = 2 };
+enum { TC_MODE_PLAIN = 0, TC_MODE_CELL = 1, TC_MODE_ARGMAX = 2, TC_MODE_TOPK = 3 };
 enum {
   TC_FLAG_PDL = 1,       // launch with programmatic stream serialization (the kernel waits on griddepcontrol itself)
   TC_FLAG_B_CONST = 2,   // operand B was complete before the previous kernel started: prefetch it before the dependency wait
@@ -22,8 +22,13 @@ struct TcEpilogue {
   __nv_bfloat16* Cb;
   int64_t ldcb;
   // fused row arg-max (mode == TC_MODE_ARGMAX): per (row, 256-column tile) partial maximum of acc + bias
-  float* amax_val;            // [M, ceil(N/256)]
-  int* amax_idx;              // [M, ceil(N/256)]
+  float* amax_val;            // [ceil(N/256), M]
+  int* amax_idx;              // [ceil(N/256), M]
+  // fused top-8 + online log-sum-exp (mode == TC_MODE_TOPK): per (row, 256-column tile)
+  float* topk_val;            // [ceil(N/256), 8, M]
+  int* topk_idx;              // [ceil(N/256), 8, M]
+  float* lse_max;             // [ceil(N/256), M]
+  float* lse_sum;             // [ceil(N/256), M]
   // fused LSTM cell (mode == TC_MODE_CELL): N = 4H, columns permuted (j/16)*64 + gate*16 + j%16
   int H;
   const float* gx;            // [M,4H] hoisted input projection (permuted columns), ld gx_ld, may be null
@@ -48,6 +53,11 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
 int tc_gemm_argmax(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
                    float* pval, int* pidx, int64_t* out, int64_t* out2, int64_t out2_ld, int flags, cudaStream_t st);
 int tc_gemm_argmax_tiles(int N);
+// K-E (beam): cand_val[m, k] / cand_idx[m, k] = the `width` (<= 8) largest log-softmax values of row m of
+// A . B^T + bias and their columns, without materialising logits or log-probs.
+size_t tc_gemm_topk_scratch_bytes(int M, int N);
+int tc_gemm_topk(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
+                 void* scratch, int width, float* cand_val, int* cand_idx, int flags, cudaStream_t st);
 
 // "Tile-interleaved" gate order used by the fused cell epilogues: hidden units are grouped in blocks of 16 and
 // each block stores its four gates back to back -- column (j/16)*64 + gate*16 + j%16 is nn.LSTM row gate*H + j.

@@ -157,6 +157,50 @@ def test_vocab_argmax_fused(dev, M, V, K):
     assert float(same.float().mean()) > 0.99
 
 
+@pytest.mark.parametrize("M,V,K,width", [(640, 10547, 512, 5), (9, 300, 64, 3), (130, 3201, 512, 8)])
+def test_vocab_topk_fused(dev, M, V, K, width):
+    """K-E (beam): top-`width` log-probs + tokens from the GEMM epilogue == torch.topk(log_softmax(logits))."""
+    from salstm import cabi
+    lib = cabi.lib()
+    g = torch.Generator().manual_seed(M + V + width)
+    h = torch.randn(M, K, generator=g).bfloat16().to(dev)
+    w = (torch.randn(V, K, generator=g) * 0.2).bfloat16().to(dev)
+    b = torch.randn(V, generator=g).to(dev)
+    logp = torch.log_softmax(h.double() @ w.double().t() + b.double(), dim=1)
+    rv, ri = logp.topk(width, dim=1)
+    n = lib.mvc_vocab_topk_workspace_bytes(M, V)
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    cv = torch.empty(M, width, device=dev)
+    ci = torch.empty(M, width, dtype=torch.int32, device=dev)
+    cabi.check(lib.mvc_vocab_topk_bf16(M, V, K, cabi.ptr(h), K, cabi.ptr(w), K, cabi.ptr(b), width, cabi.ptr(ws), n,
+                                       cabi.ptr(cv), cabi.ptr(ci), cabi.stream_ptr()))
+    close(cv, rv, atol=2e-4, rtol=1e-4)
+    same = ci.long() == ri
+    if not bool(same.all()):      # near-ties may swap neighbours: the values must then be (almost) equal
+        r = torch.arange(M, device=dev).unsqueeze(1).expand_as(ri)
+        assert float((logp[r, ci.long()] - rv).abs()[~same].max()) < 2e-4
+    assert float(same.float().mean()) > 0.99
+
+
+def test_beam_bf16_width1_equals_greedy(dev):
+    """bf16 path: beam search of width 1 (fused top-k epilogue, shared-key attention) must produce the greedy
+    caption (fused arg-max epilogue) up to its first EOS."""
+    from models import AVCaptioning
+    B, T, V = 48, 30, 3201
+    torch.manual_seed(1)
+    model = AVCaptioning(Vocab(V), 0.0, "none", device=dev, precision="bf16").to(dev)
+    with torch.no_grad():
+        model.decoder.out.weight.mul_(8.0)
+    audio, visual, _ = (t.to(dev) for t in O.synth_batch(B, T, 20, V, seed=7, min_frames=10))
+    with torch.no_grad():
+        gr = model.predict_ids(audio, visual, 20, mode="direct")
+        b1 = model.predict_ids(audio, visual, 20, mode="beam", beam_width=1)
+        b5 = model.predict_ids(audio, visual, 20, mode="beam", beam_width=5)
+    agree = sum(_prefix([1] + g[1:])[1:] == _prefix(b)[1:len(_prefix([1] + g[1:]))] for g, b in zip(gr, b1))
+    assert agree >= 0.9 * B, f"{agree}/{B} width-1 beams equal the greedy caption"
+    assert len(b5) == B and all(len(x) == 22 and x[0] == 1 for x in b5)
+
+
 def test_gemm_bf16_rejects_bad_pitch(dev):
     from salstm import cabi
     lib = cabi.lib()

@@ -28,6 +28,10 @@ training = workload.startswith("train") or workload.startswith("recnet")
 
 
 def step(b):
+    if workload == "beam":
+        from salstm import functional as Fn
+        dec = model.decoder
+        return Fn.decoder_beam(dec._dims(b[0].shape[0], b[0].shape[1], L), b[0], b[1], dec._params(), 5, 0.0)
     if not training:
         return model.decoder.greedy_ids((b[0], b[1]), L)
     opt.zero_grad()
