@@ -76,6 +76,12 @@ int mvc_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, const void* B
                   float beta, float* C, int64_t ldc, const float* bias, void* Cb, int64_t ldcb,
                   void* stream);
 
+/* Same contraction with either operand stored TRANSPOSED: a_transposed -> A is [K, M] row-major (lda >= M),
+ * b_transposed -> B is [K, N] row-major (ldb >= N); consumed in place as MN-major tcgen05 operands (no transpose pass).
+ * This is the shape of every weight-gradient GEMM (dW = dY^T . X) of the backward pass. */
+int mvc_gemm_bf16_ex(int M, int N, int K, const void* A, int64_t lda, int a_transposed, const void* B, int64_t ldb,
+                     int b_transposed, float beta, float* C, int64_t ldc, const float* bias, void* stream);
+
 /* dst (fp32 or bf16) [rows, Fa+Fv] = cat(a [rows,Fa], v [rows,Fv]) ; either
  * source may be NULL with width 0.  captioning.py:109 (torch.cat, audio first). */
 int mvc_concat_cast(const float* a, int Fa, const float* v, int Fv, int64_t rows, void* dst,

@@ -61,6 +61,24 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (the matrix is stored [K rows, MN contiguous], i.e. TRANSPOSED w.r.t. the K-major case), 128-byte
+// swizzle, tile built from TMA boxes {64 MN elements, 64 K rows}: one box = 64 rows (k) of 128 B; 8 consecutive k rows
+// form a 1024-byte swizzle atom (stride byte offset = 1024), boxes for MN = 64.. follow 8192 B later (leading byte
+// offset = 8192).  One UMMA (K = 16) consumes two k-groups: the start address advances by 2048 B per step.
+__device__ __forceinline__ uint64_t make_sw128_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;                   // leading byte offset: next 64-element block along MN
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: next group of 8 k rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_major(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
 // Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -424,7 +442,7 @@ constexpr int PG_EPI_BYTES = 4 * 32 * 33 * 4;
 constexpr int PG_BAR_OFF = PG_EPI_OFF + PG_EPI_BYTES;
 constexpr int PG_SMEM = PG_BAR_OFF + (2 * PG_STAGES + 4) * 8 + 16 + 1024;
 
-template <int MODE>
+template <int MODE, int A_MN = 0, int B_MN = 0>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M,
                             int N, int K, const __grid_constant__ TcEpilogue ep) {
@@ -479,15 +497,26 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           mbar_wait(empty_bar(stage), par ^ 1u);
           mbar_expect_tx(full_bar(stage), PG_STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * PG_STAGE_BYTES;
-          tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TC_BK, m0);
-          tma_load_2d(a_dst + PG_A_BYTES, &map_b, full_bar(stage), kb * TC_BK, n0);
+          if constexpr (A_MN) {                   // A stored [K, M]: two boxes of {64 m, 64 k}
+#pragma unroll
+            for (int i = 0; i < TC_BM / 64; ++i) tma_load_2d(a_dst + i * 8192, &map_a, full_bar(stage), m0 + i * 64, kb * TC_BK);
+          } else {
+            tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TC_BK, m0);
+          }
+          if constexpr (B_MN) {                   // B stored [K, N]: four boxes of {64 n, 64 k}
+#pragma unroll
+            for (int i = 0; i < PG_BN / 64; ++i)
+              tma_load_2d(a_dst + PG_A_BYTES + i * 8192, &map_b, full_bar(stage), n0 + i * 64, kb * TC_BK);
+          } else {
+            tma_load_2d(a_dst + PG_A_BYTES, &map_b, full_bar(stage), kb * TC_BK, n0);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, PG_BN);
+      constexpr uint32_t idesc = make_idesc_bf16_major(TC_BM, PG_BN, A_MN, B_MN);
       uint32_t it = 0;
       int ti = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
@@ -501,11 +530,13 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           mbar_wait(full_bar(stage), par);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * PG_STAGE_BYTES;
-          const uint64_t adesc = make_sw128_desc(a_addr);
-          const uint64_t bdesc = make_sw128_desc(a_addr + PG_A_BYTES);
+          const uint64_t adesc = A_MN ? make_sw128_desc_mn(a_addr) : make_sw128_desc(a_addr);
+          const uint64_t bdesc = B_MN ? make_sw128_desc_mn(a_addr + PG_A_BYTES) : make_sw128_desc(a_addr + PG_A_BYTES);
+          // per K = 16 step: K-major operands advance 32 B inside the swizzle atom, MN-major ones two k-groups (2048 B)
+          constexpr uint64_t a_step = A_MN ? (2048 >> 4) : 2, b_step = B_MN ? (2048 >> 4) : 2;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(tacc, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) ? 1u : 0u);
           umma_commit(empty_bar(stage));
         }
         umma_commit(tfull_bar(buf));
@@ -623,7 +654,10 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           if (gn < N) {
             float r = stg[rr * 33 + lane] + bv;
             if (ep.C) {
-              float* dst = ep.C + gm * ep.ldc + gn;
+              // output row: optionally un-permute tile-interleaved gate rows; columns >= split_col go to C2
+              const int64_t orow = ep.row_unperm_H ? (int64_t)gate_unperm(ep.row_unperm_H, (int)gm) : gm;
+              float* dst = (ep.C2 && gn >= ep.split_col) ? ep.C2 + orow * ep.ldc2 + (gn - ep.split_col)
+                                                         : ep.C + orow * ep.ldc + gn;
               if (ep.beta != 0.f) r += ep.beta * (*dst);
               *dst = r;
             }
@@ -784,15 +818,19 @@ static int max_active_clusters(int cs) {
   return n;
 }
 
-template <int MODE>
+template <int MODE, int A_MN = 0, int B_MN = 0>
 static int launch_tc_persist(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, TcEpilogue ep,
                              bool pdl, cudaStream_t st) {
   CUtensorMap ma, mb;
-  MVC_TRY(get_tensor_map(A, M, K, lda, TC_BM, &ma));
-  MVC_TRY(get_tensor_map(B, N, K, ldb, PG_BN, &mb));
+  // K-major operand [rows = M|N, cols = K], box {64 k, rows}; MN-major operand stored [K, M|N], box {64 mn, 64 k}
+  if (A_MN) MVC_TRY(get_tensor_map(A, K, M, lda, 64, &ma));
+  else MVC_TRY(get_tensor_map(A, M, K, lda, TC_BM, &ma));
+  if (B_MN) MVC_TRY(get_tensor_map(B, K, N, ldb, 64, &mb));
+  else MVC_TRY(get_tensor_map(B, N, K, ldb, PG_BN, &mb));
   static bool configured = false;
   if (!configured) {
-    MVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_persist_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+    MVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_persist_kernel<MODE, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  PG_SMEM));
     configured = true;
   }
   const int64_t tiles = cdiv(M, TC_BM) * cdiv(N, PG_BN);
@@ -807,7 +845,7 @@ static int launch_tc_persist(int M, int N, int K, const void* A, int64_t lda, co
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   ProfScope prof(PK_GEMM_TC, M, N, K, st);
-  MVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_persist_kernel<MODE>, ma, mb, M, N, K, ep));
+  MVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_persist_kernel<MODE, A_MN, B_MN>, ma, mb, M, N, K, ep));
   MVC_LAUNCH_CHECK();
   return 0;
 }
@@ -850,6 +888,14 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
     return launch_tc<128, 4, TC_MODE_CELL>(M, N, K, A, lda, B, ldb, ep, s, pdl, st);
   }
   // big GEMMs (>= half a wave of 128x256 tiles): persistent kernel with double-buffered TMEM accumulators
+  if (flags & (TC_FLAG_A_MN | TC_FLAG_B_MN)) {
+    // transposed operands (weight-gradient GEMMs: A stored [K,M] and / or B stored [K,N]): persistent kernel only
+    MVC_CHECK(ep.mode == TC_MODE_PLAIN, "tcgen05 GEMM: MN-major operands support the plain epilogue only");
+    const bool amn = flags & TC_FLAG_A_MN, bmn = flags & TC_FLAG_B_MN;
+    if (amn && bmn) return launch_tc_persist<TC_MODE_PLAIN, 1, 1>(M, N, K, A, lda, B, ldb, ep, pdl, st);
+    if (amn) return launch_tc_persist<TC_MODE_PLAIN, 1, 0>(M, N, K, A, lda, B, ldb, ep, pdl, st);
+    return launch_tc_persist<TC_MODE_PLAIN, 0, 1>(M, N, K, A, lda, B, ldb, ep, pdl, st);
+  }
   if (ep.mode == TC_MODE_ARGMAX) {
     MVC_CHECK(ep.amax_val && ep.amax_idx, "tcgen05 GEMM arg-max epilogue: null partial buffers");
     return launch_tc_persist<TC_MODE_ARGMAX>(M, N, K, A, lda, B, ldb, ep, pdl, st);
@@ -968,6 +1014,18 @@ extern "C" int mvc_vocab_argmax_bf16(int M, int V, int K, const void* h, int64_t
   float* pval = static_cast<float*>(workspace);
   int* pidx = reinterpret_cast<int*>(pval + (size_t)M * tc_gemm_argmax_tiles(V));
   return tc_gemm_argmax(M, V, K, h, ldh, out_w, ldw, out_b, pval, pidx, ids, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+extern "C" int mvc_gemm_bf16_ex(int M, int N, int K, const void* A, int64_t lda, int a_transposed, const void* B, int64_t ldb,
+                                int b_transposed, float beta, float* C, int64_t ldc, const float* bias, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  MVC_CHECK(A && B && C, "mvc_gemm_bf16_ex: null operand");
+  if (!a_transposed && !b_transposed) return mvc_gemm_bf16(M, N, K, A, lda, B, ldb, beta, C, ldc, bias, nullptr, 0, stream);
+  TcEpilogue ep{};
+  ep.mode = TC_MODE_PLAIN;
+  ep.beta = beta; ep.C = C; ep.ldc = ldc; ep.bias = bias;
+  return tc_gemm(M, N, K, A, lda, B, ldb, ep, (a_transposed ? TC_FLAG_A_MN : 0) | (b_transposed ? TC_FLAG_B_MN : 0),
+                 (cudaStream_t)stream);
 }
 
 extern "C" size_t mvc_vocab_topk_workspace_bytes(int M, int V) { return tc_gemm_topk_scratch_bytes(M, V); }

@@ -8,7 +8,9 @@ enum { TC_MODE_PLAIN = 0, TC_MODE_CELL = 1, TC_MODE_ARGMAX = 2, TC_MODE_TOPK = 3
 enum {
   TC_FLAG_PDL = 1,       // launch with programmatic stream serialization (the kernel waits on griddepcontrol itself)
   TC_FLAG_B_CONST = 2,   // operand B was complete before the previous kernel started: prefetch it before the dependency wait
-  TC_FLAG_NO_SPLIT = 4   // never split K
+  TC_FLAG_NO_SPLIT = 4,  // never split K
+  TC_FLAG_A_MN = 8,      // A is stored transposed: [K, M] row-major (ld = lda), consumed as an MN-major UMMA operand
+  TC_FLAG_B_MN = 16      // B is stored transposed: [K, N] row-major (ld = ldb)
 };
 
 struct TcEpilogue {
@@ -21,6 +23,12 @@ struct TcEpilogue {
   const float* bias;          // also the (permuted) gate bias in cell mode, may be null
   __nv_bfloat16* Cb;
   int64_t ldcb;
+  // persistent plain epilogue extras: un-permute tile-interleaved gate rows (row_unperm_H = H, 0 = off); send
+  // columns >= split_col to a second destination C2 (ld ldc2, column index rebased)
+  int row_unperm_H;
+  float* C2;
+  int64_t ldc2;
+  int split_col;
   // fused row arg-max (mode == TC_MODE_ARGMAX): per (row, 256-column tile) partial maximum of acc + bias
   float* amax_val;            // [ceil(N/256), M]
   int* amax_idx;              // [ceil(N/256), M]

@@ -201,6 +201,34 @@ def test_beam_bf16_width1_equals_greedy(dev):
     assert len(b5) == B and all(len(x) == 22 and x[0] == 1 for x in b5)
 
 
+@pytest.mark.parametrize("M,N,K", [(2048, 2176, 2944), (256, 512, 2944), (3201, 512, 2944), (130, 72, 200), (2048, 304, 136)])
+@pytest.mark.parametrize("ta,tb", [(1, 1), (1, 0), (0, 1)])
+def test_gemm_bf16_transposed_operands(dev, M, N, K, ta, tb):
+    """Weight-gradient shaped GEMMs: operands consumed in place as MN-major tcgen05 operands (no transpose pass)."""
+    from salstm import cabi
+    lib = cabi.lib()
+    g = torch.Generator().manual_seed(M + 3 * N + 5 * K + ta + 2 * tb)
+    a = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    b = torch.randn(N, K, generator=g).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = (a.double() @ b.double().t() + bias.double()).float()
+    pad = lambda x: x + (-x) % 8
+    def store(x, t):                     # operand as stored: [rows, K] or transposed [K, rows] with a padded pitch
+        if not t:
+            buf = torch.zeros(x.shape[0], pad(K) + 8, device=dev, dtype=torch.bfloat16)
+            buf[:, :K] = x
+            return buf, buf.shape[1]
+        buf = torch.zeros(K, pad(x.shape[0]) + 8, device=dev, dtype=torch.bfloat16)
+        buf[:, :x.shape[0]] = x.t()
+        return buf, buf.shape[1]
+    A, lda = store(a, ta)
+    Bm, ldb = store(b, tb)
+    c = torch.empty(M, N, device=dev)
+    cabi.check(lib.mvc_gemm_bf16_ex(M, N, K, cabi.ptr(A), lda, ta, cabi.ptr(Bm), ldb, tb, 0.0, cabi.ptr(c), N, cabi.ptr(bias),
+                                    cabi.stream_ptr()))
+    close(c, ref, atol=2e-4 * math.sqrt(K), rtol=1e-4)
+
+
 def test_gemm_bf16_rejects_bad_pitch(dev):
     from salstm import cabi
     lib = cabi.lib()

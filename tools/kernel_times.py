@@ -66,6 +66,14 @@ classes = [
     ("gemm_tc embtab", (1, V, 2048, 304)),
     ("gemm_tc gates greedy (B,4H,F+H)", (1, B, 2048, 2688)),
     ("gemm_tc uk", (1, B * T, 256, 2176)),
+    ("gemm_tc gx (SB,4H,Ep)", (1, S * B, 2048, 304)),
+    ("gemm_tn dW_cat (4H,F+H,SB)", (1, 2048, 2688, S * B)),
+    ("gemm_tn dW_out (V,H,SB)", (1, V, 512, S * B)),
+    ("gemm_nn dhall (SB,H,V)", (1, S * B, 512, V)),
+    ("gemm_tn dW_att (A,H,SB)", (1, 256, 512, S * B)),
+    ("gemm_tn dU (A,F,BT)", (1, 256, 2176, B * T)),
+    ("gemm_tn dW_ie (4H,E,SB)", (1, 2048, 300, S * B)),
+    ("gemm_nn dxemb (SB,E,4H)", (1, S * B, 300, 2048)),
     ("persistent recurrence fwd", (8, -1, -1, -1)),
     ("attention fwd", (3, -1, -1, -1)),
     ("attention bwd", (4, -1, -1, -1)),
