@@ -76,6 +76,24 @@ def test_decoder_sampling_and_greedy():
     assert torch.equal(s0, torch.random.get_rng_state())
 
 
+def test_batched_rng_draw_equals_reference_draws():
+    """The module layer draws its teacher-forcing flags with one torch.rand(n); the reference draws n times
+    torch.rand(1) (features_captioning.py:116).  Values and final generator state must be identical."""
+    import sys
+    from conftest import PKG
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    from salstm.functional import teacher_flags
+    for n, ratio in ((2, 0.5), (9, 0.3), (24, 0.7), (31, 1.0), (65, 0.5)):
+        caps = torch.ones(n, 1, dtype=torch.long)
+        torch.manual_seed(77)
+        ref = O.teacher_flags(caps, n, ratio)
+        s_ref = torch.random.get_rng_state()
+        torch.manual_seed(77)
+        got = teacher_flags(caps, n, ratio)
+        assert got == ref and torch.equal(s_ref, torch.random.get_rng_state())
+
+
 def _prefix(ids):
     ids = [int(x) for x in ids]
     return ids[: ids.index(O.EOS) + 1] if O.EOS in ids[1:] else ids
