@@ -360,9 +360,14 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
   if (all_tf) {
     // all S*B rows at once: log_softmax(h . out_w^T + out_b)
     float* lp = out_logp + (int64_t)B * V;
-    if (bf) MVC_TRY(gemm_nt(MVC_BF16, S * B, V, H, cptr(w.xh, (int64_t)B * ldx + F, es), ldx, w.outw, H, 0.f, lp, V, p->out_b, st));
-    else MVC_TRY(gemm_nt(MVC_F32, S * B, V, H, out_hid + (int64_t)B * H, H, p->out_w, H, 0.f, lp, V, p->out_b, st));
-    MVC_TRY(mvc_log_softmax_rows(lp, (int64_t)S * B, V, nullptr, st));
+    if (bf) {
+      // K-D: vocabulary projection with the log-sum-exp kept in the tcgen05 epilogue; `pre` is free scratch here
+      MVC_TRY(tc_gemm_logsoftmax(S * B, V, H, cptr(w.xh, (int64_t)B * ldx + F, es), ldx, w.outw, H, p->out_b, lp, V, w.pre,
+                                 sizeof(float) * (size_t)B * 4 * H, st));
+    } else {
+      MVC_TRY(gemm_nt(MVC_F32, S * B, V, H, out_hid + (int64_t)B * H, H, p->out_w, H, 0.f, lp, V, p->out_b, st));
+      MVC_TRY(mvc_log_softmax_rows(lp, (int64_t)S * B, V, nullptr, st));
+    }
   }
   return 0;
 }

@@ -438,7 +438,7 @@ constexpr int PG_A_BYTES = TC_BM * TC_BK * 2;            // 16 KB
 constexpr int PG_B_BYTES = PG_BN * TC_BK * 2;            // 32 KB
 constexpr int PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;  // 48 KB
 constexpr int PG_EPI_OFF = PG_STAGES * PG_STAGE_BYTES;   // 4 warps x [32][33] floats staging
-constexpr int PG_EPI_BYTES = 4 * 32 * 33 * 4;
+constexpr int PG_EPI_BYTES = 4 * 32 * 33 * 4 + 4 * PG_BN * 4;   // per-warp transpose staging + per-warp bias tile
 constexpr int PG_BAR_OFF = PG_EPI_OFF + PG_EPI_BYTES;
 constexpr int PG_SMEM = PG_BAR_OFF + (2 * PG_STAGES + 4) * 8 + 16 + 1024;
 
@@ -546,11 +546,16 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
   } else {
     const int q = warp & 3;                       // TMEM lane quarter of this warp
     float* stg = reinterpret_cast<float*>(smem + PG_EPI_OFF) + (warp - 2) * (32 * 33);
+    float* sbias = reinterpret_cast<float*>(smem + PG_EPI_OFF + 4 * 32 * 33 * 4) + (warp - 2) * PG_BN;   // bias of this tile
     pdl_wait();
     int ti = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
       const int buf = ti & 1;
       const int m0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * PG_BN;
+      // this tile's bias values -> the warp's private smem copy (broadcast reads below instead of 256 LDGs per thread)
+#pragma unroll
+      for (int i = lane; i < PG_BN; i += 32) sbias[i] = (ep.bias && n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
+      __syncwarp();
       mbar_wait(tfull_bar(buf), ((uint32_t)ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PG_BN);
@@ -569,7 +574,7 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           for (int j = 0; j < 32; ++j) {
             const int gn = gn0 + j;
             if (gn < N) {
-              const float x = __uint_as_float(v[j]) + (ep.bias ? __ldg(ep.bias + gn) : 0.f);
+              const float x = __uint_as_float(v[j]) + sbias[c * 32 + j];
               if (x > best) { best = x; bi = gn; }
             }
           }
@@ -598,7 +603,7 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int gn = gn0 + j;
-            x[j] = (gn < N) ? __uint_as_float(v[j]) + (ep.bias ? __ldg(ep.bias + gn) : 0.f) : -INFINITY;
+            x[j] = (gn < N) ? __uint_as_float(v[j]) + sbias[c * 32 + j] : -INFINITY;
             cmax = fmaxf(cmax, x[j]);
           }
           // online log-sum-exp, one rescale per 32-column chunk; the 32 exponentials are independent
@@ -636,35 +641,62 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           ep.lse_sum[tn * M + gm] = sm;
         }
       } else {
+      float lmx = -INFINITY, lsm = 0.f;           // K-D: running log-sum-exp of this row over the tile (optional)
 #pragma unroll 1
       for (int c = 0; c < PG_BN / 32; ++c) {
         const int gn0 = n0 + c * 32;
         if (gn0 >= N) break;
         uint32_t v[32];
         tmem_ld32(trow + (uint32_t)(c * 32), v);
+        if (ep.lse_max) {
+          float cmax = -INFINITY;
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gn = gn0 + j;
+            x[j] = (gn < N) ? __uint_as_float(v[j]) + sbias[c * 32 + j] : -INFINITY;
+            cmax = fmaxf(cmax, x[j]);
+          }
+          const float nmx = fmaxf(lmx, cmax);
+          float part = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part += __expf(x[j] - nmx);
+          lsm = lsm * __expf(lmx - nmx) + part;
+          lmx = nmx;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
         __syncwarp();
         const int gn = gn0 + lane;
-        const float bv = (ep.bias && gn < N) ? ep.bias[gn] : 0.f;
+        const float bv = sbias[c * 32 + lane];
+        const int64_t gm0 = (int64_t)m0 + q * 32;
+        const int nrows = (int)((M - gm0) < 32 ? (M - gm0) : 32);
+        if (gn < N && nrows > 0) {
+          float* dst = ep.C ? ep.C + gm0 * ep.ldc + gn : nullptr;
+          __nv_bfloat16* dstb = ep.Cb ? ep.Cb + gm0 * ep.ldcb + gn : nullptr;
+          const float beta = ep.beta;
 #pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int64_t gm = (int64_t)m0 + q * 32 + rr;
-          if (gm >= M) break;
-          if (gn < N) {
+          for (int rr = 0; rr < nrows; ++rr) {
             float r = stg[rr * 33 + lane] + bv;
-            if (ep.C) {
-              // output row: optionally un-permute tile-interleaved gate rows; columns >= split_col go to C2
-              const int64_t orow = ep.row_unperm_H ? (int64_t)gate_unperm(ep.row_unperm_H, (int)gm) : gm;
-              float* dst = (ep.C2 && gn >= ep.split_col) ? ep.C2 + orow * ep.ldc2 + (gn - ep.split_col)
-                                                         : ep.C + orow * ep.ldc + gn;
-              if (ep.beta != 0.f) r += ep.beta * (*dst);
+            if (dst) {
+              if (beta != 0.f) r += beta * (*dst);
               *dst = r;
+              dst += ep.ldc;
             }
-            if (ep.Cb) ep.Cb[gm * ep.ldcb + gn] = __float2bfloat16(r);
+            if (dstb) {
+              *dstb = __float2bfloat16(r);
+              dstb += ep.ldcb;
+            }
           }
         }
         __syncwarp();
+      }
+      if (ep.lse_max) {
+        const int64_t gm = (int64_t)m0 + q * 32 + lane;
+        if (gm < M) {
+          ep.lse_max[(int64_t)(tile % ntn) * M + gm] = lmx;
+          ep.lse_sum[(int64_t)(tile % ntn) * M + gm] = lsm;
+        }
       }
       }
       tc_fence_before();
@@ -979,6 +1011,48 @@ __global__ void topk_partials_kernel(const float* __restrict__ tval, const int* 
     cand_val[(int64_t)m * width + k] = bv[k] - lse;
     cand_idx[(int64_t)m * width + k] = bi[k];
   }
+}
+
+// K-D: x[r,:] (logits written by the GEMM) -> log-probs in place, the row's log-sum-exp coming from the per-tile
+// partials of the GEMM epilogue (one read + one write of the row instead of three reads + one write)
+__global__ void logsoftmax_finish_kernel(float* __restrict__ x, int64_t ld, int M, int V, int ntn,
+                                         const float* __restrict__ lmax, const float* __restrict__ lsum) {
+  __shared__ float s_lse;
+  const int64_t m = blockIdx.x;
+  if (threadIdx.x < 32) {
+    float mx = -INFINITY;
+    for (int t = threadIdx.x; t < ntn; t += 32) mx = fmaxf(mx, lmax[(int64_t)t * M + m]);
+    mx = warp_max(mx);
+    float sm = 0.f;
+    for (int t = threadIdx.x; t < ntn; t += 32) sm += lsum[(int64_t)t * M + m] * expf(lmax[(int64_t)t * M + m] - mx);
+    sm = warp_sum(sm);
+    if (threadIdx.x == 0) s_lse = mx + logf(sm);
+  }
+  __syncthreads();
+  const float lse = s_lse;
+  float* row = x + m * ld;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) row[v] -= lse;
+}
+
+int tc_gemm_logsoftmax(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
+                       float* C, int64_t ldc, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  const int ntn = (int)cdiv(N, PG_BN);
+  const bool fused = cdiv(M, TC_BM) * ntn >= kNumSMs / 2 && K >= 2 * TC_BK && scratch &&
+                     scratch_bytes >= (size_t)2 * M * ntn * sizeof(float);
+  TcEpilogue ep{};
+  ep.mode = TC_MODE_PLAIN;
+  ep.C = C; ep.ldc = ldc; ep.bias = bias;
+  if (fused) {
+    ep.lse_max = static_cast<float*>(scratch);
+    ep.lse_sum = ep.lse_max + (size_t)M * ntn;
+  }
+  MVC_TRY(tc_gemm(M, N, K, A, lda, B, ldb, ep, 0, st));
+  if (fused) {
+    logsoftmax_finish_kernel<<<(unsigned)M, 256, 0, st>>>(C, ldc, M, N, ntn, ep.lse_max, ep.lse_sum);
+    MVC_LAUNCH_CHECK();
+    return 0;
+  }
+  return mvc_log_softmax_rows(C, M, N, nullptr, st);      // small problems: separate row kernel (needs ldc == N)
 }
 
 size_t tc_gemm_topk_scratch_bytes(int M, int N) { return (size_t)M * cdiv(N, PG_BN) * (8 + 8 + 2) * 4; }

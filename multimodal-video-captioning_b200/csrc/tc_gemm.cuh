@@ -23,12 +23,6 @@ struct TcEpilogue {
   const float* bias;          // also the (permuted) gate bias in cell mode, may be null
   __nv_bfloat16* Cb;
   int64_t ldcb;
-  // persistent plain epilogue extras: un-permute tile-interleaved gate rows (row_unperm_H = H, 0 = off); send
-  // columns >= split_col to a second destination C2 (ld ldc2, column index rebased)
-  int row_unperm_H;
-  float* C2;
-  int64_t ldc2;
-  int split_col;
   // fused row arg-max (mode == TC_MODE_ARGMAX): per (row, 256-column tile) partial maximum of acc + bias
   float* amax_val;            // [ceil(N/256), M]
   int* amax_idx;              // [ceil(N/256), M]
@@ -61,6 +55,10 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
 int tc_gemm_argmax(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
                    float* pval, int* pidx, int64_t* out, int64_t* out2, int64_t out2_ld, int flags, cudaStream_t st);
 int tc_gemm_argmax_tiles(int N);
+// K-D: C = log_softmax(A . B^T + bias) row-wise: the GEMM epilogue keeps an online (max, sum exp) per row and tile,
+// a finishing kernel subtracts the row's log-sum-exp in place.  scratch >= 2 * M * ceil(N/256) floats.
+int tc_gemm_logsoftmax(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
+                       float* C, int64_t ldc, void* scratch, size_t scratch_bytes, cudaStream_t st);
 // K-E (beam): cand_val[m, k] / cand_idx[m, k] = the `width` (<= 8) largest log-softmax values of row m of
 // A . B^T + bias and their columns, without materialising logits or log-probs.
 size_t tc_gemm_topk_scratch_bytes(int M, int N);
