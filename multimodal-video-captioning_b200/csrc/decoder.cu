@@ -15,6 +15,8 @@
 //   * backward: every weight gradient is one GEMM over all S*B rows after the
 //     time loop; only d[ctx;h] = dgates.[W_ih[:,E:]|W_hh], the attention
 //     backward and dh += dwq.W stay inside the loop.
+#include <mutex>
+
 #include "recur.cuh"
 #include "step.cuh"
 
@@ -46,6 +48,29 @@ struct DecWs {
   unsigned* sync; // grid-barrier counter of the persistent recurrence kernel
   size_t bytes;
 };
+
+// A library-owned side stream per device (+ fork / join events): work that does not feed the recurrence (the weight
+// gradients of the vocabulary projection) runs there, on the SMs the persistent backward kernel leaves idle.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int get_side_stream(SideStream** out) {
+  static std::mutex mu;
+  static SideStream pool[64];
+  int dev = 0;
+  MVC_CUDA(cudaGetDevice(&dev));
+  MVC_CHECK(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(mu);
+  SideStream& s = pool[dev];
+  if (!s.stream) {
+    MVC_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    MVC_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    MVC_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return 0;
+}
 
 // tile-interleaved gate order (fused gate-GEMM + cell epilogue): bf16 path with H a multiple of 32
 static inline int dec_perm(const MvcDecoderDims* d) { return d->precision == MVC_BF16 && d->H % 32 == 0; }
@@ -465,6 +490,8 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   const char* hprev = cptr(w.xh, F, es);                      // rows = slots 0..S-1
 
   // ---- vocabulary projection backward (all steps at once)
+  SideStream* side = nullptr;
+  bool forked = false;
   if (dlogp) {
     const float* lp = out_logp + (int64_t)B * V;
     const float* dl = dlogp + (int64_t)B * V;
@@ -474,11 +501,18 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_TRY(mvc_transpose_to_bf16(p->out_w, 0, V, H, H, q.outwT, Vp, st));
       // dhall = dlogits . out_w
       MVC_TRY(mvc_gemm_bf16(SB, H, V, q.dlogits_b, Vp, q.outwT, Vp, 0.f, q.dhall, H, nullptr, nullptr, 0, st));
-      // dW_out = dlogits^T . hall ; db_out = colsum(dlogits) (fp32)
-      MVC_TRY(mvc_transpose_to_bf16(q.dlogits_b, 1, SB, V, Vp, q.dlogitsT, SBp, st));
-      MVC_TRY(mvc_transpose_to_bf16(hall, 1, SB, H, ldx, q.hallT, SBp, st));
-      MVC_TRY(mvc_gemm_bf16(V, H, SB, q.dlogitsT, SBp, q.hallT, SBp, 0.f, g->out_w, H, nullptr, nullptr, 0, st));
-      MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, st));
+      // dW_out = dlogits^T . hall ; db_out = colsum(dlogits) (fp32).  Nothing in the recurrence needs them: fork them
+      // onto the side stream, where they overlap the persistent backward kernel (joined before returning).
+      MVC_TRY(get_side_stream(&side));
+      MVC_CUDA(cudaEventRecord(side->fork, st));
+      MVC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      forked = true;
+      cudaStream_t ss = side->stream;
+      MVC_TRY(mvc_transpose_to_bf16(q.dlogits_b, 1, SB, V, Vp, q.dlogitsT, SBp, ss));
+      MVC_TRY(mvc_transpose_to_bf16(hall, 1, SB, H, ldx, q.hallT, SBp, ss));
+      MVC_TRY(mvc_gemm_bf16(V, H, SB, q.dlogitsT, SBp, q.hallT, SBp, 0.f, g->out_w, H, nullptr, nullptr, 0, ss));
+      MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, ss));
+      MVC_CUDA(cudaEventRecord(side->join, ss));
     } else {
       MVC_TRY(mvc_log_softmax_bwd(lp, dl, SB, V, q.dlogits, nullptr, st));
       MVC_TRY(mvc_gemm_f32(SB, H, V, 1.f, q.dlogits, V, 1, p->out_w, 1, H, 0.f, q.dhall, H, nullptr, st));
@@ -581,6 +615,7 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, q.wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, st));
   }
   MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, st));
+  if (forked) MVC_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   return 0;
 }
 

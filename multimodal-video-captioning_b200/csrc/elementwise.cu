@@ -443,7 +443,9 @@ namespace mvc {
 int launch_transpose_bf16(const void* src, int src_bf16, int64_t R, int64_t C, int64_t lds, void* dst, int64_t ldd,
                           int permH, cudaStream_t st) {
   if (R == 0 || C == 0) return 0;
-  if (src_bf16 && C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 &&
+  // fast path: 16-byte accesses.  C need not be a multiple of 8 as long as the source rows are padded to the pitch
+  // (the last vector of a row then reads pad columns, which are never written out: `c >= C` rows are skipped)
+  if (src_bf16 && lds % 8 == 0 && ldd % 8 == 0 && (C % 8 == 0 || ((C + 7) / 8) * 8 <= lds) &&
       ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
     dim3 g64((unsigned)cdiv(C, 64), (unsigned)cdiv(R, 64));
     transpose_bf16_tile64_kernel<<<g64, 256, 0, st>>>((const __nv_bfloat16*)src, R, C, lds, (__nv_bfloat16*)dst, ldd, permH);
