@@ -512,6 +512,12 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_TRY(mvc_transpose_to_bf16(hall, 1, SB, H, ldx, q.hallT, SBp, ss));
       MVC_TRY(mvc_gemm_bf16(V, H, SB, q.dlogitsT, SBp, q.hallT, SBp, 0.f, g->out_w, H, nullptr, nullptr, 0, ss));
       MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, ss));
+      // operand transposes of the post-loop weight-gradient GEMMs that only need forward data
+      MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, ss));
+      MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, ss));
+      MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
+      MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, ss));
+      MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, ss));
       MVC_CUDA(cudaEventRecord(side->join, ss));
     } else {
       MVC_TRY(mvc_log_softmax_bwd(lp, dl, SB, V, q.dlogits, nullptr, st));
@@ -598,20 +604,27 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     MVC_TRY(mvc_gemm_f32(SB, E, 4 * H, 1.f, q.dG, 4 * H, 1, p->w_ih, 1, E + F, 0.f, q.dxemb, E, nullptr, st));
   } else {
     // transposed bf16 operands (tcgen05 GEMM takes K-contiguous A[M,K], B[N,K])
+    const bool pre_t = forked;                 // xhT / featsT / xembT / wieT were produced on the side stream
+    if (forked) {
+      MVC_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+      forked = false;
+    }
     MVC_TRY(launch_transpose_bf16(q.dG_b, 1, SB, 4 * H, 4 * H, q.dGT, SBp, permH, st));   // natural gate rows
-    MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, st));
+    if (!pre_t) MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, st));
     MVC_TRY(mvc_transpose_to_bf16(q.dwq_b, 1, SB, A, A, q.dwqT, SBp, st));
     MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * T, A, A, q.dukT, BTp, st));
-    MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
+    if (!pre_t) MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
     const char* hprevT = cptr(q.xhT, (int64_t)F * SBp, 2);
     MVC_TRY(mvc_gemm_bf16(A, H, SB, q.dwqT, SBp, hprevT, SBp, 0.f, g->att_W, H, nullptr, nullptr, 0, st));
     MVC_TRY(mvc_gemm_bf16(A, F, B * T, q.dukT, BTp, q.featsT, BTp, 0.f, g->att_U, F, nullptr, nullptr, 0, st));
     MVC_TRY(mvc_gemm_bf16(4 * H, F, SB, q.dGT, SBp, q.xhT, SBp, 0.f, g->w_ih + E, E + F, nullptr, nullptr, 0, st));
     MVC_TRY(mvc_gemm_bf16(4 * H, H, SB, q.dGT, SBp, hprevT, SBp, 0.f, g->w_hh, H, nullptr, nullptr, 0, st));
-    MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, st));
-    MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, st));
+    if (!pre_t) {
+      MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, st));
+      MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, st));
+    }
     MVC_TRY(mvc_gemm_bf16(4 * H, E, SB, q.dGT, SBp, q.xembT, SBp, 0.f, g->w_ih, E + F, nullptr, nullptr, 0, st));
-    MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
+    if (!pre_t) MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
     MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, q.wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, st));
   }
   MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, st));
