@@ -219,18 +219,26 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
   const int Ep = bf ? pad8(E) : E;
   const int perm = dec_perm(d);
   MVC_CHECK(Fa + Fv == F, "decoder: Fa (%d) + Fv (%d) != in_feature_size (%d)", Fa, Fv, F);
-  MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, bf, st));
-  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, perm ? H : 0, st));
-  MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, bf, perm, st));
+  // weight packing / casting on the side stream, concurrent with the feature cast and the U.k GEMM
+  SideStream* side = nullptr;
+  MVC_TRY(get_side_stream(&side));
+  MVC_CUDA(cudaEventRecord(side->fork, st));
+  MVC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  cudaStream_t ss = side->stream;
+  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, perm ? H : 0, ss));
+  MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, bf, perm, ss));
   if (bf) {
-    MVC_TRY(launch_cast_pad_bf16(p->w_ih, 4 * H, E, E + F, Ep, w.wie, perm ? H : 0, st));
-    MVC_TRY(mvc_cast_bf16(p->att_U, w.U, (int64_t)A * F, st));
-    MVC_TRY(mvc_cast_bf16(p->att_W, w.W, (int64_t)A * H, st));
-    MVC_TRY(mvc_cast_bf16(p->out_w, w.outw, (int64_t)V * H, st));
-    if (need_embtab) MVC_TRY(launch_cast_pad_bf16(p->embedding, V, E, E, Ep, w.embb, 0, st));
+    MVC_TRY(launch_cast_pad_bf16(p->w_ih, 4 * H, E, E + F, Ep, w.wie, perm ? H : 0, ss));
+    MVC_TRY(mvc_cast_bf16(p->att_W, w.W, (int64_t)A * H, ss));
+    MVC_TRY(mvc_cast_bf16(p->out_w, w.outw, (int64_t)V * H, ss));
+    if (need_embtab) MVC_TRY(launch_cast_pad_bf16(p->embedding, V, E, E, Ep, w.embb, 0, ss));
   }
+  MVC_CUDA(cudaEventRecord(side->join, ss));
+  MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, bf, st));
+  if (bf) MVC_TRY(mvc_cast_bf16(p->att_U, w.U, (int64_t)A * F, st));
   // uk = feats . U^T      (temporal_attention.py:21, hoisted)
   MVC_TRY(gemm_nt(d->precision, B * T, A, F, w.feats, F, bf ? w.U : (const void*)p->att_U, F, 0.f, w.uk, A, nullptr, st));
+  MVC_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   if (need_embtab) {
     // embtab[v,:] = embedding[v] . W_ih[:, :E]^T + b_ih + b_hh
     if (bf) MVC_TRY(gemm_nt(MVC_BF16, V, 4 * H, Ep, w.embb, Ep, w.wie, Ep, 0.f, w.embtab, 4 * H, w.bsum, st));
@@ -609,14 +617,25 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_CUDA(cudaStreamWaitEvent(st, side->join, 0));
       forked = false;
     }
-    MVC_TRY(launch_transpose_bf16(q.dG_b, 1, SB, 4 * H, 4 * H, q.dGT, SBp, permH, st));   // natural gate rows
-    if (!pre_t) MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, st));
-    MVC_TRY(mvc_transpose_to_bf16(q.dwq_b, 1, SB, A, A, q.dwqT, SBp, st));
-    MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * T, A, A, q.dukT, BTp, st));
-    if (!pre_t) MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
+    if (!pre_t) {
+      MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, st));
+      MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
+    }
     const char* hprevT = cptr(q.xhT, (int64_t)F * SBp, 2);
-    MVC_TRY(mvc_gemm_bf16(A, H, SB, q.dwqT, SBp, hprevT, SBp, 0.f, g->att_W, H, nullptr, nullptr, 0, st));
-    MVC_TRY(mvc_gemm_bf16(A, F, B * T, q.dukT, BTp, q.featsT, BTp, 0.f, g->att_U, F, nullptr, nullptr, 0, st));
+    // the attention-parameter gradients (small GEMMs) run on the side stream next to the LSTM weight gradients
+    if (!side) MVC_TRY(get_side_stream(&side));
+    MVC_CUDA(cudaEventRecord(side->fork, st));
+    MVC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    {
+      cudaStream_t ss = side->stream;
+      MVC_TRY(mvc_transpose_to_bf16(q.dwq_b, 1, SB, A, A, q.dwqT, SBp, ss));
+      MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * T, A, A, q.dukT, BTp, ss));
+      MVC_TRY(mvc_gemm_bf16(A, H, SB, q.dwqT, SBp, hprevT, SBp, 0.f, g->att_W, H, nullptr, nullptr, 0, ss));
+      MVC_TRY(mvc_gemm_bf16(A, F, B * T, q.dukT, BTp, q.featsT, BTp, 0.f, g->att_U, F, nullptr, nullptr, 0, ss));
+      MVC_CUDA(cudaEventRecord(side->join, ss));
+      forked = true;
+    }
+    MVC_TRY(launch_transpose_bf16(q.dG_b, 1, SB, 4 * H, 4 * H, q.dGT, SBp, permH, st));   // natural gate rows
     MVC_TRY(mvc_gemm_bf16(4 * H, F, SB, q.dGT, SBp, q.xhT, SBp, 0.f, g->w_ih + E, E + F, nullptr, nullptr, 0, st));
     MVC_TRY(mvc_gemm_bf16(4 * H, H, SB, q.dGT, SBp, hprevT, SBp, 0.f, g->w_hh, H, nullptr, nullptr, 0, st));
     if (!pre_t) {
