@@ -11,6 +11,7 @@
 // T-rows split over thread groups and combined through shared memory.  Bound
 // by the read of keys [B,T,F] + uk [B,T,A]: HBM on first touch, L2 afterwards
 // (MSVD-shaped bf16 working set = 27 MB << 126 MB L2).
+#include <cstdlib>
 #include <mutex>
 #include <unordered_set>
 
@@ -500,6 +501,8 @@ static int ensure_big_smem(const void* kern) {
   std::lock_guard<std::mutex> lk(mu);
   if (done.count(kern)) return 0;
   MVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnMaxSmem));
+  // all of the unified L1 / shared array as shared memory: several staged CTAs per SM when their stages are small
+  MVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   done.insert(kern);
   return 0;
 }
@@ -566,6 +569,11 @@ int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
     int chunk = F;
     while (smem_for(fs, &chunk) > kAttnMaxSmem && fs < F / VN) ++fs;
     while ((int64_t)a.keys_batch * fs < kNumSMs && fs < 8 && chunk > 64 * VN) { ++fs; smem_for(fs, &chunk); }
+    // several waves of CTAs: keep the stage small enough for 3 resident CTAs per SM, so one CTA's bulk loads overlap
+    // another's score / context arithmetic (a single resident CTA serialises load -> compute: 2.6 TB/s at B=512)
+    if ((int64_t)a.keys_batch * fs > kNumSMs)
+      while (smem_for(fs, &chunk) > 72 * 1024 && fs < 8 && chunk > 64 * VN) ++fs;
+    if (const char* e = getenv("MVC_B200_ATTN_FS")) { fs = atoi(e); }   // tuning aid
     const size_t smem = smem_for(fs, &chunk);
     fs = (int)cdiv(F, chunk);
     if (smem <= kAttnMaxSmem) {

@@ -121,6 +121,12 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
+// bf16-path LSTM cell activations: ex2.approx + fast reciprocal (abs. error ~1e-7, far below the bf16 rounding of the
+// operands) -- a handful of instructions instead of the ~40-instruction IEEE expf / tanhf sequences, which made the
+// fused cell epilogues instruction-fetch bound (11 K SASS instructions executed once per CTA).
+__device__ __forceinline__ float sigmoid_ex2(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_ex2(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

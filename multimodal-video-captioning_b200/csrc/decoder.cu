@@ -93,8 +93,10 @@ static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
   w.wcat = ar.take<char>(4 * H * (F + H) * es);
   w.wie = bf ? ar.take<char>(4 * H * Ep * es) : nullptr;
   w.U = bf ? ar.take<char>(A * F * es) : nullptr;
-  w.W = bf ? ar.take<char>(A * H * es) : nullptr;
-  w.outw = bf ? ar.take<char>(V * H * es) : nullptr;
+  // bf16 vocabulary weights, followed (after padding to a multiple of 256 rows) by the attention query weights: one
+  // B operand [aux0 + A, H] lets the decode loops fold W.h of the next step into the vocabulary GEMM (TcAux)
+  w.outw = bf ? ar.take<char>((tc_aux_row0((int)V) + A) * H * es) : nullptr;
+  w.W = bf ? (void*)((char*)w.outw + (size_t)tc_aux_row0((int)V) * H * es) : nullptr;
   w.embb = bf ? ar.take<char>(V * Ep * es) : nullptr;
   w.bsum = ar.take<float>(4 * H);
   w.pre = ar.take<float>(B * 4 * H);
@@ -231,6 +233,8 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
     MVC_TRY(launch_cast_pad_bf16(p->w_ih, 4 * H, E, E + F, Ep, w.wie, perm ? H : 0, ss));
     MVC_TRY(mvc_cast_bf16(p->att_W, w.W, (int64_t)A * H, ss));
     MVC_TRY(mvc_cast_bf16(p->out_w, w.outw, (int64_t)V * H, ss));
+    if (tc_aux_row0(V) > V)
+      MVC_CUDA(cudaMemsetAsync((char*)w.outw + (size_t)V * H * 2, 0, (size_t)(tc_aux_row0(V) - V) * H * 2, ss));
     if (need_embtab) MVC_TRY(launch_cast_pad_bf16(p->embedding, V, E, E, Ep, w.embb, 0, ss));
   }
   MVC_CUDA(cudaEventRecord(side->join, ss));
@@ -721,6 +725,7 @@ extern "C" int mvc_decoder_greedy(const MvcDecoderDims* d, const MvcDecoderParam
     io.h_out32 = gw.h32;
     io.h_ld = H;
     io.first = (s == 0);
+    io.wq_ready = bf;
     MVC_TRY(step_forward(cfg, io, st));
     int64_t* nxt = gw.tok + (int64_t)((s + 1) & 1) * B;
     if (bf) {
@@ -729,8 +734,10 @@ extern "C" int mvc_decoder_greedy(const MvcDecoderDims* d, const MvcDecoderParam
       const int ntn = tc_gemm_argmax_tiles(V);
       float* pval = gw.logits;
       int* pidx = reinterpret_cast<int*>(gw.logits + (size_t)B * ntn);
+      // the same GEMM also produces wq = W.h_{s+1} for the next step's attention (auxiliary column block)
+      const TcAux aux{tc_aux_row0(V), d->A, gw.wq, d->A};
       MVC_TRY(tc_gemm_argmax(B, V, H, cptr(io.xh_dst, F, es), ldx, w.outw, H, p->out_b, pval, pidx, nxt, ids + (s + 1), L,
-                             TC_FLAG_PDL | TC_FLAG_B_CONST, st));
+                             TC_FLAG_PDL | TC_FLAG_B_CONST, st, &aux));
       continue;
     }
     MVC_TRY(gemm_nt(d->precision, B, V, H, (const char*)gw.h32, H, (const void*)p->out_w, H, 0.f, gw.logits, V, p->out_b, st));
@@ -857,11 +864,14 @@ template <typename XT>
 __global__ void beam_reorder_kernel(int B, int H, int F, int width, int t, int Lb, const int* __restrict__ sel_beam,
                                     const int64_t* __restrict__ tok, const XT* __restrict__ xh_src,
                                     XT* __restrict__ xh_dst, const float* __restrict__ c_src, float* __restrict__ c_dst,
-                                    const int* __restrict__ seq_src, int* __restrict__ seq_dst) {
+                                    const int* __restrict__ seq_src, int* __restrict__ seq_dst,
+                                    const float* __restrict__ wq_src, float* __restrict__ wq_dst, int A) {
   const int dst = blockIdx.x;             // k*B + b
   const int b = dst % B;
   const int src = sel_beam[dst] * B + b;
   const int64_t ldx = F + H;
+  if (wq_src)
+    for (int j = threadIdx.x; j < A; j += blockDim.x) wq_dst[(int64_t)dst * A + j] = wq_src[(int64_t)src * A + j];
   for (int j = threadIdx.x; j < H; j += blockDim.x) {
     xh_dst[(int64_t)dst * ldx + F + j] = xh_src[(int64_t)src * ldx + F + j];
     c_dst[(int64_t)dst * H + j] = c_src[(int64_t)src * H + j];
@@ -889,6 +899,7 @@ struct BeamWs {
   float* c[3];       // [W*B, H]  (prev, new-unordered, reordered)
   int* seq[2];       // [W*B, Lb]
   float* wq;         // [W*B, A]
+  float* wq2;        // [W*B, A] W.h of the new (not yet reordered) states, from the vocabulary GEMM
   float* alpha;      // [W*B, T]
   float* h32;        // [W*B, H]
   float* pre;        // [W*B, 4H]
@@ -917,6 +928,7 @@ static BeamWs beam_layout(const MvcDecoderDims* d, int width, void* base, size_t
     w.xh[i] = ar.take<char>(R * (d->F + d->H) * es);
   }
   w.wq = ar.take<float>(R * d->A);
+  w.wq2 = ar.take<float>(R * d->A);
   w.alpha = ar.take<float>(R * d->T);
   w.h32 = ar.take<float>(R * d->H);
   w.pre = ar.take<float>(R * 4 * d->H);
@@ -981,11 +993,15 @@ extern "C" int mvc_decoder_beam(const MvcDecoderDims* d, const MvcDecoderParams*
     io.h_out32 = bw.h32;
     io.h_ld = H;
     io.first = (t == 0);
+    const bool fused_topk = bf && V >= 64;
+    io.wq_ready = fused_topk;
     MVC_TRY(step_forward(cfg, io, st));
-    if (bf && V >= 64) {
-      // K-E: vocabulary projection with top-k + log-sum-exp in the tcgen05 epilogue (no [rows,V] logits)
+    if (fused_topk) {
+      // K-E: vocabulary projection with top-k + log-sum-exp in the tcgen05 epilogue (no [rows,V] logits); the same
+      // GEMM produces W.h of the new states (auxiliary column block), reordered with them below
+      const TcAux aux{tc_aux_row0(V), d->A, bw.wq2, d->A};
       MVC_TRY(tc_gemm_topk(rows, V, H, cptr(xh_new, F, es), ldx, w.outw, H, p->out_b, bw.logits, width, bw.cand_val,
-                           bw.cand_idx, TC_FLAG_PDL | TC_FLAG_B_CONST, st));
+                           bw.cand_idx, TC_FLAG_PDL | TC_FLAG_B_CONST, st, &aux));
     } else {
       MVC_TRY(gemm_nt(d->precision, rows, V, H, bf ? cptr(xh_new, F, es) : (const char*)bw.h32, bf ? ldx : H,
                       bf ? w.outw : (const void*)p->out_w, H, 0.f, bw.logits, V, p->out_b, st));
@@ -1000,11 +1016,12 @@ extern "C" int mvc_decoder_beam(const MvcDecoderDims* d, const MvcDecoderParams*
     if (bf)
       beam_reorder_kernel<__nv_bfloat16><<<(unsigned)R, 128, 0, st>>>(B, H, F, width, t, Lb, bw.sel, bw.tok[nx],
                                                                      (const __nv_bfloat16*)xh_new, (__nv_bfloat16*)xh_nxt,
-                                                                     c_new, c_nxt, bw.seq[cur], bw.seq[nx]);
+                                                                     c_new, c_nxt, bw.seq[cur], bw.seq[nx],
+                                                                     fused_topk ? bw.wq2 : nullptr, bw.wq, d->A);
     else
       beam_reorder_kernel<float><<<(unsigned)R, 128, 0, st>>>(B, H, F, width, t, Lb, bw.sel, bw.tok[nx],
                                                              (const float*)xh_new, (float*)xh_nxt, c_new, c_nxt,
-                                                             bw.seq[cur], bw.seq[nx]);
+                                                             bw.seq[cur], bw.seq[nx], nullptr, nullptr, 0);
     MVC_LAUNCH_CHECK();
     // rotate: reordered state becomes current
     void* tx = xh_cur; xh_cur = xh_nxt; xh_nxt = tx;

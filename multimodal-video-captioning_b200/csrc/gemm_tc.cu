@@ -185,11 +185,11 @@ __device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int
     float cn[4], hn[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float ig = sigmoid_f(g[0][j + e]), fg = sigmoid_f(g[1][j + e]);
-      const float gg = tanhf(g[2][j + e]), og = sigmoid_f(g[3][j + e]);
+      const float ig = sigmoid_ex2(g[0][j + e]), fg = sigmoid_ex2(g[1][j + e]);
+      const float gg = tanh_ex2(g[2][j + e]), og = sigmoid_ex2(g[3][j + e]);
       g[0][j + e] = ig; g[1][j + e] = fg; g[2][j + e] = gg; g[3][j + e] = og;
       cn[e] = fg * cpv[e] + ig * gg;
-      hn[e] = og * tanhf(cn[e]);
+      hn[e] = og * tanh_ex2(cn[e]);
     }
     *reinterpret_cast<float4*>(co + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
     if (h1) *reinterpret_cast<float4*>(h1 + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
@@ -554,16 +554,16 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       const int m0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * PG_BN;
       // this tile's bias values -> the warp's private smem copy (broadcast reads below instead of 256 LDGs per thread)
 #pragma unroll
-      for (int i = lane; i < PG_BN; i += 32) sbias[i] = (ep.bias && n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
+      const int nmain = (MODE != TC_MODE_PLAIN && ep.aux_C) ? ep.n_main : N;   // columns that carry a bias / reduction
+      for (int i = lane; i < PG_BN; i += 32) sbias[i] = (ep.bias && n0 + i < nmain) ? __ldg(ep.bias + n0 + i) : 0.f;
       __syncwarp();
       mbar_wait(tfull_bar(buf), ((uint32_t)ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PG_BN);
-      if constexpr (MODE == TC_MODE_ARGMAX) {
-        // K-E: row-wise arg-max of (acc + bias) over this tile's columns; the logits never leave the SM.
-        // Thread = row; columns ascend, so a strict > keeps the lowest index on ties.
-        float best = -INFINITY;
-        int bi = 0x7fffffff;
+      if (MODE != TC_MODE_PLAIN && ep.aux_C && n0 >= ep.aux_n0) {
+        // auxiliary column block: plain fp32 store (32x32 chunks transposed through smem -> 128-byte row segments)
+        const int64_t gm0 = (int64_t)m0 + q * 32;
+        const int nrows = (int)((M - gm0) < 32 ? (M - gm0) : 32);
 #pragma unroll 1
         for (int c = 0; c < PG_BN / 32; ++c) {
           const int gn0 = n0 + c * 32;
@@ -571,9 +571,34 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           uint32_t v[32];
           tmem_ld32(trow + (uint32_t)(c * 32), v);
 #pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+          __syncwarp();
+          const int gn = gn0 + lane;
+          if (gn < N && nrows > 0) {
+            float* dst = ep.aux_C + gm0 * ep.aux_ld + (gn - ep.aux_n0);
+#pragma unroll 4
+            for (int rr = 0; rr < nrows; ++rr) {
+              *dst = stg[rr * 33 + lane];
+              dst += ep.aux_ld;
+            }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (MODE == TC_MODE_ARGMAX) {
+        // K-E: row-wise arg-max of (acc + bias) over this tile's columns; the logits never leave the SM.
+        // Thread = row; columns ascend, so a strict > keeps the lowest index on ties.
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll 1
+        for (int c = 0; c < PG_BN / 32; ++c) {
+          const int gn0 = n0 + c * 32;
+          if (gn0 >= nmain) break;
+          uint32_t v[32];
+          tmem_ld32(trow + (uint32_t)(c * 32), v);
+#pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int gn = gn0 + j;
-            if (gn < N) {
+            if (gn < nmain) {
               const float x = __uint_as_float(v[j]) + sbias[c * 32 + j];
               if (x > best) { best = x; bi = gn; }
             }
@@ -595,7 +620,7 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
 #pragma unroll 1
         for (int c = 0; c < PG_BN / 32; ++c) {
           const int gn0 = n0 + c * 32;
-          if (gn0 >= N) break;
+          if (gn0 >= nmain) break;
           uint32_t v[32];
           tmem_ld32(trow + (uint32_t)(c * 32), v);
           float x[32];
@@ -603,7 +628,7 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int gn = gn0 + j;
-            x[j] = (gn < N) ? __uint_as_float(v[j]) + sbias[c * 32 + j] : -INFINITY;
+            x[j] = (gn < nmain) ? __uint_as_float(v[j]) + sbias[c * 32 + j] : -INFINITY;
             cmax = fmaxf(cmax, x[j]);
           }
           // online log-sum-exp, one rescale per 32-column chunk; the 32 exponentials are independent
@@ -939,12 +964,21 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
   if (mt * cdiv(N, PG_BN) >= kNumSMs / 2 && K >= 2 * TC_BK)
     return launch_tc_persist<TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, pdl, st);
   const int64_t t128 = mt * cdiv(N, 128), t64 = mt * cdiv(N, 64), t32 = mt * cdiv(N, 32);
-  // widest tile whose CTA count (tiles x K-splits) covers most of the 148 SMs
   const int s128 = splits_for(t128, max_active_clusters<128, 4, TC_MODE_PLAIN>);
   const int s64 = splits_for(t64, max_active_clusters<64, 6, TC_MODE_PLAIN>);
   const int s32 = splits_for(t32, max_active_clusters<32, 8, TC_MODE_PLAIN>);
-  if (t128 * s128 >= 96) return launch_tc<128, 4, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s128, pdl, st);
-  if (t64 * s64 >= 96) return launch_tc<64, 6, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s64, pdl, st);
+  // The kernel is a serial chain of k-blocks per CTA (latency bound at these sizes), so pick the tile width whose
+  // CTAs run the FEWEST k-blocks: waves x ceil(nkb / splits), weighted by the per-k-block cost of the tile width
+  // (a narrower B tile is a little cheaper, but re-reads A more often).  Ties go to the wider tile.
+  // A split adds the park + DSMEM reduction of the partial tile, proportional to the tile width (measured: ~6 us at
+  // BN = 128 vs ~1.5 us at BN = 32, in units of one k-block ~ 0.5 us).
+  auto cost = [&](int64_t tiles, int s, double w, double red) {
+    const int64_t waves = s > 1 ? 1 : cdiv(tiles, kNumSMs);
+    return (double)(waves * cdiv(nkb, s)) * w + (s > 1 ? red : 0.0);
+  };
+  const double c128 = cost(t128, s128, 1.0, 12.0), c64 = cost(t64, s64, 0.85, 6.0), c32 = cost(t32, s32, 0.75, 3.0);
+  if (c128 <= c64 && c128 <= c32) return launch_tc<128, 4, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s128, pdl, st);
+  if (c64 <= c32) return launch_tc<64, 6, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s64, pdl, st);
   return launch_tc<32, 8, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s32, pdl, st);
 }
 
@@ -964,13 +998,20 @@ __global__ void argmax_partials_kernel(const float* __restrict__ pval, const int
 }
 
 int tc_gemm_argmax(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
-                   float* pval, int* pidx, int64_t* out, int64_t* out2, int64_t out2_ld, int flags, cudaStream_t st) {
+                   float* pval, int* pidx, int64_t* out, int64_t* out2, int64_t out2_ld, int flags, cudaStream_t st,
+                   const TcAux* aux) {
   TcEpilogue ep{};
   ep.mode = TC_MODE_ARGMAX;
   ep.bias = bias;
   ep.amax_val = pval;
   ep.amax_idx = pidx;
-  MVC_TRY(tc_gemm(M, N, K, A, lda, B, ldb, ep, flags, st));
+  int Nt = N;
+  if (aux) {
+    MVC_CHECK(aux->C && aux->n0 % PG_BN == 0 && aux->n0 >= N && aux->cols > 0, "fused arg-max: bad auxiliary block");
+    ep.aux_C = aux->C; ep.aux_ld = aux->ld; ep.aux_n0 = aux->n0; ep.n_main = N;
+    Nt = aux->n0 + aux->cols;
+  }
+  MVC_TRY(tc_gemm(M, Nt, K, A, lda, B, ldb, ep, flags, st));
   argmax_partials_kernel<<<(unsigned)cdiv(M, 128), 128, 0, st>>>(pval, pidx, M, (int)cdiv(N, PG_BN), out, out2, out2_ld);
   MVC_LAUNCH_CHECK();
   return 0;
@@ -1058,7 +1099,7 @@ int tc_gemm_logsoftmax(int M, int N, int K, const void* A, int64_t lda, const vo
 size_t tc_gemm_topk_scratch_bytes(int M, int N) { return (size_t)M * cdiv(N, PG_BN) * (8 + 8 + 2) * 4; }
 
 int tc_gemm_topk(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
-                 void* scratch, int width, float* cand_val, int* cand_idx, int flags, cudaStream_t st) {
+                 void* scratch, int width, float* cand_val, int* cand_idx, int flags, cudaStream_t st, const TcAux* aux) {
   MVC_CHECK(width >= 1 && width <= 8, "fused top-k: width %d not in [1,8]", width);
   const int ntn = (int)cdiv(N, PG_BN);
   float* tval = static_cast<float*>(scratch);
@@ -1069,7 +1110,13 @@ int tc_gemm_topk(int M, int N, int K, const void* A, int64_t lda, const void* B,
   ep.mode = TC_MODE_TOPK;
   ep.bias = bias;
   ep.topk_val = tval; ep.topk_idx = tidx; ep.lse_max = lmax; ep.lse_sum = lsum;
-  MVC_TRY(tc_gemm(M, N, K, A, lda, B, ldb, ep, flags, st));
+  int Nt = N;
+  if (aux) {
+    MVC_CHECK(aux->C && aux->n0 % PG_BN == 0 && aux->n0 >= N && aux->cols > 0, "fused top-k: bad auxiliary block");
+    ep.aux_C = aux->C; ep.aux_ld = aux->ld; ep.aux_n0 = aux->n0; ep.n_main = N;
+    Nt = aux->n0 + aux->cols;
+  }
+  MVC_TRY(tc_gemm(M, Nt, K, A, lda, B, ldb, ep, flags, st));
   topk_partials_kernel<<<(unsigned)cdiv(M, 128), 128, 0, st>>>(tval, tidx, lmax, lsum, M, ntn, width, cand_val, cand_idx);
   MVC_LAUNCH_CHECK();
   return 0;

@@ -245,7 +245,7 @@ recur_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_consta
       float di[2], df[2], dg[2], dO[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const float tc = tanhf(cnv[e]);
+        const float tc = tanh_ex2(cnv[e]);
         const float dct = dcr[i][e] + dhv[e] * ogv[e] * (1.f - tc * tc);
         di[e] = dct * ggv[e] * igv[e] * (1.f - igv[e]);
         df[e] = dct * cpv[e] * fgv[e] * (1.f - fgv[e]);

@@ -474,10 +474,10 @@ recur_fwd_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_consta
         float cn[2], hn[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const float ig = sigmoid_f(g2[0][e]), fg = sigmoid_f(g2[1][e]), gg = tanhf(g2[2][e]), og = sigmoid_f(g2[3][e]);
+          const float ig = sigmoid_ex2(g2[0][e]), fg = sigmoid_ex2(g2[1][e]), gg = tanh_ex2(g2[2][e]), og = sigmoid_ex2(g2[3][e]);
           g2[0][e] = ig; g2[1][e] = fg; g2[2][e] = gg; g2[3][e] = og;
           cn[e] = fg * cpv[e] + ig * gg;
-          hn[e] = og * tanhf(cn[e]);
+          hn[e] = og * tanh_ex2(cn[e]);
         }
         const size_t nrow = (size_t)(s + 1) * B + row;
         *reinterpret_cast<float2*>(p.c + nrow * H + ug0) = make_float2(cn[0], cn[1]);

@@ -103,7 +103,8 @@ struct StepFwd {
   const int64_t* tokens; // rows of embtab to gather, or null
   float* h_out32;        // fp32 h_{s+1} (ld h_ld), may be null
   int64_t h_ld;
-  bool first;            // h_s == 0: skip the wq GEMM
+  bool first;
+  bool wq_ready;       // wq already holds W.h_s (written by the previous vocabulary GEMM), skip the projection            // h_s == 0: skip the wq GEMM
 };
 
 static inline int step_forward(const StepCfg& c, const StepFwd& io, cudaStream_t st) {
@@ -114,6 +115,8 @@ static inline int step_forward(const StepCfg& c, const StepFwd& io, cudaStream_t
   // wq = h_s . W^T                                   (temporal_attention.py:20)
   if (io.first) {
     MVC_CUDA(cudaMemsetAsync(io.wq, 0, sizeof(float) * (size_t)R * c.A, st));
+  } else if (io.wq_ready) {
+    // already produced by the auxiliary column block of the previous step's vocabulary GEMM (greedy / beam decode)
   } else if (bf) {
     MVC_TRY(gemm_tc_chain(R, c.A, c.H, cptr(io.xh_src, c.F, es), ldx, c.attW, c.H, 0.f, io.wq, c.A, nullptr, 0, true, st));
   } else {

@@ -31,6 +31,14 @@ struct TcEpilogue {
   int* topk_idx;              // [ceil(N/256), 8, M]
   float* lse_max;             // [ceil(N/256), M]
   float* lse_sum;             // [ceil(N/256), M]
+  // arg-max / top-k modes, optional auxiliary column block: B rows [aux_n0, N) (aux_n0 a multiple of 256, >= n_main)
+  // are a second weight matrix applied to the same A; its product is stored plainly to aux_C[m, n - aux_n0] while
+  // columns [0, n_main) go through the arg-max / top-k reduction (rows [n_main, aux_n0) of B are padding).
+  // Used to fold the attention query projection W.h of the NEXT decode step into this step's vocabulary GEMM.
+  float* aux_C;
+  int64_t aux_ld;
+  int aux_n0;
+  int n_main;
   // fused LSTM cell (mode == TC_MODE_CELL): N = 4H, columns permuted (j/16)*64 + gate*16 + j%16
   int H;
   const float* gx;            // [M,4H] hoisted input projection (permuted columns), ld gx_ld, may be null
@@ -52,8 +60,15 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
             cudaStream_t st);
 // K-E: ids[m] = argmax_n (A[m,:] . B[n,:] + bias[n]) without materialising the logits (lowest index wins ties);
 // pval / pidx: [M, tc_gemm_argmax_tiles(N)] scratch; out2 (optional) receives the same ids with stride out2_ld.
+struct TcAux {          // auxiliary column block of the arg-max / top-k GEMMs (see TcEpilogue::aux_C)
+  int n0, cols;
+  float* C;
+  int64_t ld;
+};
+inline int tc_aux_row0(int N) { return (N + 255) / 256 * 256; }   // first B row of the auxiliary block for N main rows
 int tc_gemm_argmax(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
-                   float* pval, int* pidx, int64_t* out, int64_t* out2, int64_t out2_ld, int flags, cudaStream_t st);
+                   float* pval, int* pidx, int64_t* out, int64_t* out2, int64_t out2_ld, int flags, cudaStream_t st,
+                   const TcAux* aux = nullptr);
 int tc_gemm_argmax_tiles(int N);
 // K-D: C = log_softmax(A . B^T + bias) row-wise: the GEMM epilogue keeps an online (max, sum exp) per row and tile,
 // a finishing kernel subtracts the row's log-sum-exp in place.  scratch >= 2 * M * ceil(N/256) floats.
@@ -63,7 +78,8 @@ int tc_gemm_logsoftmax(int M, int N, int K, const void* A, int64_t lda, const vo
 // A . B^T + bias and their columns, without materialising logits or log-probs.
 size_t tc_gemm_topk_scratch_bytes(int M, int N);
 int tc_gemm_topk(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias,
-                 void* scratch, int width, float* cand_val, int* cand_idx, int flags, cudaStream_t st);
+                 void* scratch, int width, float* cand_val, int* cand_idx, int flags, cudaStream_t st,
+                 const TcAux* aux = nullptr);
 
 // "Tile-interleaved" gate order used by the fused cell epilogues: hidden units are grouped in blocks of 16 and
 // each block stores its four gates back to back -- column (j/16)*64 + gate*16 + j%16 is nn.LSTM row gate*H + j.

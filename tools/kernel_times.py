@@ -74,6 +74,19 @@ classes = [
     ("gemm_tn dU (A,F,BT)", (1, 256, 2176, B * T)),
     ("gemm_tn dW_ie (4H,E,SB)", (1, 2048, 300, S * B)),
     ("gemm_nn dxemb (SB,E,4H)", (1, S * B, 300, 2048)),
+    ("recon-g xproj (SB,4F,H)", (1, S * B, 8704, 512)),
+    ("recon-g gates+cell (B,4F,F)", (1, B, 8704, 2176)),
+    ("recon-g dh (B,F,4F)", (1, B, 2176, 8704)),
+    ("recon-g dW_hh (4F,F,SB)", (1, 8704, 2176, S * B)),
+    ("recon-g dW_ih (4F,H,SB)", (1, 8704, 512, S * B)),
+    ("recon-g dx (SB,H,4F)", (1, S * B, 512, 8704)),
+    ("recon-l wq (B,A,F)", (1, B, 256, 2176)),
+    ("recon-l gates+cell (B,4F,H+F)", (1, B, 8704, 2688)),
+    ("recon-l dxh (B,H+F,4F)", (1, B, 2688, 8704)),
+    ("recon-l dq (B,F,A)", (1, B, 2176, 256)),
+    ("recon-l dW_hh (4F,F,TB)", (1, 8704, 2176, T * B)),
+    ("recon-l dW_ih (4F,H,TB)", (1, 8704, 512, T * B)),
+    ("recon-l uk (BL,A,H)", (1, B * L, 256, 512)),
     ("persistent recurrence fwd", (8, -1, -1, -1)),
     ("attention fwd", (3, -1, -1, -1)),
     ("attention bwd", (4, -1, -1, -1)),
