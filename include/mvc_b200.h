@@ -55,6 +55,9 @@ int mvc_prof_collect(double* total_ms, long long* launches);
  * persistent recurrence kernel (CTA 0); NULL switches it off. */
 int mvc_debug_set_recur_prof(long long* dev_buf);
 int mvc_debug_set_recur_bwd_prof(long long* dev_buf);
+/* Debug: device buffer (8 uint64 per CTA of the staged soft-attention forward kernel, CTA index = blockIdx.y *
+ * gridDim.x + blockIdx.x) that receives %globaltimer stamps of its phases; NULL switches it off. */
+int mvc_debug_set_attn_prof(unsigned long long* dev_buf);
 
 /* ------------------------------------------------------------------ */
 /* Building-block kernels (each is unit-tested against the oracle)     */

@@ -249,7 +249,7 @@ constexpr int ATT_MAXR = 8;      // frame rounds per warp held in registers (for
 constexpr int ATT_MAXR_BWD = 4;  // backward, 16 warps
 
 template <typename KT, bool FAST, int AV, int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 2)
 attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int NW = NT / 32;
@@ -258,108 +258,176 @@ attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
   const int kb = blockIdx.x;                     // key block; rows kb, kb + keys_batch, ... (beams) share it
   const int nq = a.B / a.keys_batch;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int f0 = blockIdx.y * chunk, f1 = min(F, f0 + chunk), ncols = f1 - f0;
+  // The gridDim.y CTAs of one key block form a thread-block cluster: CTA r stages F-chunk r of the keys and scores
+  // the frames [r*Tc, (r+1)*Tc); the scores are exchanged through distributed shared memory, so no work is repeated
+  // however finely the row is split.  Everything loop invariant (keys chunk, U.k slab) arrives by TMA bulk copies:
+  // register prefetches of U.k queued ~300 LDGs per SM in front of every other load (3 us before the first score).
+  const int cl = gridDim.y, rank = blockIdx.y;
+  const int f0 = rank * chunk, f1 = min(F, f0 + chunk), ncols = f1 - f0;
+  const int Tc = (T + cl - 1) / cl, t0 = min(T, rank * Tc), t1 = min(T, t0 + Tc);
+  const int Tp = (T + 3) & ~3;
   const size_t stage_bytes = ((size_t)T * chunk * sizeof(KT) + 127) & ~size_t(127);
   KT* sK = reinterpret_cast<KT*>(smem_raw);
-  float* sQ = reinterpret_cast<float*>(smem_raw + stage_bytes);
+  float* sU = reinterpret_cast<float*>(smem_raw + stage_bytes);     // [Tc][A] U.k rows of this CTA's frames
+  float* sQ = sU + (size_t)Tc * A;
   float* sW = sQ + A;
-  float* sE = sW + A;
-  float* sRed = sE + ((T + 3) & ~3);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sRed + 32);
-  const uint32_t bar = smem_u32(mbar);
-
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0 && ncols > 0) {
+  float* sE = sW + A;                            // [2][Tp]: raw scores, double buffered over queries
+  float* sP = sE + 2 * Tp;                       // [Tp]: soft-max weights of the current query
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sP + Tp);
+  const uint32_t bar_u = smem_u32(mbar), bar_k = smem_u32(mbar + 1);
+  unsigned long long* prof = a.prof ? a.prof + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+#define AT_STAMP(i) do { if (prof && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); prof[i] = t_; } } while (0)
+  AT_STAMP(0);
+  if (wid == 0) {
     const KT* kbase = reinterpret_cast<const KT*>(a.keys) + (int64_t)kb * a.k_sb + f0;
     const uint32_t row_bytes = (uint32_t)(ncols * sizeof(KT));
-    mbar_expect_tx(bar, row_bytes * (uint32_t)T);
-    for (int t = 0; t < T; ++t)
-      bulk_load_1d(smem_u32(sK + (size_t)t * chunk), kbase + (int64_t)t * a.k_st, row_bytes, bar);
-  }
-  // loop-invariant operands: U.k rows of this batch row -> registers, w -> smem
-  float ur[ATT_MAXR][AV];
-  const float* ukb = a.uk + (int64_t)kb * T * A;
-#pragma unroll
-  for (int r = 0; r < ATT_MAXR; ++r) {
-    const int t = wid + r * NW;
-    if (t < T) {
-#pragma unroll
-      for (int k = 0; k < AV; ++k) ur[r][k] = __ldg(ukb + (int64_t)t * A + lane + 32 * k);
+    const bool one_copy = (ncols == chunk && a.k_st == chunk);       // contiguous [T, F] block
+    if (lane == 0) {
+      mbar_init(bar_u, 1);
+      mbar_init(bar_k, 1);
+      fence_mbar_init();
+      // U.k slab first (the scores need it first), then the keys chunk
+      const uint32_t ub = (uint32_t)((t1 - t0) * A * sizeof(float));
+      if (ub) {
+        mbar_expect_tx(bar_u, ub);
+        bulk_load_1d(smem_u32(sU), a.uk + ((int64_t)kb * T + t0) * A, ub, bar_u);
+      }
+      if (ncols > 0) {
+        mbar_expect_tx(bar_k, row_bytes * (uint32_t)T);
+        if (one_copy) bulk_load_1d(smem_u32(sK), kbase, row_bytes * (uint32_t)T, bar_k);
+      }
     }
+    __syncwarp();
+    // per-frame copies of an F-chunk: issued by the 32 lanes in parallel (one cp.async.bulk costs its issuing thread
+    // ~0.1 us, so a single thread would spend 3 us on T = 30 of them)
+    if (ncols > 0 && !one_copy)
+      for (int t = lane; t < T; t += 32)
+        bulk_load_1d(smem_u32(sK + (size_t)t * chunk), kbase + (int64_t)t * a.k_st, row_bytes, bar_k);
   }
   for (int i = tid; i < A; i += NT) sW[i] = a.w[i];
+  __syncthreads();                  // barriers initialised, sW visible
+  if (cl > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // "I am running" (waited below)
+  AT_STAMP(1);
   pdl_trigger();
   pdl_wait();                       // the query (wq) comes from the preceding kernel
+  if (cl > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // every peer CTA has started
+  AT_STAMP(2);
+  const uint32_t sE_u32 = smem_u32(sE);
   for (int qi = 0; qi < nq; ++qi) {
-  const int b = qi * a.keys_batch + kb;
-  __syncthreads();                  // previous query's readers of sQ / sE are done
-  for (int i = tid; i < A; i += NT) sQ[i] = a.wq[(int64_t)b * A + i] + a.bias[i];
-  __syncthreads();
+    const int b = qi * a.keys_batch + kb;
+    float* sEq = sE + (qi & 1) * Tp;
+    if (qi) __syncthreads();        // previous query's readers of sQ / sP are done
+    for (int i = tid; i < A; i += NT) sQ[i] = a.wq[(int64_t)b * A + i] + a.bias[i];
+    __syncthreads();
+    if (qi == 0 && t1 > t0) mbar_wait(bar_u, 0);
+    AT_STAMP(3);
+    float qv[AV], wv[AV];
 #pragma unroll
-  for (int r = 0; r < ATT_MAXR; ++r) {
-    const int t = wid + r * NW;
-    if (t < T) {
+    for (int k = 0; k < AV; ++k) { qv[k] = sQ[lane + 32 * k]; wv[k] = sW[lane + 32 * k]; }
+    for (int t = t0 + wid; t < t1; t += NW) {
+      const float* urow = sU + (size_t)(t - t0) * A + lane;
       float e = 0.f;
 #pragma unroll
-      for (int k = 0; k < AV; ++k) e = fmaf(sW[lane + 32 * k], tanh_sel<FAST>(sQ[lane + 32 * k] + ur[r][k]), e);
+      for (int k = 0; k < AV; ++k) e = fmaf(wv[k], tanh_sel<FAST>(qv[k] + urow[32 * k]), e);
       e = warp_sum(e);
       if (lane == 0) {
         if (a.mask && !a.mask[b * a.m_sb + t * a.m_st]) e = -INFINITY;
-        sE[t] = e;
+        if (cl == 1) {
+          sEq[t] = e;
+        } else {
+          const uint32_t off = sE_u32 + (uint32_t)(((qi & 1) * Tp + t) * 4);
+          for (int pr = 0; pr < cl; ++pr) {
+            uint32_t dst;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(off), "r"(pr));
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst), "f"(e) : "memory");
+          }
+        }
       }
     }
-  }
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int t = tid; t < T; t += NT) mx = fmaxf(mx, sE[t]);
-  mx = block_max(mx, sRed);
-  float s = 0.f;
-  for (int t = tid; t < T; t += NT) {
-    const float p = FAST ? __expf(sE[t] - mx) : expf(sE[t] - mx);
-    sE[t] = p;
-    s += p;
-  }
-  s = block_sum(s, sRed);
-  const float inv = 1.f / s;
-  for (int t = tid; t < T; t += NT) {
-    const float p = sE[t] * inv;
-    sE[t] = p;
-    if (blockIdx.y == 0) a.alpha[(int64_t)b * T + t] = p;
-  }
-  __syncthreads();
-  if (ncols <= 0) continue;
-  mbar_wait(bar, 0);                // keys chunk has landed (immediate for every query after the first)
-  const int nvec = ncols / VN;
-  for (int v = tid; v < nvec; v += NT) {
-    float acc[VN];
-#pragma unroll
-    for (int i = 0; i < VN; ++i) acc[i] = 0.f;
-#pragma unroll 4
-    for (int t = 0; t < T; ++t) {
-      const typename VecOf<KT>::Raw raw = *reinterpret_cast<const typename VecOf<KT>::Raw*>(sK + (size_t)t * chunk + v * VN);
-      float x[VN];
-      VecOf<KT>::unpack(raw, x);
-      const float p = sE[t];
-#pragma unroll
-      for (int i = 0; i < VN; ++i) acc[i] = fmaf(p, x[i], acc[i]);
+    if (cl > 1) {
+      // all scores of this query have landed in every CTA of the cluster.  One barrier per query is enough: the
+      // buffers alternate, and a peer cannot start query qi + 2 before this CTA has passed the barrier of qi + 1.
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+      __syncthreads();
     }
-    const int f = f0 + v * VN;
-    if (a.ctx_f32) {
-      float* dst = a.ctx_f32 + b * a.ctx_ld + f;
+    AT_STAMP(4);
+    // soft-max over T by warp 0 (T <= 72: at most three values per lane)
+    if (wid == 0) {
+      float v[3];
+      float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < VN; ++i) dst[i] = acc[i];
-    }
-    if (a.ctx_bf16) {
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.ctx_bf16) + b * a.ctxb_ld + f;
+      for (int i = 0; i < 3; ++i) {
+        const int t = lane + 32 * i;
+        v[i] = t < T ? sEq[t] : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+      }
+      mx = warp_max(mx);
+      float sm = 0.f;
 #pragma unroll
-      for (int i = 0; i < VN; ++i) dst[i] = __float2bfloat16(acc[i]);
+      for (int i = 0; i < 3; ++i) {
+        const int t = lane + 32 * i;
+        v[i] = t < T ? (FAST ? __expf(v[i] - mx) : expf(v[i] - mx)) : 0.f;
+        sm += v[i];
+      }
+      sm = warp_sum(sm);
+      const float inv = 1.f / sm;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int t = lane + 32 * i;
+        if (t < T) {
+          const float pv = v[i] * inv;
+          sP[t] = pv;
+          if (rank == 0) a.alpha[(int64_t)b * T + t] = pv;
+        }
+      }
     }
-  }
+    __syncthreads();
+    AT_STAMP(5);
+    if (ncols <= 0) continue;
+    if (qi == 0) mbar_wait(bar_k, 0);   // keys chunk has landed
+    AT_STAMP(6);
+    const int nvec = ncols / VN;
+    for (int v = tid; v < nvec; v += NT) {
+      float acc[VN];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+#pragma unroll 6
+      for (int t = 0; t < T; ++t) {
+        const typename VecOf<KT>::Raw raw = *reinterpret_cast<const typename VecOf<KT>::Raw*>(sK + (size_t)t * chunk + v * VN);
+        float x[VN];
+        VecOf<KT>::unpack(raw, x);
+        const float pw = sP[t];
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[i] = fmaf(pw, x[i], acc[i]);
+      }
+      const int f = f0 + v * VN;
+      if (a.ctx_f32) {          // vectorised path: f, ctx_ld multiples of VN and 16-byte aligned base (checked on the host)
+        float4* dst = reinterpret_cast<float4*>(a.ctx_f32 + b * a.ctx_ld + f);
+#pragma unroll
+        for (int i = 0; i < VN / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+      }
+      if (a.ctx_bf16) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.ctx_bf16) + b * a.ctxb_ld + f;
+        if constexpr (VN == 8) {
+          uint4 pk;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]), h3 = __floats2bfloat162_rn(acc[6], acc[7]);
+          pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(dst) = pk;
+        } else {
+          uint2 pk;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+          pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(dst) = pk;
+        }
+      }
+    }
+    AT_STAMP(7);
   }   // queries
+#undef AT_STAMP
 }
 
 // Backward, one CTA per batch row; keys row block staged by TMA bulk copies, U.k in registers.
@@ -507,14 +575,24 @@ static int ensure_big_smem(const void* kern) {
   return 0;
 }
 
-static int launch_ex(const void* kern, dim3 grid, dim3 block, size_t smem, bool pdl, void** args, cudaStream_t st) {
+static int launch_ex(const void* kern, dim3 grid, dim3 block, size_t smem, bool pdl, void** args, cudaStream_t st,
+                     int cluster_y = 1) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl && pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_y > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = (unsigned)cluster_y; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  cfg.numAttrs = na;
   MVC_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
   return 0;
 }
@@ -540,6 +618,9 @@ static const void* pick_bwd_staged(int A) {
   }
 }
 
+static unsigned long long* g_attn_prof = nullptr;
+void set_attn_prof(unsigned long long* p) { g_attn_prof = p; }
+
 int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
   const int B = a.B, T = a.T, A = a.A, F = a.F;
   if (B == 0) return 0;
@@ -548,39 +629,45 @@ int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
   const int VN = a.keys_bf16 ? 8 : 4;
   const size_t es = a.keys_bf16 ? 2 : 4;
   const bool vec = (F % VN == 0) && (a.k_sb % VN == 0) && (a.k_st % VN == 0) &&
-                   (reinterpret_cast<uintptr_t>(a.keys) % 16 == 0) &&
-                   (!a.ctx_f32 || true);
+                   (reinterpret_cast<uintptr_t>(a.keys) % 16 == 0);
+  // the staged kernel also stores the context with 16-byte vectors and pulls U.k by bulk copies
+  const bool vec_out = (!a.ctx_f32 || (reinterpret_cast<uintptr_t>(a.ctx_f32) % 16 == 0 && a.ctx_ld % 4 == 0)) &&
+                       (!a.ctx_bf16 || (reinterpret_cast<uintptr_t>(a.ctx_bf16) % 16 == 0 && a.ctxb_ld % 8 == 0)) &&
+                       (reinterpret_cast<uintptr_t>(a.uk) % 16 == 0);
   ProfScope prof(PK_ATTN_FWD, B, T, F, st);
   // ---- staged fast path
   const void* kern = nullptr;
-  if (vec && T <= ATT_MAXR * 9 && B % a.keys_batch == 0) {
+  if (vec && vec_out && T <= ATT_MAXR * 9 && B % a.keys_batch == 0) {
     if (a.keys_bf16) kern = a.fast_math ? pick_fwd_staged<__nv_bfloat16, true>(A) : pick_fwd_staged<__nv_bfloat16, false>(A);
     else kern = a.fast_math ? pick_fwd_staged<float, true>(A) : pick_fwd_staged<float, false>(A);
   }
   if (kern) {
-    const size_t tail = sizeof(float) * (2 * (size_t)A + ((T + 3) & ~3) + 32) + 16;
-    // fewest F-chunks whose staged keys fit in shared memory; more when the batch alone cannot fill the SMs
+    const size_t tail0 = sizeof(float) * (2 * (size_t)A + 3 * (size_t)((T + 3) & ~3)) + 16;
+    // F-chunks per key block = CTAs per cluster (1, 2, 4 or 8; scores are shared through DSMEM, so splitting costs no
+    // repeated work): the fewest whose staged keys fit in shared memory, more while the grid cannot fill the SMs.
+    // An unsplit row whose [T, F] block is contiguous arrives by ONE bulk copy; an F-chunk needs T strided copies,
+    // and each cp.async.bulk occupies the SM's TMA unit for ~0.1 us whatever its size (measured: 3.6 us for 30
+    // copies of 2 KB), so grids that already fill the machine are never split further.
     int fs = 1;
     auto smem_for = [&](int fsplit, int* chunk_out) {
       int chunk = (int)cdiv(cdiv(F, fsplit), VN) * VN;
       *chunk_out = chunk;
-      return (((size_t)T * chunk * es + 127) & ~size_t(127)) + tail;
+      const size_t uslab = sizeof(float) * (size_t)cdiv(T, fsplit) * A;     // U.k rows of the CTA's frames
+      return (((size_t)T * chunk * es + 127) & ~size_t(127)) + uslab + tail0;
     };
     int chunk = F;
-    while (smem_for(fs, &chunk) > kAttnMaxSmem && fs < F / VN) ++fs;
-    while ((int64_t)a.keys_batch * fs < kNumSMs && fs < 8 && chunk > 64 * VN) { ++fs; smem_for(fs, &chunk); }
-    // several waves of CTAs: keep the stage small enough for 3 resident CTAs per SM, so one CTA's bulk loads overlap
-    // another's score / context arithmetic (a single resident CTA serialises load -> compute: 2.6 TB/s at B=512)
-    if ((int64_t)a.keys_batch * fs > kNumSMs)
-      while (smem_for(fs, &chunk) > 72 * 1024 && fs < 8 && chunk > 64 * VN) ++fs;
+    while (smem_for(fs, &chunk) > kAttnMaxSmem && fs < 8) fs *= 2;
+    while ((int64_t)a.keys_batch * fs < kNumSMs && fs < 8 && chunk > 64 * VN) { fs *= 2; smem_for(fs, &chunk); }
     if (const char* e = getenv("MVC_B200_ATTN_FS")) { fs = atoi(e); }   // tuning aid
-    const size_t smem = smem_for(fs, &chunk);
-    fs = (int)cdiv(F, chunk);
-    if (smem <= kAttnMaxSmem) {
+    smem_for(fs, &chunk);
+    fs = (int)cdiv(F, chunk);       // CTAs per cluster actually needed at this chunk width
+    const size_t smem = (((size_t)T * chunk * es + 127) & ~size_t(127)) + sizeof(float) * (size_t)cdiv(T, fs) * A + tail0;
+    if (smem <= kAttnMaxSmem && fs <= 8) {
       MVC_TRY(ensure_big_smem(kern));
       AttnFwdArgs args = a;
+      args.prof = g_attn_prof;
       void* params[] = {(void*)&args, (void*)&chunk};
-      MVC_TRY(launch_ex(kern, dim3(a.keys_batch, fs), dim3(288), smem, pdl, params, st));
+      MVC_TRY(launch_ex(kern, dim3(a.keys_batch, fs), dim3(288), smem, pdl, params, st, fs));
       MVC_LAUNCH_CHECK();
       return 0;
     }
@@ -702,4 +789,9 @@ extern "C" int mvc_soft_attention_bwd(int B, int T, int A, int F, const float* w
   a.dwq = dwq; a.dwq_bf16 = nullptr; a.duk = duk; a.dw_partial = dw_partial; a.dkeys = dkeys; a.dk_sb = dk_sb; a.dk_st = dk_st;
   a.fast_math = fast_math;
   return launch_attention_bwd(a, false, (cudaStream_t)stream);
+}
+
+extern "C" int mvc_debug_set_attn_prof(unsigned long long* dev_buf) {
+  mvc::set_attn_prof(dev_buf);
+  return 0;
 }

@@ -54,6 +54,7 @@ struct AttnFwdArgs {
   const uint8_t* mask; int64_t m_sb, m_st;
   float* ctx_f32; int64_t ctx_ld; void* ctx_bf16; int64_t ctxb_ld; float* alpha;
   int fast_math;
+  unsigned long long* prof;   // debug: 8 globaltimer stamps per CTA (mvc_debug_set_attn_prof), normally null
 };
 int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st);
 

@@ -63,6 +63,7 @@ SIGNATURES = {
     "mvc_prof_collect": (i32, [P(C.c_double), P(C.c_longlong)]),
     "mvc_debug_set_recur_prof": (i32, [vp]),
     "mvc_debug_set_recur_bwd_prof": (i32, [vp]),
+    "mvc_debug_set_attn_prof": (i32, [vp]),
     "mvc_gemm_f32": (i32, [i32, i32, i32, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, vp, vp]),
     "mvc_gemm_bf16": (i32, [i32, i32, i32, vp, i64, vp, i64, f32, vp, i64, vp, vp, i64, vp]),
     "mvc_gemm_bf16_ex": (i32, [i32, i32, i32, vp, i64, i32, vp, i64, i32, f32, vp, i64, vp, vp]),
