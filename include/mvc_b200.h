@@ -58,6 +58,9 @@ int mvc_debug_set_recur_bwd_prof(long long* dev_buf);
 /* Debug: device buffer (8 uint64 per CTA of the staged soft-attention forward kernel, CTA index = blockIdx.y *
  * gridDim.x + blockIdx.x) that receives %globaltimer stamps of its phases; NULL switches it off. */
 int mvc_debug_set_attn_prof(unsigned long long* dev_buf);
+/* Debug: same for the one-tile tcgen05 GEMM kernel, for launches of exactly the shape (M, N, K); CTA index =
+ * (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x. */
+int mvc_debug_set_gemm_prof(unsigned long long* dev_buf, int M, int N, int K);
 
 /* ------------------------------------------------------------------ */
 /* Building-block kernels (each is unit-tested against the oracle)     */

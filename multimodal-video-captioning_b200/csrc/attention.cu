@@ -465,7 +465,11 @@ attn_bwd_staged_kernel(const AttnBwdArgs a) {
     const KT* kbase = reinterpret_cast<const KT*>(a.keys) + (int64_t)b * a.k_sb;
     const uint32_t row_bytes = (uint32_t)(F * sizeof(KT));
     mbar_expect_tx(bar, row_bytes * (uint32_t)T);
-    for (int t = 0; t < T; ++t) bulk_load_1d(smem_u32(sK + (size_t)t * F), kbase + (int64_t)t * a.k_st, row_bytes, bar);
+    if (a.k_st == F) {
+      bulk_load_1d(smem_u32(sK), kbase, row_bytes * (uint32_t)T, bar);      // contiguous [T, F] block: one copy
+    } else {
+      for (int t = 0; t < T; ++t) bulk_load_1d(smem_u32(sK + (size_t)t * F), kbase + (int64_t)t * a.k_st, row_bytes, bar);
+    }
   }
   float ur[ATT_MAXR_BWD][AV];
   const float* ukb = a.uk + (int64_t)b * T * A;
@@ -510,6 +514,19 @@ attn_bwd_staged_kernel(const AttnBwdArgs a) {
 #pragma unroll
   for (int k = 0; k < AV; ++k) { sq[k] = 0.f; sw[k] = 0.f; }
   float* dukb = a.duk ? a.duk + (int64_t)b * T * A : nullptr;
+  // duk accumulates over the decode steps: fetch all old values first (independent loads in flight together; a
+  // load-add-store per element in program order exposed one global round trip per element, ~0.7 us x 32)
+  float dold[ATT_MAXR_BWD][AV];
+  if (dukb) {
+#pragma unroll
+    for (int r = 0; r < ATT_MAXR_BWD; ++r) {
+      const int t = wid + r * NW;
+      if (t < T) {
+#pragma unroll
+        for (int k = 0; k < AV; ++k) dold[r][k] = dukb[(int64_t)t * A + lane + 32 * k];
+      }
+    }
+  }
 #pragma unroll
   for (int r = 0; r < ATT_MAXR_BWD; ++r) {
     const int t = wid + r * NW;
@@ -522,7 +539,7 @@ attn_bwd_staged_kernel(const AttnBwdArgs a) {
         const float dpre = de * sW[i] * (1.f - th * th);
         sq[k] += dpre;
         sw[k] = fmaf(de, th, sw[k]);
-        if (dukb) dukb[(int64_t)t * A + i] += dpre;
+        if (dukb) dukb[(int64_t)t * A + i] = dold[r][k] + dpre;
       }
     }
   }
@@ -544,10 +561,21 @@ attn_bwd_staged_kernel(const AttnBwdArgs a) {
     if (a.dw_partial) a.dw_partial[(int64_t)b * A + i] += w2;
   }
   if (a.dkeys) {
+    // dkeys[t, f] += alpha[t] * dctx[f]: four independent read-modify-writes in flight per thread
     float* dkb = a.dkeys + (int64_t)b * a.dk_sb;
-    for (int64_t i = tid; i < (int64_t)T * F; i += NT) {
-      const int t = (int)(i / F), f = (int)(i - (int64_t)t * F);
-      dkb[(int64_t)t * a.dk_st + f] += sAl[t] * sD[dpos(f)];
+    const int total = T * F;
+    for (int base = tid; base < total; base += 4 * NT) {
+      float old[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * NT;
+        if (i < total) { const int t = i / F, f = i - t * F; old[u] = dkb[(int64_t)t * a.dk_st + f]; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * NT;
+        if (i < total) { const int t = i / F, f = i - t * F; dkb[(int64_t)t * a.dk_st + f] = old[u] + sAl[t] * sD[dpos(f)]; }
+      }
     }
   }
 }

@@ -152,9 +152,12 @@ __device__ __forceinline__ void plain_store(const TcEpilogue& ep, int64_t gm, in
   }
 }
 
-// fused LSTM cell for NU hidden units [tile*32 + u0, +NU) of row gm; g[gate][j] = summed GEMM output
-template <int NU, typename Arr>
-__device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int tile, int u0, Arr& g) {
+// fused LSTM cell for NU hidden units [tile*32 + u0, +NU) of row gm, in two halves so that the split-K path can
+// fetch everything that does not depend on the accumulator while the MMAs are still running:
+//   cell_addends: g[gate][j] (+)= hoisted input projection + gathered embedding-table row + bias; cp[j] = c_prev
+//   cell_finish : activations (ex2-based), c / h update and all stores; g must hold the complete pre-activations
+template <int NU, bool ACCUM, typename Arr>
+__device__ __forceinline__ void cell_addends(const TcEpilogue& ep, int64_t gm, int tile, int u0, Arr& g, float* cp) {
   const int H = ep.H;
   const int n0 = tile * 128, ug = tile * 32 + u0;
   const float* gxr = ep.gx ? ep.gx + gm * ep.gx_ld + n0 : nullptr;
@@ -169,10 +172,22 @@ __device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int
       if (gxr) { const float4 t = *reinterpret_cast<const float4*>(gxr + lc); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
       if (etr) { const float4 t = *reinterpret_cast<const float4*>(etr + lc); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
       if (br) { const float4 t = *reinterpret_cast<const float4*>(br + lc); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-      g[c][j] += a.x; g[c][j + 1] += a.y; g[c][j + 2] += a.z; g[c][j + 3] += a.w;
+      if constexpr (ACCUM) { g[c][j] += a.x; g[c][j + 1] += a.y; g[c][j + 2] += a.z; g[c][j + 3] += a.w; }
+      else { g[c][j] = a.x; g[c][j + 1] = a.y; g[c][j + 2] = a.z; g[c][j + 3] = a.w; }
     }
   }
-  const float* cp = ep.c_prev ? ep.c_prev + gm * H + ug : nullptr;
+  const float* cpp = ep.c_prev ? ep.c_prev + gm * H + ug : nullptr;
+#pragma unroll
+  for (int j = 0; j < NU; j += 4) {
+    const float4 c4 = cpp ? *reinterpret_cast<const float4*>(cpp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
+  }
+}
+
+template <int NU, typename Arr>
+__device__ __forceinline__ void cell_finish(const TcEpilogue& ep, int64_t gm, int tile, int u0, Arr& g, const float* cpv) {
+  const int H = ep.H;
+  const int n0 = tile * 128, ug = tile * 32 + u0;
   float* co = ep.c_out + gm * H + ug;
   float* actr = ep.act ? ep.act + gm * (int64_t)(4 * H) + n0 : nullptr;
   float* h1 = ep.h32 ? ep.h32 + gm * ep.h_ld + ug : nullptr;
@@ -180,15 +195,13 @@ __device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int
   __nv_bfloat16* hb = ep.hb ? ep.hb + gm * ep.hb_ld + ug : nullptr;
 #pragma unroll
   for (int j = 0; j < NU; j += 4) {
-    const float4 cprev = cp ? *reinterpret_cast<const float4*>(cp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float cpv[4] = {cprev.x, cprev.y, cprev.z, cprev.w};
     float cn[4], hn[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float ig = sigmoid_ex2(g[0][j + e]), fg = sigmoid_ex2(g[1][j + e]);
       const float gg = tanh_ex2(g[2][j + e]), og = sigmoid_ex2(g[3][j + e]);
       g[0][j + e] = ig; g[1][j + e] = fg; g[2][j + e] = gg; g[3][j + e] = og;
-      cn[e] = fg * cpv[e] + ig * gg;
+      cn[e] = fg * cpv[j + e] + ig * gg;
       hn[e] = og * tanh_ex2(cn[e]);
     }
     *reinterpret_cast<float4*>(co + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
@@ -209,6 +222,13 @@ __device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int
       for (int j = 0; j < NU; j += 4)
         *reinterpret_cast<float4*>(actr + gate_lcol(c, u0 + j)) = make_float4(g[c][j], g[c][j + 1], g[c][j + 2], g[c][j + 3]);
   }
+}
+
+template <int NU, typename Arr>
+__device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int tile, int u0, Arr& g) {
+  float cp[NU];
+  cell_addends<NU, true>(ep, gm, tile, u0, g, cp);
+  cell_finish<NU>(ep, gm, tile, u0, g, cp);
 }
 
 template <int BN, int STAGES, int MODE>
@@ -232,6 +252,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int kb0 = (int)((long long)nkb_all * z / splits), kb1 = (int)((long long)nkb_all * (z + 1) / splits);
   const int nkb = kb1 - kb0;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  unsigned long long* prof =
+      ep.prof ? ep.prof + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+#define TC_STAMP(i, cond) do { if (prof && (cond)) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); prof[i] = t_; } } while (0)
+  TC_STAMP(0, threadIdx.x == 0);
+  float g4r[4][16], cpr[16];       // split-K cell epilogue: prefetched addends / c_prev of this thread's reduce role
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -254,6 +279,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();     // every CTA of this grid is resident by the time the dependent grid may start
+  TC_STAMP(1, threadIdx.x == 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -265,6 +291,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tma_load_2d(smem_base + kb * S::STAGE_BYTES + S::A_BYTES, &map_b, full_bar(kb), (kb0 + kb) * TC_BK, n0);
       }
       pdl_wait();
+      TC_STAMP(2, true);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -277,6 +304,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tma_load_2d(a_dst, &map_a, full_bar(stage), (kb0 + kb) * TC_BK, m0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      TC_STAMP(3, true);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -307,8 +335,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int row = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     pdl_wait();                                   // C / cell state may still be in use upstream
+    if constexpr (MODE == TC_MODE_CELL) {
+      if (splits > 1) {
+        // split-K: this thread will finish units [u0, u0 + 32/S) of tile row `rrow` after the DSMEM reduction; pull
+        // their addends (input projection, embedding row, bias) and c_prev NOW, while the MMAs are still running
+        const int te = threadIdx.x - 64, rows_per = TC_BM / splits;
+        const int rl = te / splits, cgp = te - rl * splits;
+        const int64_t gmr = (int64_t)m0 + z * rows_per + rl;
+        const int upt = 32 / splits, u0 = cgp * upt;
+        if (gmr < M) {
+          if (upt == 16) cell_addends<16, false>(ep, gmr, blockIdx.x, u0, g4r, cpr);
+          else if (upt == 8) cell_addends<8, false>(ep, gmr, blockIdx.x, u0, g4r, cpr);
+          else cell_addends<4, false>(ep, gmr, blockIdx.x, u0, g4r, cpr);
+        }
+      }
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    TC_STAMP(4, threadIdx.x == 64);
     if (splits == 1) {
       const int64_t gm = (int64_t)m0 + row;
       if constexpr (MODE == TC_MODE_PLAIN) {
@@ -359,6 +403,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // (deterministic), and runs the epilogue for it.
     cluster_arrive();
     cluster_wait();
+    TC_STAMP(5, threadIdx.x == 64);
     if (warp >= 2) {
       constexpr int RS = BN + 4;
       const int te = threadIdx.x - 64;                       // 0..127
@@ -377,49 +422,57 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int s = 0; s < 8; ++s) {
           if (s >= splits) break;
           const uint32_t src = mapa_cluster(red_base + (uint32_t)c0 * 4u, (uint32_t)s);
+          // all loads of this partial first (independent, in flight together), then the adds: interleaving them
+          // serialised one ~0.25 us DSMEM round trip per load
+          float4 t[MAXC / 4];
+#pragma unroll
+          for (int j = 0; j < MAXC; j += 4)
+            if (j < ncol) t[j >> 2] = ld_dsmem_v4(src + (uint32_t)j * 4u);
 #pragma unroll
           for (int j = 0; j < MAXC; j += 4) {
-            if (j < ncol) {
-              const float4 t = ld_dsmem_v4(src + (uint32_t)j * 4u);
-              o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
-            }
+            if (j < ncol) { o[j] += t[j >> 2].x; o[j + 1] += t[j >> 2].y; o[j + 2] += t[j >> 2].z; o[j + 3] += t[j >> 2].w; }
           }
         }
         if (gm < M) plain_store<MAXC>(ep, gm, n0 + c0, N, o, ncol);
       } else {
-        // cell: thread owns units [u0, u0 + 32/S) of its row, all four gates
+        // cell: thread owns units [u0, u0 + 32/S) of its row, all four gates; g4r already holds the addends
         const int upt = 32 / splits, u0 = cgp * upt;
-        float g4[4][16];
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) g4[g][j] = 0.f;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
           if (s >= splits) break;
+          float4 t[4][4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint32_t src = mapa_cluster(red_base + (uint32_t)gate_lcol(g, u0) * 4u, (uint32_t)s);
 #pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              if (j < upt) t[g][j >> 2] = ld_dsmem_v4(src + (uint32_t)j * 4u);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+#pragma unroll
             for (int j = 0; j < 16; j += 4) {
               if (j < upt) {
-                const float4 t = ld_dsmem_v4(src + (uint32_t)j * 4u);
-                g4[g][j] += t.x; g4[g][j + 1] += t.y; g4[g][j + 2] += t.z; g4[g][j + 3] += t.w;
+                g4r[g][j] += t[g][j >> 2].x; g4r[g][j + 1] += t[g][j >> 2].y;
+                g4r[g][j + 2] += t[g][j >> 2].z; g4r[g][j + 3] += t[g][j >> 2].w;
               }
             }
           }
         }
         if (gm < M) {
-          if (upt == 16) cell_store<16>(ep, gm, blockIdx.x, u0, g4);
-          else if (upt == 8) cell_store<8>(ep, gm, blockIdx.x, u0, g4);
-          else cell_store<4>(ep, gm, blockIdx.x, u0, g4);
+          if (upt == 16) cell_finish<16>(ep, gm, blockIdx.x, u0, g4r, cpr);
+          else if (upt == 8) cell_finish<8>(ep, gm, blockIdx.x, u0, g4r, cpr);
+          else cell_finish<4>(ep, gm, blockIdx.x, u0, g4r, cpr);
         }
       }
     }
+    TC_STAMP(6, threadIdx.x == 64);
     cluster_arrive();                                        // nobody may leave while its partial is being read
     cluster_wait();
   }
   __syncthreads();
+  TC_STAMP(7, threadIdx.x == 64);
+#undef TC_STAMP
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -806,9 +859,13 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
   return 0;
 }
 
+static unsigned long long* g_gemm_prof = nullptr;
+static int g_gemm_prof_m = 0, g_gemm_prof_n = 0, g_gemm_prof_k = 0;
+
 template <int BN, int STAGES, int MODE>
 static int launch_tc(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, TcEpilogue ep,
                      int splits, bool pdl, cudaStream_t st) {
+  ep.prof = (g_gemm_prof && M == g_gemm_prof_m && N == g_gemm_prof_n && K == g_gemm_prof_k) ? g_gemm_prof : nullptr;
   CUtensorMap ma, mb;
   MVC_TRY(get_tensor_map(A, M, K, lda, TC_BM, &ma));
   MVC_TRY(get_tensor_map(B, N, K, ldb, BN, &mb));
@@ -941,8 +998,8 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
   };
   if (ep.mode == TC_MODE_CELL) {
     MVC_CHECK(N % 128 == 0 && N == 4 * ep.H, "fused LSTM-cell epilogue needs N == 4H with H %% 32 == 0 (N=%d H=%d)", N, ep.H);
-    const int s = splits_for(mt * (N / 128), max_active_clusters<128, 4, TC_MODE_CELL>);
-    return launch_tc<128, 4, TC_MODE_CELL>(M, N, K, A, lda, B, ldb, ep, s, pdl, st);
+    const int s = splits_for(mt * (N / 128), max_active_clusters<128, 6, TC_MODE_CELL>);
+    return launch_tc<128, 6, TC_MODE_CELL>(M, N, K, A, lda, B, ldb, ep, s, pdl, st);
   }
   // big GEMMs (>= half a wave of 128x256 tiles): persistent kernel with double-buffered TMEM accumulators
   if (flags & (TC_FLAG_A_MN | TC_FLAG_B_MN)) {
@@ -964,9 +1021,9 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
   if (mt * cdiv(N, PG_BN) >= kNumSMs / 2 && K >= 2 * TC_BK)
     return launch_tc_persist<TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, pdl, st);
   const int64_t t128 = mt * cdiv(N, 128), t64 = mt * cdiv(N, 64), t32 = mt * cdiv(N, 32);
-  const int s128 = splits_for(t128, max_active_clusters<128, 4, TC_MODE_PLAIN>);
-  const int s64 = splits_for(t64, max_active_clusters<64, 6, TC_MODE_PLAIN>);
-  const int s32 = splits_for(t32, max_active_clusters<32, 8, TC_MODE_PLAIN>);
+  const int s128 = splits_for(t128, max_active_clusters<128, 6, TC_MODE_PLAIN>);
+  const int s64 = splits_for(t64, max_active_clusters<64, 8, TC_MODE_PLAIN>);
+  const int s32 = splits_for(t32, max_active_clusters<32, 10, TC_MODE_PLAIN>);
   // The kernel is a serial chain of k-blocks per CTA (latency bound at these sizes), so pick the tile width whose
   // CTAs run the FEWEST k-blocks: waves x ceil(nkb / splits), weighted by the per-k-block cost of the tile width
   // (a narrower B tile is a little cheaper, but re-reads A more often).  Ties go to the wider tile.
@@ -977,9 +1034,9 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
     return (double)(waves * cdiv(nkb, s)) * w + (s > 1 ? red : 0.0);
   };
   const double c128 = cost(t128, s128, 1.0, 12.0), c64 = cost(t64, s64, 0.85, 6.0), c32 = cost(t32, s32, 0.75, 3.0);
-  if (c128 <= c64 && c128 <= c32) return launch_tc<128, 4, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s128, pdl, st);
-  if (c64 <= c32) return launch_tc<64, 6, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s64, pdl, st);
-  return launch_tc<32, 8, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s32, pdl, st);
+  if (c128 <= c64 && c128 <= c32) return launch_tc<128, 6, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s128, pdl, st);
+  if (c64 <= c32) return launch_tc<64, 8, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s64, pdl, st);
+  return launch_tc<32, 10, TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, s32, pdl, st);
 }
 
 // token[m] = column of the best partial of row m (tiles ascend: strict > keeps the lowest index)
@@ -1168,4 +1225,10 @@ extern "C" int mvc_gemm_bf16(int M, int N, int K, const void* A, int64_t lda, co
   ep.mode = TC_MODE_PLAIN;
   ep.beta = beta; ep.C = C; ep.ldc = ldc; ep.bias = bias; ep.Cb = (__nv_bfloat16*)Cb; ep.ldcb = ldcb;
   return tc_gemm(M, N, K, A, lda, B, ldb, ep, 0, (cudaStream_t)stream);
+}
+
+extern "C" int mvc_debug_set_gemm_prof(unsigned long long* dev_buf, int M, int N, int K) {
+  mvc::g_gemm_prof = dev_buf;
+  mvc::g_gemm_prof_m = M; mvc::g_gemm_prof_n = N; mvc::g_gemm_prof_k = K;
+  return 0;
 }

@@ -35,6 +35,7 @@ struct TcEpilogue {
   // are a second weight matrix applied to the same A; its product is stored plainly to aux_C[m, n - aux_n0] while
   // columns [0, n_main) go through the arg-max / top-k reduction (rows [n_main, aux_n0) of B are padding).
   // Used to fold the attention query projection W.h of the NEXT decode step into this step's vocabulary GEMM.
+  unsigned long long* prof;   // debug: 8 %globaltimer stamps per CTA of the one-tile kernel (mvc_debug_set_gemm_prof)
   float* aux_C;
   int64_t aux_ld;
   int aux_n0;

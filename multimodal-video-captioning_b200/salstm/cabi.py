@@ -64,6 +64,7 @@ SIGNATURES = {
     "mvc_debug_set_recur_prof": (i32, [vp]),
     "mvc_debug_set_recur_bwd_prof": (i32, [vp]),
     "mvc_debug_set_attn_prof": (i32, [vp]),
+    "mvc_debug_set_gemm_prof": (i32, [vp, i32, i32, i32]),
     "mvc_gemm_f32": (i32, [i32, i32, i32, f32, vp, i64, i64, vp, i64, i64, f32, vp, i64, vp, vp]),
     "mvc_gemm_bf16": (i32, [i32, i32, i32, vp, i64, vp, i64, f32, vp, i64, vp, vp, i64, vp]),
     "mvc_gemm_bf16_ex": (i32, [i32, i32, i32, vp, i64, i32, vp, i64, i32, f32, vp, i64, vp, vp]),
