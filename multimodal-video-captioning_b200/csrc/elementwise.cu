@@ -272,17 +272,41 @@ __global__ void argmax_rows_kernel(const float* __restrict__ x, const float* __r
   }
 }
 
-__global__ void log_softmax_bwd_kernel(const float* __restrict__ logp, const float* __restrict__ dlogp, int V,
-                                       float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dl_bf16, int64_t ldb) {
+// REG = values of the row each thread keeps in registers between the row sum and the update (0: re-read the row)
+template <int REG>
+__global__ void __launch_bounds__(256)
+log_softmax_bwd_kernel(const float* __restrict__ logp, const float* __restrict__ dlogp, int V,
+                       float* __restrict__ dlogits, __nv_bfloat16* __restrict__ dl_bf16, int64_t ldb) {
   __shared__ float red[32];
   const int64_t off = (int64_t)blockIdx.x * V;
   float s = 0.f;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) s += dlogp[off + v];
-  s = block_sum(s, red);
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
-    const float d = dlogp[off + v] - expf(logp[off + v]) * s;
-    if (dlogits) dlogits[off + v] = d;
-    if (dl_bf16) dl_bf16[(int64_t)blockIdx.x * ldb + v] = __float2bfloat16(d);
+  if constexpr (REG > 0) {
+    float g[REG], lp[REG];
+#pragma unroll
+    for (int i = 0; i < REG; ++i) {
+      const int v = threadIdx.x + i * 256;
+      g[i] = v < V ? dlogp[off + v] : 0.f;
+      lp[i] = v < V ? logp[off + v] : 0.f;
+      s += g[i];
+    }
+    s = block_sum(s, red);
+#pragma unroll
+    for (int i = 0; i < REG; ++i) {
+      const int v = threadIdx.x + i * 256;
+      if (v < V) {
+        const float d = g[i] - __expf(lp[i]) * s;
+        if (dlogits) dlogits[off + v] = d;
+        if (dl_bf16) dl_bf16[(int64_t)blockIdx.x * ldb + v] = __float2bfloat16(d);
+      }
+    }
+  } else {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) s += dlogp[off + v];
+    s = block_sum(s, red);
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float d = dlogp[off + v] - expf(logp[off + v]) * s;
+      if (dlogits) dlogits[off + v] = d;
+      if (dl_bf16) dl_bf16[(int64_t)blockIdx.x * ldb + v] = __float2bfloat16(d);
+    }
   }
 }
 
@@ -563,8 +587,13 @@ extern "C" int mvc_log_softmax_bwd(const float* logp, const float* dlogp, int64_
   if (rows == 0) return 0;
   MVC_CHECK(logp && dlogp && (dlogits || dlogits_bf16), "mvc_log_softmax_bwd: bad arguments");
   const int64_t ldb = (V + 7) / 8 * 8;
-  log_softmax_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logp, dlogp, V, dlogits,
-                                                                        (__nv_bfloat16*)dlogits_bf16, ldb);
+  // bf16 consumers only (training hot path): row kept in registers, one read of each operand
+  if (!dlogits && V <= 16 * 256)
+    log_softmax_bwd_kernel<16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logp, dlogp, V, dlogits,
+                                                                              (__nv_bfloat16*)dlogits_bf16, ldb);
+  else
+    log_softmax_bwd_kernel<0><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logp, dlogp, V, dlogits,
+                                                                             (__nv_bfloat16*)dlogits_bf16, ldb);
   MVC_LAUNCH_CHECK();
   return 0;
 }

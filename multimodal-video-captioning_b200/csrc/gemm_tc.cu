@@ -90,7 +90,8 @@ struct TcSmem {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+  static constexpr int TOK_OFF = BAR_OFF + (2 * STAGES + 1) * 8 + 16;        // int64 tokens of the CTA's reduce rows
+  static constexpr int TOTAL = TOK_OFF + 64 * 8 + 1024;                      // + alignment slack
 };
 
 
@@ -231,6 +232,82 @@ __device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int
   cell_finish<NU>(ep, gm, tile, u0, g, cp);
 }
 
+// ---- split-K cell epilogue: warp e of the 4 epilogue warps finishes rows z*R + e, e + 4, ... (R = 128 / S) of the
+// tile, lane <-> hidden unit, so a warp touches 32 consecutive units of one row (c / h: one 128-byte segment; packed
+// gate columns: two 64-byte segments per gate).
+__device__ __forceinline__ void cell_finish_unit(const TcEpilogue& ep, int64_t gm, int tile, int u, const float (&g)[4], float cp) {
+  const int H = ep.H;
+  const int ug = tile * 32 + u;
+  const float ig = sigmoid_ex2(g[0]), fg = sigmoid_ex2(g[1]), gg = tanh_ex2(g[2]), og = sigmoid_ex2(g[3]);
+  const float cn = fg * cp + ig * gg;
+  const float hn = og * tanh_ex2(cn);
+  ep.c_out[gm * H + ug] = cn;
+  if (ep.h32) ep.h32[gm * ep.h_ld + ug] = hn;
+  if (ep.h32b) ep.h32b[gm * ep.h2_ld + ug] = hn;
+  if (ep.hb) ep.hb[gm * ep.hb_ld + ug] = __float2bfloat16(hn);
+  if (ep.act) {
+    float* actr = ep.act + gm * (int64_t)(4 * H) + tile * 128;
+    actr[gate_lcol(0, u)] = ig; actr[gate_lcol(1, u)] = fg; actr[gate_lcol(2, u)] = gg; actr[gate_lcol(3, u)] = og;
+  }
+}
+
+// DSMEM reduction + cell for the warp's rows, S = cluster size (compile time): a real loop of four batches of 8 / S
+// rows (straight-line code for all 16 rows was instruction-fetch bound: 2400 SASS instructions executed once, 80 %
+// of the samples `stall_no_inst`).  Per batch the 8 float4 DSMEM loads (rows x partials) and the rows' global
+// addends (input projection, embedding-table row, c_prev) are all in flight before anything consumes them.
+template <int S>
+__device__ __forceinline__ void cell_reduce_rows(const TcEpilogue& ep, uint32_t smem_base, int RS, int z, int ew, int lane,
+                                                 int64_t m0, int M, int tile, const int64_t* s_tok) {
+  constexpr int RB = 8 / S;                       // rows per batch
+  constexpr int rows_per = TC_BM / S;
+  const int H = ep.H;
+  const int n0 = tile * 128;
+  const int woff = ((lane >> 4) * 64 + (lane & 15) * 4);     // unit-major word offset inside the parked row
+  int lc[4];
+  float bias4[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    lc[c] = n0 + gate_lcol(c, lane);
+    bias4[c] = ep.bias ? __ldg(ep.bias + lc[c]) : 0.f;
+  }
+#pragma unroll 1
+  for (int b = 0; b < 4; ++b) {
+    float4 t[8];
+    float a[RB][4], e[RB][4], cp[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int rl = ew + 4 * (b * RB + r);
+      const int row = z * rows_per + rl;
+      const uint32_t addr = smem_base + (uint32_t)(row * RS + woff) * 4u;
+#pragma unroll
+      for (int s = 0; s < S; ++s) t[r * S + s] = ld_dsmem_v4(mapa_cluster(addr, (uint32_t)s));
+      const int64_t gm = m0 + row;
+      const bool ok = gm < M;
+      const float* gxr = (ok && ep.gx) ? ep.gx + gm * ep.gx_ld : nullptr;
+      const float* etr = (ok && ep.embtab) ? ep.embtab + s_tok[rl] * (int64_t)(4 * H) : nullptr;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        a[r][c] = gxr ? gxr[lc[c]] : 0.f;
+        e[r][c] = etr ? etr[lc[c]] : 0.f;
+      }
+      cp[r] = (ok && ep.c_prev) ? ep.c_prev[gm * H + tile * 32 + lane] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int row = z * rows_per + ew + 4 * (b * RB + r);
+      float g[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) g[c] = a[r][c] + e[r][c] + bias4[c];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {               // rank order: deterministic
+        g[0] += t[r * S + s].x; g[1] += t[r * S + s].y; g[2] += t[r * S + s].z; g[3] += t[r * S + s].w;
+      }
+      const int64_t gm = m0 + row;
+      if (gm < M) cell_finish_unit(ep, gm, tile, lane, g, cp[r]);
+    }
+  }
+}
+
 template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
@@ -256,7 +333,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       ep.prof ? ep.prof + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
 #define TC_STAMP(i, cond) do { if (prof && (cond)) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); prof[i] = t_; } } while (0)
   TC_STAMP(0, threadIdx.x == 0);
-  float g4r[4][16], cpr[16];       // split-K cell epilogue: prefetched addends / c_prev of this thread's reduce role
+  int64_t* s_tok = reinterpret_cast<int64_t*>(smem + S::TOK_OFF);   // split-K cell epilogue: tokens of my reduce rows
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -337,17 +414,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     pdl_wait();                                   // C / cell state may still be in use upstream
     if constexpr (MODE == TC_MODE_CELL) {
       if (splits > 1) {
-        // split-K: this thread will finish units [u0, u0 + 32/S) of tile row `rrow` after the DSMEM reduction; pull
-        // their addends (input projection, embedding row, bias) and c_prev NOW, while the MMAs are still running
-        const int te = threadIdx.x - 64, rows_per = TC_BM / splits;
-        const int rl = te / splits, cgp = te - rl * splits;
-        const int64_t gmr = (int64_t)m0 + z * rows_per + rl;
-        const int upt = 32 / splits, u0 = cgp * upt;
-        if (gmr < M) {
-          if (upt == 16) cell_addends<16, false>(ep, gmr, blockIdx.x, u0, g4r, cpr);
-          else if (upt == 8) cell_addends<8, false>(ep, gmr, blockIdx.x, u0, g4r, cpr);
-          else cell_addends<4, false>(ep, gmr, blockIdx.x, u0, g4r, cpr);
-        }
+        // split-K: stage the tokens of the rows this CTA will finish (embedding-table gather in the reduction)
+        const int rows_per = TC_BM / splits;
+        const int te = threadIdx.x - 64;
+        const int64_t gmr = (int64_t)m0 + z * rows_per + te;
+        if (te < rows_per) s_tok[te] = (ep.embtab && gmr < M) ? ep.tokens[gmr] : 0;
       }
     }
     mbar_wait(tmem_full_bar, 0);
@@ -380,19 +451,34 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (gm < M) cell_store<32>(ep, gm, blockIdx.x, 0, g4);
       }
     } else {
-      // split-K: park this CTA's partial tile in its own shared memory (the operand ring is idle now:
-      // every MMA has completed), row-major with a 4-word pad so 128-bit accesses are conflict-free
+      // split-K: park this CTA's partial tile in its own shared memory (the operand ring is idle now: every MMA has
+      // completed), row pitch BN + 4 words.  Plain: row-major.  Cell: UNIT-major, the four gates of a unit adjacent
+      // (word (k*16 + u)*4 + g for packed column k*64 + g*16 + u), so that the reduction reads one float4 per unit.
       float* red = reinterpret_cast<float*>(smem);
       constexpr int RS = BN + 4;
+      if constexpr (MODE == TC_MODE_CELL) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(trow + (uint32_t)(c * 32), v);
-        float4* dst = reinterpret_cast<float4*>(red + (size_t)row * RS + c * 32);
+        for (int k = 0; k < BN / 64; ++k) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(trow + (uint32_t)(k * 64), v0);          // gates i, f of units [16k, 16k + 16)
+          tmem_ld32(trow + (uint32_t)(k * 64 + 32), v1);     // gates g, o
+          float4* dst = reinterpret_cast<float4*>(red + (size_t)row * RS + k * 64);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                    __uint_as_float(v[j + 3]));
+          for (int u = 0; u < 16; ++u)
+            dst[u] = make_float4(__uint_as_float(v0[u]), __uint_as_float(v0[16 + u]), __uint_as_float(v1[u]),
+                                 __uint_as_float(v1[16 + u]));
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(trow + (uint32_t)(c * 32), v);
+          float4* dst = reinterpret_cast<float4*>(red + (size_t)row * RS + c * 32);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                      __uint_as_float(v[j + 3]));
+        }
       }
     }
     tc_fence_before();
@@ -405,65 +491,35 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     cluster_wait();
     TC_STAMP(5, threadIdx.x == 64);
     if (warp >= 2) {
+      // A warp reads whole rows: BN / 4 lanes x float4 per row (32 / (BN/4) rows per instruction), so every DSMEM
+      // request is a conflict-free contiguous row segment of the peer's shared memory and every global store a
+      // contiguous row segment of C.  All S partial loads of a row are issued before the adds.
       constexpr int RS = BN + 4;
-      const int te = threadIdx.x - 64;                       // 0..127
+      const int ew = warp - 2;
       const int rows_per = TC_BM / splits;
-      const int rl = te / splits, cgp = te - rl * splits;    // 128 threads = rows_per x S column groups
-      const int row = z * rows_per + rl;
-      const int64_t gm = (int64_t)m0 + row;
-      const uint32_t red_base = smem_base + (uint32_t)(row * RS) * 4u;
       if constexpr (MODE == TC_MODE_PLAIN) {
-        constexpr int MAXC = BN / 2;                         // columns per thread at S = 2
-        const int ncol = BN / splits, c0 = cgp * ncol;
-        float o[MAXC];
+        constexpr int LPR = BN / 4, RPI = 32 / LPR;          // lanes per row, rows per warp instruction
+        const int col = (lane % LPR) * 4;
+#pragma unroll 2
+        for (int rl = ew * RPI + lane / LPR; rl < rows_per; rl += 4 * RPI) {
+          const int row = z * rows_per + rl;
+          const uint32_t addr = smem_base + (uint32_t)(row * RS + col) * 4u;
+          float4 t[8];
 #pragma unroll
-        for (int j = 0; j < MAXC; ++j) o[j] = 0.f;
+          for (int s = 0; s < 8; ++s)
+            if (s < splits) t[s] = ld_dsmem_v4(mapa_cluster(addr, (uint32_t)s));
+          float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          if (s >= splits) break;
-          const uint32_t src = mapa_cluster(red_base + (uint32_t)c0 * 4u, (uint32_t)s);
-          // all loads of this partial first (independent, in flight together), then the adds: interleaving them
-          // serialised one ~0.25 us DSMEM round trip per load
-          float4 t[MAXC / 4];
-#pragma unroll
-          for (int j = 0; j < MAXC; j += 4)
-            if (j < ncol) t[j >> 2] = ld_dsmem_v4(src + (uint32_t)j * 4u);
-#pragma unroll
-          for (int j = 0; j < MAXC; j += 4) {
-            if (j < ncol) { o[j] += t[j >> 2].x; o[j + 1] += t[j >> 2].y; o[j + 2] += t[j >> 2].z; o[j + 3] += t[j >> 2].w; }
-          }
+          for (int s = 0; s < 8; ++s)
+            if (s < splits) { o[0] += t[s].x; o[1] += t[s].y; o[2] += t[s].z; o[3] += t[s].w; }
+          const int64_t gm = (int64_t)m0 + row;
+          if (gm < M) plain_store<4>(ep, gm, n0 + col, N, o, 4);
         }
-        if (gm < M) plain_store<MAXC>(ep, gm, n0 + c0, N, o, ncol);
       } else {
-        // cell: thread owns units [u0, u0 + 32/S) of its row, all four gates; g4r already holds the addends
-        const int upt = 32 / splits, u0 = cgp * upt;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          if (s >= splits) break;
-          float4 t[4][4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t src = mapa_cluster(red_base + (uint32_t)gate_lcol(g, u0) * 4u, (uint32_t)s);
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              if (j < upt) t[g][j >> 2] = ld_dsmem_v4(src + (uint32_t)j * 4u);
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              if (j < upt) {
-                g4r[g][j] += t[g][j >> 2].x; g4r[g][j + 1] += t[g][j >> 2].y;
-                g4r[g][j + 2] += t[g][j >> 2].z; g4r[g][j + 3] += t[g][j >> 2].w;
-              }
-            }
-          }
-        }
-        if (gm < M) {
-          if (upt == 16) cell_finish<16>(ep, gm, blockIdx.x, u0, g4r, cpr);
-          else if (upt == 8) cell_finish<8>(ep, gm, blockIdx.x, u0, g4r, cpr);
-          else cell_finish<4>(ep, gm, blockIdx.x, u0, g4r, cpr);
-        }
+        // cell: lane <-> hidden unit of the tile (32 units), float4 = its four gates; g4r / cpr hold the addends
+        if (splits == 2) cell_reduce_rows<2>(ep, smem_base, RS, z, ew, lane, m0, M, blockIdx.x, s_tok);
+        else if (splits == 4) cell_reduce_rows<4>(ep, smem_base, RS, z, ew, lane, m0, M, blockIdx.x, s_tok);
+        else cell_reduce_rows<8>(ep, smem_base, RS, z, ew, lane, m0, M, blockIdx.x, s_tok);
       }
     }
     TC_STAMP(6, threadIdx.x == 64);
