@@ -161,6 +161,16 @@ int mvc_lstm_gates_cell_bf16(int B, int H, int K, const void* x, int64_t ldx, co
 int mvc_vocab_argmax_bf16(int M, int V, int K, const void* h, int64_t ldh, const void* out_w, int64_t ldw,
                           const float* out_b, void* workspace, size_t workspace_bytes, int64_t* ids, void* stream);
 
+/* Same GEMM with an auxiliary column block (decode loops: features_captioning.py:87-88 of step s together with
+ * temporal_attention.py:20 of step s+1).  w_ext [mvc_vocab_aux_row0(V) + A, K] bf16 holds out_w in rows [0, V),
+ * padding up to the next multiple of 256, then the attention query weights W in the last A rows; besides ids the call
+ * writes wq[m, a] = h[m,:] . W[a,:] (fp32, ld A) -- the query projection the NEXT step's soft attention needs -- so the
+ * decode loop launches no separate projection kernel. */
+int mvc_vocab_aux_row0(int V);
+int mvc_vocab_argmax_wq_bf16(int M, int V, int K, int A, const void* h, int64_t ldh, const void* w_ext, int64_t ldw,
+                             const float* out_b, void* workspace, size_t workspace_bytes, int64_t* ids, float* wq,
+                             void* stream);
+
 /* Vocabulary projection fused with log-softmax + top-k (K-E, beam search: features_captioning.py:160-189):
  * cand_logp[m,k], cand_idx[m,k] (k < width <= 8) = the largest log_softmax(h[m,:] . out_w^T + out_b) values of row m
  * and their tokens, best first, ties -> lowest token.  Top-8 lists and an online log-sum-exp are kept per row and

@@ -1250,6 +1250,20 @@ extern "C" int mvc_vocab_argmax_bf16(int M, int V, int K, const void* h, int64_t
   return tc_gemm_argmax(M, V, K, h, ldh, out_w, ldw, out_b, pval, pidx, ids, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
+extern "C" int mvc_vocab_aux_row0(int V) { return tc_aux_row0(V); }
+
+extern "C" int mvc_vocab_argmax_wq_bf16(int M, int V, int K, int A, const void* h, int64_t ldh, const void* w_ext,
+                                        int64_t ldw, const float* out_b, void* workspace, size_t workspace_bytes,
+                                        int64_t* ids, float* wq, void* stream) {
+  MVC_CHECK(h && w_ext && workspace && ids && wq && A > 0, "mvc_vocab_argmax_wq_bf16: bad argument");
+  const size_t need = (size_t)M * tc_gemm_argmax_tiles(V) * 8;
+  MVC_CHECK(workspace_bytes >= need, "mvc_vocab_argmax_wq_bf16: workspace %zu < %zu", workspace_bytes, need);
+  float* pval = static_cast<float*>(workspace);
+  int* pidx = reinterpret_cast<int*>(pval + (size_t)M * tc_gemm_argmax_tiles(V));
+  const TcAux aux{tc_aux_row0(V), A, wq, A};
+  return tc_gemm_argmax(M, V, K, h, ldh, w_ext, ldw, out_b, pval, pidx, ids, nullptr, 0, 0, (cudaStream_t)stream, &aux);
+}
+
 extern "C" int mvc_gemm_bf16_ex(int M, int N, int K, const void* A, int64_t lda, int a_transposed, const void* B, int64_t ldb,
                                 int b_transposed, float beta, float* C, int64_t ldc, const float* bias, void* stream) {
   if (M <= 0 || N <= 0) return 0;

@@ -79,6 +79,8 @@ SIGNATURES = {
     "mvc_pack_gate_rows_bf16": (i32, [vp, i32, i32, i64, i32, vp, vp]),
     "mvc_lstm_gates_cell_bf16": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
     "mvc_vocab_argmax_bf16": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, vp, sz, vp, vp]),
+    "mvc_vocab_aux_row0": (i32, [i32]),
+    "mvc_vocab_argmax_wq_bf16": (i32, [i32, i32, i32, i32, vp, i64, vp, i64, vp, vp, sz, vp, vp, vp]),
     "mvc_vocab_topk_workspace_bytes": (sz, [i32, i32]),
     "mvc_vocab_topk_bf16": (i32, [i32, i32, i32, vp, i64, vp, i64, vp, i32, vp, sz, vp, vp, vp]),
     "mvc_lstm_cell_bwd": (i32, [i32, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp]),

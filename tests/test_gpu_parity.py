@@ -157,6 +157,41 @@ def test_vocab_argmax_fused(dev, M, V, K):
     assert float(same.float().mean()) > 0.99
 
 
+@pytest.mark.parametrize("M,V,K,A", [(512, 10547, 512, 256), (5, 300, 64, 32), (130, 3201, 512, 256)])
+def test_vocab_argmax_with_query_projection(dev, M, V, K, A):
+    """Decode-loop GEMM: arg-max over the vocabulary columns AND W.h of the next step from the auxiliary column block
+    of the same launch (B operand = [out.weight ; zero padding ; attention.W])."""
+    from salstm import cabi
+    lib = cabi.lib()
+    g = torch.Generator().manual_seed(M + V + A)
+    h = torch.randn(M, K, generator=g).bfloat16().to(dev)
+    w = (torch.randn(V, K, generator=g) * 0.2).bfloat16()
+    attw = (torch.randn(A, K, generator=g) * 0.3).bfloat16()
+    b = torch.randn(V, generator=g).to(dev)
+    r0 = lib.mvc_vocab_aux_row0(V)
+    assert r0 % 256 == 0 and 0 <= r0 - V < 256
+    w_ext = torch.zeros(r0 + A, K, dtype=torch.bfloat16)
+    w_ext[:V] = w
+    w_ext[V:r0] = 7.0                        # padding rows must be ignored by the arg-max
+    w_ext[r0:] = attw
+    w_ext = w_ext.to(dev)
+    ws = torch.empty(M * ((V + 255) // 256) * 8, dtype=torch.uint8, device=dev)
+    ids = torch.empty(M, dtype=torch.int64, device=dev)
+    wq = torch.full((M, A), float("nan"), device=dev)
+    cabi.check(lib.mvc_vocab_argmax_wq_bf16(M, V, K, A, cabi.ptr(h), K, cabi.ptr(w_ext), K, cabi.ptr(b), cabi.ptr(ws),
+                                            ws.numel(), cabi.ptr(ids), cabi.ptr(wq), cabi.stream_ptr()))
+    logits = h.double() @ w.to(dev).double().t() + b.double()
+    ref = logits.argmax(1)
+    same = ids == ref
+    if not bool(same.all()):
+        r = torch.arange(M, device=dev)
+        gap = (logits[r, ref] - logits[r, ids]).abs()
+        assert float(gap[~same].max()) < 1e-4 * float(logits.abs().max())
+    assert float(same.float().mean()) > 0.99
+    wq_ref = (h.double() @ attw.to(dev).double().t()).float()
+    close(wq.cpu(), wq_ref.cpu(), atol=2e-3, rtol=1e-4)      # bf16 products, fp32 accumulation over K
+
+
 @pytest.mark.parametrize("M,V,K,width", [(640, 10547, 512, 5), (9, 300, 64, 3), (130, 3201, 512, 8)])
 def test_vocab_topk_fused(dev, M, V, K, width):
     """K-E (beam): top-`width` log-probs + tokens from the GEMM epilogue == torch.topk(log_softmax(logits))."""

@@ -64,6 +64,9 @@ classes = [
     ("gemm_tc vocab fwd", (1, S * B, V, 512)),
     ("gemm_tc vocab step", (1, B, V, 512)),
     ("gemm_tc embtab", (1, V, 2048, 304)),
+    ("beam gates+cell (5B,4H,F+H)", (1, 5 * B, 2048, 2688)),
+    ("beam vocab topk (5B,V+aux,H)", (1, 5 * B, (V + 255) // 256 * 256 + 256, 512)),
+    ("greedy vocab argmax (B,V+aux,H)", (1, B, (V + 255) // 256 * 256 + 256, 512)),
     ("gemm_tc gates greedy (B,4H,F+H)", (1, B, 2048, 2688)),
     ("gemm_tc uk", (1, B * T, 256, 2176)),
     ("gemm_tc gx (SB,4H,Ep)", (1, S * B, 2048, 304)),
