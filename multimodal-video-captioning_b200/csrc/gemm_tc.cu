@@ -91,7 +91,7 @@ struct TcSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOK_OFF = BAR_OFF + (2 * STAGES + 1) * 8 + 16;        // int64 tokens of the CTA's reduce rows
-  static constexpr int TOTAL = TOK_OFF + 64 * 8 + 1024;                      // + alignment slack
+  static constexpr int TOTAL = TOK_OFF + 128 * 8 + 1024;                     // + alignment slack
 };
 
 
@@ -309,7 +309,7 @@ __device__ __forceinline__ void cell_reduce_rows(const TcEpilogue& ep, uint32_t 
 }
 
 template <int BN, int STAGES, int MODE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, (STAGES <= 3 ? 2 : 1))
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
                     int K, const __grid_constant__ TcEpilogue ep) {
   using S = TcSmem<BN, STAGES>;
@@ -413,46 +413,31 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     pdl_wait();                                   // C / cell state may still be in use upstream
     if constexpr (MODE == TC_MODE_CELL) {
-      if (splits > 1) {
-        // split-K: stage the tokens of the rows this CTA will finish (embedding-table gather in the reduction)
-        const int rows_per = TC_BM / splits;
-        const int te = threadIdx.x - 64;
-        const int64_t gmr = (int64_t)m0 + z * rows_per + te;
-        if (te < rows_per) s_tok[te] = (ep.embtab && gmr < M) ? ep.tokens[gmr] : 0;
-      }
+      // stage the tokens of the rows this CTA will finish (embedding-table gather in the cell epilogue)
+      const int rows_per = TC_BM / splits;
+      const int te = threadIdx.x - 64;
+      const int64_t gmr = (int64_t)m0 + z * rows_per + te;
+      if (te < rows_per) s_tok[te] = (ep.embtab && gmr < M) ? ep.tokens[gmr] : 0;
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     TC_STAMP(4, threadIdx.x == 64);
-    if (splits == 1) {
+    if (splits == 1 && MODE == TC_MODE_PLAIN) {
       const int64_t gm = (int64_t)m0 + row;
-      if constexpr (MODE == TC_MODE_PLAIN) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(trow + (uint32_t)(c * 32), v);
-          if (gm < M) {
-            float o[32];
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(trow + (uint32_t)(c * 32), v);
+        if (gm < M) {
+          float o[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
-            plain_store<32>(ep, gm, n0 + c * 32, N, o);
-          }
+          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+          plain_store<32>(ep, gm, n0 + c * 32, N, o);
         }
-      } else {
-        float g4[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(trow + (uint32_t)(c * 32), v);
-          // tile column c*32 + j  ->  unit block c/2, gate (c%2)*2 + j/16, unit j%16
-#pragma unroll
-          for (int j = 0; j < 32; ++j) g4[(c & 1) * 2 + (j >> 4)][(c >> 1) * 16 + (j & 15)] = __uint_as_float(v[j]);
-        }
-        if (gm < M) cell_store<32>(ep, gm, blockIdx.x, 0, g4);
       }
     } else {
-      // split-K: park this CTA's partial tile in its own shared memory (the operand ring is idle now: every MMA has
-      // completed), row pitch BN + 4 words.  Plain: row-major.  Cell: UNIT-major, the four gates of a unit adjacent
+      // split-K (and the unsplit cell epilogue): park this CTA's tile in its own shared memory (the operand ring is
+      // idle now: every MMA has completed), row pitch BN + 4 words.  Plain: row-major.  Cell: UNIT-major, the four gates of a unit adjacent
       // (word (k*16 + u)*4 + g for packed column k*64 + g*16 + u), so that the reduction reads one float4 per unit.
       float* red = reinterpret_cast<float*>(smem);
       constexpr int RS = BN + 4;
@@ -479,6 +464,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                       __uint_as_float(v[j + 3]));
         }
+      }
+    }
+    if constexpr (MODE == TC_MODE_CELL) {
+      if (splits == 1) {
+        // unsplit cell epilogue = the same warp-per-row pass over the parked tile (S = 1: only this CTA's partial)
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps: whole tile parked
+        cell_reduce_rows<1>(ep, smem_base, BN + 4, 0, warp - 2, lane, m0, M, blockIdx.x, s_tok);
       }
     }
     tc_fence_before();
@@ -1055,6 +1047,9 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
   if (ep.mode == TC_MODE_CELL) {
     MVC_CHECK(N % 128 == 0 && N == 4 * ep.H, "fused LSTM-cell epilogue needs N == 4H with H %% 32 == 0 (N=%d H=%d)", N, ep.H);
     const int s = splits_for(mt * (N / 128), max_active_clusters<128, 6, TC_MODE_CELL>);
+    // several waves of tiles (beam search: M = width x B): a 3-stage ring leaves room for TWO resident CTAs per SM, so
+    // one CTA's cell epilogue overlaps the other's MMAs
+    if (s == 1 && mt * (N / 128) > kNumSMs) return launch_tc<128, 3, TC_MODE_CELL>(M, N, K, A, lda, B, ldb, ep, 1, pdl, st);
     return launch_tc<128, 6, TC_MODE_CELL>(M, N, K, A, lda, B, ldb, ep, s, pdl, st);
   }
   // big GEMMs (>= half a wave of 128x256 tiles): persistent kernel with double-buffered TMEM accumulators
