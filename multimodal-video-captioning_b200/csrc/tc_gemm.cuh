@@ -29,6 +29,7 @@ struct TcEpilogue {
   // fused top-8 + online log-sum-exp (mode == TC_MODE_TOPK): per (row, 256-column tile)
   float* topk_val;            // [ceil(N/256), 8, M]
   int* topk_idx;              // [ceil(N/256), 8, M]
+  int topk_k;                 // entries of the per-tile lists actually needed (<= 8)
   float* lse_max;             // [ceil(N/256), M]
   float* lse_sum;             // [ceil(N/256), M]
   // arg-max / top-k modes, optional auxiliary column block: B rows [aux_n0, N) (aux_n0 a multiple of 256, >= n_main)
