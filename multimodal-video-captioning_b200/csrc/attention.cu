@@ -430,6 +430,225 @@ attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
 #undef AT_STAMP
 }
 
+// Multi-query variant (beam search: the `nq` beams of one video share its staged key block).  Up to QB queries are
+// processed per pass: the U.k row of a frame is read once for all their scores, every staged key vector once for all
+// their context sums, and the soft-max of query q runs on warp q -- instead of nq sequential single-query passes,
+// each with its own global round trip for wq and its own four block-wide synchronisations.
+template <typename KT, bool FAST, int AV, int NT, int QB>
+__global__ void __launch_bounds__(NT, 2)
+attn_fwd_staged_mq_kernel(const AttnFwdArgs a, int chunk) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int NW = NT / 32;
+  constexpr int VN = VecOf<KT>::N;
+  static_assert(QB <= NW, "one soft-max warp per query");
+  const int T = a.T, A = AV * 32, F = a.F;
+  const int kb = blockIdx.x;
+  const int nq = a.B / a.keys_batch;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int cl = gridDim.y, rank = blockIdx.y;
+  const int f0 = rank * chunk, f1 = min(F, f0 + chunk), ncols = f1 - f0;
+  const int Tc = (T + cl - 1) / cl, t0 = min(T, rank * Tc), t1 = min(T, t0 + Tc);
+  const int Tp = (T + 3) & ~3;
+  const size_t stage_bytes = ((size_t)T * chunk * sizeof(KT) + 127) & ~size_t(127);
+  KT* sK = reinterpret_cast<KT*>(smem_raw);
+  float* sU = reinterpret_cast<float*>(smem_raw + stage_bytes);     // [Tc][A]
+  float* sQ = sU + (size_t)Tc * A;                                  // [QB][A]
+  float* sW = sQ + (size_t)QB * A;                                  // [A]
+  float* sE = sW + A;                                               // [2][QB][Tp] raw scores, double buffered over passes
+  float* sP = sE + 2 * QB * Tp;                                     // [QB][Tp] soft-max weights of the current pass
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sP + QB * Tp);
+  const uint32_t bar_u = smem_u32(mbar), bar_k = smem_u32(mbar + 1);
+  unsigned long long* prof = a.prof ? a.prof + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+#define AT_STAMP(i) do { if (prof && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); prof[i] = t_; } } while (0)
+  AT_STAMP(0);
+  if (wid == 0) {
+    const KT* kbase = reinterpret_cast<const KT*>(a.keys) + (int64_t)kb * a.k_sb + f0;
+    const uint32_t row_bytes = (uint32_t)(ncols * sizeof(KT));
+    const bool one_copy = (ncols == chunk && a.k_st == chunk);
+    if (lane == 0) {
+      mbar_init(bar_u, 1);
+      mbar_init(bar_k, 1);
+      fence_mbar_init();
+      const uint32_t ub = (uint32_t)((t1 - t0) * A * sizeof(float));
+      if (ub) {
+        mbar_expect_tx(bar_u, ub);
+        bulk_load_1d(smem_u32(sU), a.uk + ((int64_t)kb * T + t0) * A, ub, bar_u);
+      }
+      if (ncols > 0) {
+        mbar_expect_tx(bar_k, row_bytes * (uint32_t)T);
+        if (one_copy) bulk_load_1d(smem_u32(sK), kbase, row_bytes * (uint32_t)T, bar_k);
+      }
+    }
+    __syncwarp();
+    if (ncols > 0 && !one_copy)
+      for (int t = lane; t < T; t += 32)
+        bulk_load_1d(smem_u32(sK + (size_t)t * chunk), kbase + (int64_t)t * a.k_st, row_bytes, bar_k);
+  }
+  for (int i = tid; i < A; i += NT) sW[i] = a.w[i];
+  __syncthreads();
+  if (cl > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  AT_STAMP(1);
+  pdl_trigger();
+  pdl_wait();
+  if (cl > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  AT_STAMP(2);
+  const uint32_t sE_u32 = smem_u32(sE);
+  float wv[AV];
+#pragma unroll
+  for (int k = 0; k < AV; ++k) wv[k] = sW[lane + 32 * k];
+  int pass = 0;
+  for (int q0 = 0; q0 < nq; q0 += QB, ++pass) {
+    const int nqp = min(QB, nq - q0);
+    float* sEp = sE + (pass & 1) * QB * Tp;
+    if (q0) __syncthreads();        // previous pass's readers of sQ / sP are done
+    for (int i = tid; i < nqp * A; i += NT) {
+      const int q = i / A, c = i - q * A;
+      sQ[i] = a.wq[((int64_t)(q0 + q) * a.keys_batch + kb) * A + c] + a.bias[c];
+    }
+    __syncthreads();
+    if (q0 == 0 && t1 > t0) mbar_wait(bar_u, 0);
+    AT_STAMP(3);
+    for (int t = t0 + wid; t < t1; t += NW) {
+      const float* urow = sU + (size_t)(t - t0) * A + lane;
+      float u[AV];
+#pragma unroll
+      for (int k = 0; k < AV; ++k) u[k] = urow[32 * k];
+      float e[QB];
+#pragma unroll
+      for (int q = 0; q < QB; ++q) {
+        e[q] = 0.f;
+        if (q < nqp) {
+          const float* qrow = sQ + q * A + lane;
+#pragma unroll
+          for (int k = 0; k < AV; ++k) e[q] = fmaf(wv[k], tanh_sel<FAST>(qrow[32 * k] + u[k]), e[q]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < QB; ++q) e[q] += __shfl_xor_sync(0xffffffffu, e[q], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+          if (q < nqp) {
+            float ev = e[q];
+            const int b = (q0 + q) * a.keys_batch + kb;
+            if (a.mask && !a.mask[b * a.m_sb + t * a.m_st]) ev = -INFINITY;
+            if (cl == 1) {
+              sEp[q * Tp + t] = ev;
+            } else {
+              const uint32_t off = sE_u32 + (uint32_t)((((pass & 1) * QB + q) * Tp + t) * 4);
+              for (int pr = 0; pr < cl; ++pr) {
+                uint32_t dst;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(off), "r"(pr));
+                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst), "f"(ev) : "memory");
+              }
+            }
+          }
+        }
+      }
+    }
+    if (cl > 1) {
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+      __syncthreads();
+    }
+    AT_STAMP(4);
+    // soft-max of query q on warp q (T <= 72: at most three values per lane)
+    if (wid < nqp) {
+      const float* er = sEp + wid * Tp;
+      const int b = (q0 + wid) * a.keys_batch + kb;
+      float v[3];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int t = lane + 32 * i;
+        v[i] = t < T ? er[t] : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+      }
+      mx = warp_max(mx);
+      float sm = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int t = lane + 32 * i;
+        v[i] = t < T ? (FAST ? __expf(v[i] - mx) : expf(v[i] - mx)) : 0.f;
+        sm += v[i];
+      }
+      sm = warp_sum(sm);
+      const float inv = 1.f / sm;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int t = lane + 32 * i;
+        if (t < T) {
+          const float pv = v[i] * inv;
+          sP[wid * Tp + t] = pv;
+          if (rank == 0) a.alpha[(int64_t)b * T + t] = pv;
+        }
+      }
+    }
+    __syncthreads();
+    AT_STAMP(5);
+    if (ncols <= 0) continue;
+    if (q0 == 0) mbar_wait(bar_k, 0);
+    AT_STAMP(6);
+    const int nvec = ncols / VN;
+    for (int v = tid; v < nvec; v += NT) {
+      float acc[QB][VN];
+#pragma unroll
+      for (int q = 0; q < QB; ++q)
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[q][i] = 0.f;
+#pragma unroll 2
+      for (int t = 0; t < T; ++t) {
+        const typename VecOf<KT>::Raw raw = *reinterpret_cast<const typename VecOf<KT>::Raw*>(sK + (size_t)t * chunk + v * VN);
+        float x[VN];
+        VecOf<KT>::unpack(raw, x);
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+          if (q < nqp) {
+            const float pw = sP[q * Tp + t];
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc[q][i] = fmaf(pw, x[i], acc[q][i]);
+          }
+        }
+      }
+      const int f = f0 + v * VN;
+#pragma unroll
+      for (int q = 0; q < QB; ++q) {
+        if (q < nqp) {
+          const int64_t b = (int64_t)(q0 + q) * a.keys_batch + kb;
+          if (a.ctx_f32) {
+            float4* dst = reinterpret_cast<float4*>(a.ctx_f32 + b * a.ctx_ld + f);
+#pragma unroll
+            for (int i = 0; i < VN / 4; ++i)
+              dst[i] = make_float4(acc[q][4 * i], acc[q][4 * i + 1], acc[q][4 * i + 2], acc[q][4 * i + 3]);
+          }
+          if (a.ctx_bf16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.ctx_bf16) + b * a.ctxb_ld + f;
+            if constexpr (VN == 8) {
+              uint4 pk;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[q][0], acc[q][1]), h1 = __floats2bfloat162_rn(acc[q][2], acc[q][3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[q][4], acc[q][5]), h3 = __floats2bfloat162_rn(acc[q][6], acc[q][7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(dst) = pk;
+            } else {
+              uint2 pk;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[q][0], acc[q][1]), h1 = __floats2bfloat162_rn(acc[q][2], acc[q][3]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(dst) = pk;
+            }
+          }
+        }
+      }
+    }
+    AT_STAMP(7);
+  }   // passes
+#undef AT_STAMP
+}
+
 // Backward, one CTA per batch row; keys row block staged by TMA bulk copies, U.k in registers.
 template <typename KT, bool FAST, int AV, int NT>
 __global__ void __launch_bounds__(NT)
@@ -635,6 +854,17 @@ static const void* pick_fwd_staged(int A) {
     default: return nullptr;
   }
 }
+constexpr int ATT_QB = 8;      // queries per pass of the multi-query kernel (beam widths up to 8 in one pass)
+static const void* pick_fwd_staged_mq(int A) {
+  switch (A) {
+    case 32: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 1, 288, ATT_QB>;
+    case 64: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 2, 288, ATT_QB>;
+    case 128: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 4, 288, ATT_QB>;
+    case 256: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 8, 288, ATT_QB>;
+    default: return nullptr;
+  }
+}
+
 template <typename KT, bool FAST>
 static const void* pick_bwd_staged(int A) {
   switch (A) {
@@ -669,8 +899,14 @@ int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
     if (a.keys_bf16) kern = a.fast_math ? pick_fwd_staged<__nv_bfloat16, true>(A) : pick_fwd_staged<__nv_bfloat16, false>(A);
     else kern = a.fast_math ? pick_fwd_staged<float, true>(A) : pick_fwd_staged<float, false>(A);
   }
+  // several queries per key block (beam search), bf16 keys, fast math: the multi-query kernel
+  const int nq = a.keys_batch > 0 ? B / a.keys_batch : 1;
+  const bool mq = kern && nq > 1 && a.keys_bf16 && a.fast_math && pick_fwd_staged_mq(A);
+  if (mq) kern = pick_fwd_staged_mq(A);
   if (kern) {
-    const size_t tail0 = sizeof(float) * (2 * (size_t)A + 3 * (size_t)((T + 3) & ~3)) + 16;
+    const size_t tp = (size_t)((T + 3) & ~3);
+    const size_t tail0 = mq ? sizeof(float) * ((ATT_QB + 1) * (size_t)A + 3 * ATT_QB * tp) + 16
+                            : sizeof(float) * (2 * (size_t)A + 3 * tp) + 16;
     // F-chunks per key block = CTAs per cluster (1, 2, 4 or 8; scores are shared through DSMEM, so splitting costs no
     // repeated work): the fewest whose staged keys fit in shared memory, more while the grid cannot fill the SMs.
     // An unsplit row whose [T, F] block is contiguous arrives by ONE bulk copy; an F-chunk needs T strided copies,

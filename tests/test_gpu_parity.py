@@ -341,6 +341,38 @@ def test_attention_kernels_vs_oracle(dev, B, T, A, F, bf16):
         close(dk, k_.grad, atol=1e-5, rtol=1e-3)
 
 
+@pytest.mark.parametrize("NB,nq,T,A,F", [(16, 5, 30, 256, 2176), (3, 8, 7, 32, 64), (20, 11, 24, 256, 512)])
+def test_attention_multi_query_shared_keys(dev, NB, nq, T, A, F):
+    """Beam-search layout: query row q*NB + b attends over key block b (keys_batch = NB).  bf16 keys + fast math take
+    the multi-query kernel (up to 8 queries per pass, so nq = 11 needs two passes); checked against the closed form
+    with tanh.approx-level tolerances."""
+    from salstm import cabi
+    lib = cabi.lib()
+    g = torch.Generator().manual_seed(NB * 100 + nq)
+    B = NB * nq
+    wq = torch.randn(B, A, generator=g)
+    uk = torch.randn(NB, T, A, generator=g)
+    bias = torch.randn(A, generator=g)
+    w = torch.randn(A, generator=g) * 0.3
+    keys = torch.randn(NB, T, F, generator=g).bfloat16()
+    kb = torch.arange(B) % NB
+    e = torch.tanh(wq.double().unsqueeze(1) + uk.double()[kb] + bias.double()) @ w.double()
+    al = torch.softmax(e, 1)
+    ctx = (keys.double()[kb] * al.unsqueeze(2)).sum(1)
+    d = lambda t: t.to(dev).contiguous()
+    ctx_g = torch.empty(B, F, device=dev)
+    ctx_b = torch.empty(B, F, device=dev, dtype=torch.bfloat16)
+    al_g = torch.empty(B, T, device=dev)
+    wqd, ukd, bd, wd, kd = d(wq), d(uk), d(bias), d(w), d(keys)
+    cabi.check(lib.mvc_soft_attention_fwd(B, T, A, F, cabi.ptr(wqd), cabi.ptr(ukd), cabi.ptr(bd), cabi.ptr(wd),
+                                          cabi.ptr(kd), 1, NB, T * F, F, None, 0, 0, cabi.ptr(ctx_g), F,
+                                          cabi.ptr(ctx_b), F, cabi.ptr(al_g), 1, cabi.stream_ptr()))
+    close(al_g, al, atol=3e-3, rtol=2e-2)
+    close(ctx_g, ctx, atol=2e-2, rtol=2e-2)
+    close(ctx_b.float(), ctx, atol=4e-2, rtol=2e-2)
+    assert float((al_g.sum(1) - 1).abs().max()) < 1e-5
+
+
 # --------------------------------------------------------------------------- decoder vs golden
 def _small_decoder(dev, g, precision="fp32"):
     from salstm.modules import FeaturesCaptioning
