@@ -435,7 +435,7 @@ attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
 // their context sums, and the soft-max of query q runs on warp q -- instead of nq sequential single-query passes,
 // each with its own global round trip for wq and its own four block-wide synchronisations.
 template <typename KT, bool FAST, int AV, int NT, int QB>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 1)
 attn_fwd_staged_mq_kernel(const AttnFwdArgs a, int chunk) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int NW = NT / 32;
@@ -513,15 +513,15 @@ attn_fwd_staged_mq_kernel(const AttnFwdArgs a, int chunk) {
       float u[AV];
 #pragma unroll
       for (int k = 0; k < AV; ++k) u[k] = urow[32 * k];
+      // branch-free over the QB slots (slots >= nqp compute on stale shared memory and are never stored): a uniform
+      // branch per query cut the loop into 9-instruction basic blocks, each exposing its own shared-memory latency
       float e[QB];
 #pragma unroll
       for (int q = 0; q < QB; ++q) {
         e[q] = 0.f;
-        if (q < nqp) {
-          const float* qrow = sQ + q * A + lane;
+        const float* qrow = sQ + q * A + lane;
 #pragma unroll
-          for (int k = 0; k < AV; ++k) e[q] = fmaf(wv[k], tanh_sel<FAST>(qrow[32 * k] + u[k]), e[q]);
-        }
+        for (int k = 0; k < AV; ++k) e[q] = fmaf(wv[k], tanh_sel<FAST>(qrow[32 * k] + u[k]), e[q]);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -600,19 +600,18 @@ attn_fwd_staged_mq_kernel(const AttnFwdArgs a, int chunk) {
       for (int q = 0; q < QB; ++q)
 #pragma unroll
         for (int i = 0; i < VN; ++i) acc[q][i] = 0.f;
-#pragma unroll 2
+#pragma unroll 6
       for (int t = 0; t < T; ++t) {
         const typename VecOf<KT>::Raw raw = *reinterpret_cast<const typename VecOf<KT>::Raw*>(sK + (size_t)t * chunk + v * VN);
         float x[VN];
         VecOf<KT>::unpack(raw, x);
+        float pw[QB];
 #pragma unroll
-        for (int q = 0; q < QB; ++q) {
-          if (q < nqp) {
-            const float pw = sP[q * Tp + t];
+        for (int q = 0; q < QB; ++q) pw[q] = sP[q * Tp + t];
 #pragma unroll
-            for (int i = 0; i < VN; ++i) acc[q][i] = fmaf(pw, x[i], acc[q][i]);
-          }
-        }
+        for (int q = 0; q < QB; ++q)
+#pragma unroll
+          for (int i = 0; i < VN; ++i) acc[q][i] = fmaf(pw[q], x[i], acc[q][i]);
       }
       const int f = f0 + v * VN;
 #pragma unroll
@@ -854,13 +853,14 @@ static const void* pick_fwd_staged(int A) {
     default: return nullptr;
   }
 }
-constexpr int ATT_QB = 8;      // queries per pass of the multi-query kernel (beam widths up to 8 in one pass)
+// queries per pass of the multi-query kernel: 5 (the reference's beam width, features_captioning.py:131) or 8
+template <int QB>
 static const void* pick_fwd_staged_mq(int A) {
   switch (A) {
-    case 32: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 1, 288, ATT_QB>;
-    case 64: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 2, 288, ATT_QB>;
-    case 128: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 4, 288, ATT_QB>;
-    case 256: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 8, 288, ATT_QB>;
+    case 32: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 1, 288, QB>;
+    case 64: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 2, 288, QB>;
+    case 128: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 4, 288, QB>;
+    case 256: return (const void*)attn_fwd_staged_mq_kernel<__nv_bfloat16, true, 8, 288, QB>;
     default: return nullptr;
   }
 }
@@ -901,11 +901,13 @@ int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
   }
   // several queries per key block (beam search), bf16 keys, fast math: the multi-query kernel
   const int nq = a.keys_batch > 0 ? B / a.keys_batch : 1;
-  const bool mq = kern && nq > 1 && a.keys_bf16 && a.fast_math && pick_fwd_staged_mq(A);
-  if (mq) kern = pick_fwd_staged_mq(A);
+  const int qb = nq <= 5 ? 5 : 8;
+  const void* kern_mq = qb == 5 ? pick_fwd_staged_mq<5>(A) : pick_fwd_staged_mq<8>(A);
+  const bool mq = kern && nq > 1 && a.keys_bf16 && a.fast_math && kern_mq;
+  if (mq) kern = kern_mq;
   if (kern) {
     const size_t tp = (size_t)((T + 3) & ~3);
-    const size_t tail0 = mq ? sizeof(float) * ((ATT_QB + 1) * (size_t)A + 3 * ATT_QB * tp) + 16
+    const size_t tail0 = mq ? sizeof(float) * ((qb + 1) * (size_t)A + 3 * qb * tp) + 16
                             : sizeof(float) * (2 * (size_t)A + 3 * tp) + 16;
     // F-chunks per key block = CTAs per cluster (1, 2, 4 or 8; scores are shared through DSMEM, so splitting costs no
     // repeated work): the fewest whose staged keys fit in shared memory, more while the grid cannot fill the SMs.
