@@ -437,9 +437,10 @@ def roofline_pass(lib, args, step, resident, shape, pk, arm=True):
                          "(see profiles/recur_phases_r1.txt); tensor pipe is idle between steps"}
     else:
         # launch-chain paths: soft-attention forward kernel, reads keys [B,T,F] + U.k [B,T,A] once per launch
+        # (beam: the 5 beams of a video share ONE staged key block and U.k slab; only queries / outputs are per beam)
         rows = B if args.workload != "beam" else 5 * B
         kid, m, n, k = 3, rows, T, F
-        alg = rows * T * (F * es + A * 4) + rows * (F * es + T * 4 + A * 4)
+        alg = B * T * (F * es + A * 4) + rows * (F * es + T * 4 + A * 4)
         bound, peak, unit, scale = "hbm", pk["hbm"], "GB/s", 1e9
         name = f"attn_fwd_staged_kernel B={rows} T={T} F={F} ({'bf16' if es == 2 else 'fp32'} keys)"
         extra = {"algorithmic_bytes_per_launch": alg, "peak_source": pk["src"] + " (hbm_gbs)",

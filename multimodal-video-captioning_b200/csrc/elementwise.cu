@@ -587,8 +587,8 @@ extern "C" int mvc_log_softmax_bwd(const float* logp, const float* dlogp, int64_
   if (rows == 0) return 0;
   MVC_CHECK(logp && dlogp && (dlogits || dlogits_bf16), "mvc_log_softmax_bwd: bad arguments");
   const int64_t ldb = (V + 7) / 8 * 8;
-  // bf16 consumers only (training hot path): row kept in registers, one read of each operand
-  if (!dlogits && V <= 16 * 256)
+  // bf16 path (training hot path): row kept in registers, one read of each operand
+  if (dlogits_bf16 && V <= 16 * 256)
     log_softmax_bwd_kernel<16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logp, dlogp, V, dlogits,
                                                                               (__nv_bfloat16*)dlogits_bf16, ldb);
   else
