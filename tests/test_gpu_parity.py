@@ -236,6 +236,34 @@ def test_beam_bf16_width1_equals_greedy(dev):
     assert len(b5) == B and all(len(x) == 22 and x[0] == 1 for x in b5)
 
 
+def test_beam5_bf16_agrees_with_fp32_path(dev):
+    """Width-5 beam search, bf16 path (multi-query shared-key attention, fused top-5 + log-sum-exp epilogue with the next
+    step's query projection in the same GEMM, two-CTA cell GEMM) against the fp32 exact path of the same weights
+    (which is pinned to the reference's golden beams).  bf16 rounding flips near-ties and a flip cascades, so the bar
+    is statistical: on O(1)-scaled features the bf16 beams must equal the fp32 beams up to the first EOS for >= 70 %
+    of the videos, and not much less often than the bf16 GREEDY captions equal the fp32 greedy ones (measured on a
+    B200: beam 54/64, greedy 55/64; raw-scale features: 37/64 and 50/64, `tools/beam_probe.py`)."""
+    from models import AVCaptioning
+    B, T, V = 64, 30, 10547
+    torch.manual_seed(3)
+    m32 = AVCaptioning(Vocab(V), 0.0, "none", device=dev).to(dev)
+    with torch.no_grad():
+        m32.decoder.out.weight.mul_(8.0)
+    mbf = AVCaptioning(Vocab(V), 0.0, "none", device=dev, precision="bf16").to(dev)
+    mbf.load_state_dict(m32.state_dict())
+    audio, visual, _ = (t.to(dev) for t in O.synth_batch(B, T, 20, V, seed=11, min_frames=10))
+    audio, visual = audio / 255.0, visual / 48.0
+    with torch.no_grad():
+        g32 = m32.predict_ids(audio, visual, 20, mode="direct")
+        gbf = mbf.predict_ids(audio, visual, 20, mode="direct")
+        a = m32.predict_ids(audio, visual, 20, mode="beam", beam_width=5)
+        b = mbf.predict_ids(audio, visual, 20, mode="beam", beam_width=5)
+    greedy_agree = sum(_prefix([1] + list(x[1:])) == _prefix([1] + list(y[1:])) for x, y in zip(g32, gbf))
+    agree = sum(_prefix(x) == _prefix(y) for x, y in zip(a, b))
+    assert agree >= 0.7 * B, f"{agree}/{B} bf16 beams equal the fp32 beams up to EOS"
+    assert agree >= greedy_agree - 0.2 * B, f"beam agreement {agree} far below greedy agreement {greedy_agree} (of {B})"
+
+
 @pytest.mark.parametrize("M,N,K", [(2048, 2176, 2944), (256, 512, 2944), (3201, 512, 2944), (130, 72, 200), (2048, 304, 136)])
 @pytest.mark.parametrize("ta,tb", [(1, 1), (1, 0), (0, 1)])
 def test_gemm_bf16_transposed_operands(dev, M, N, K, ta, tb):
