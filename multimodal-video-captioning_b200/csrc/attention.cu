@@ -430,6 +430,189 @@ attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
 #undef AT_STAMP
 }
 
+// Streaming variant for grids of several waves (greedy decode at B = 512: 3.5 key blocks per SM): ONE persistent CTA
+// per SM walks its key blocks and keeps the TMA engine busy across them.  The [T, F] key stage is refilled in two
+// frame halves -- half 0 of the next block is requested as soon as the context sum has consumed half 0 of the current
+// one, half 1 likewise -- and the U.k slab is double buffered, so the loads of block i + 1 overlap the second half of
+// the context sum, the stores and the query / score / soft-max phases of block i + 1.  (A fresh CTA per block
+// serialises load -> compute: 4.7 us per block of which 3.6 us is the block's share of HBM time.)
+// Requires: one query per key block, bf16 keys with k_st == F (contiguous block), F / 8 <= NT.
+template <bool FAST, int AV, int NT>
+__global__ void __launch_bounds__(NT, 1)
+attn_fwd_stream_kernel(const AttnFwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  using KT = __nv_bfloat16;
+  constexpr int NW = NT / 32;
+  constexpr int VN = 8;
+  const int T = a.T, A = AV * 32, F = a.F;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int Tp = (T + 3) & ~3;
+  const int Th = (T + 1) / 2;                                       // frames in half 0
+  const size_t stage_bytes = ((size_t)T * F * sizeof(KT) + 127) & ~size_t(127);
+  KT* sK = reinterpret_cast<KT*>(smem_raw);
+  float* sU = reinterpret_cast<float*>(smem_raw + stage_bytes);     // [2][T][A]
+  float* sQ = sU + 2 * (size_t)T * A;
+  float* sW = sQ + A;
+  float* sE = sW + A;                                               // [Tp]
+  float* sP = sE + Tp;                                              // [Tp]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sP + Tp);
+  const uint32_t bar_k0 = smem_u32(mbar), bar_k1 = smem_u32(mbar + 1), bar_u0 = smem_u32(mbar + 2);
+  const uint32_t half0_bytes = (uint32_t)((size_t)Th * F * sizeof(KT)), half1_bytes = (uint32_t)((size_t)(T - Th) * F * sizeof(KT));
+  const uint32_t slab_bytes = (uint32_t)((size_t)T * A * sizeof(float));
+  const int nblk = a.keys_batch;
+  auto load_keys = [&](int kb, int half) {      // tid 0 only
+    const KT* src = reinterpret_cast<const KT*>(a.keys) + (int64_t)kb * a.k_sb + (half ? (size_t)Th * F : 0);
+    const uint32_t bytes = half ? half1_bytes : half0_bytes;
+    const uint32_t bar = half ? bar_k1 : bar_k0;
+    if (bytes) {
+      mbar_expect_tx(bar, bytes);
+      bulk_load_1d(smem_u32(sK + (half ? (size_t)Th * F : 0)), src, bytes, bar);
+    } else {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    }
+  };
+  auto load_slab = [&](int kb, int buf) {       // tid 0 only
+    mbar_expect_tx(bar_u0 + 8u * buf, slab_bytes);
+    bulk_load_1d(smem_u32(sU + (size_t)buf * T * A), a.uk + (int64_t)kb * T * A, slab_bytes, bar_u0 + 8u * buf);
+  };
+  if (tid == 0) {
+    mbar_init(bar_k0, 1);
+    mbar_init(bar_k1, 1);
+    mbar_init(bar_u0, 1);
+    mbar_init(bar_u0 + 8u, 1);
+    fence_mbar_init();
+    if ((int)blockIdx.x < nblk) {
+      load_slab(blockIdx.x, 0);
+      load_keys(blockIdx.x, 0);
+      load_keys(blockIdx.x, 1);
+    }
+  }
+  for (int i = tid; i < A; i += NT) sW[i] = a.w[i];
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();                       // the queries (wq) come from the preceding kernel
+  float wv[AV];
+#pragma unroll
+  for (int k = 0; k < AV; ++k) wv[k] = sW[lane + 32 * k];
+  int it = 0;
+  for (int kb = blockIdx.x; kb < nblk; kb += gridDim.x, ++it) {
+    const int b = kb;
+    const int ub = it & 1;
+    const int nxt = kb + gridDim.x;
+    // U.k slab of the next block into the other buffer (its last readers finished before the previous iteration's
+    // barriers)
+    if (tid == 0 && nxt < nblk) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of that buffer, async-proxy writes next
+      load_slab(nxt, ub ^ 1);
+    }
+    for (int i = tid; i < A; i += NT) sQ[i] = a.wq[(int64_t)b * A + i] + a.bias[i];
+    __syncthreads();
+    mbar_wait(bar_u0 + 8u * ub, (uint32_t)(it >> 1) & 1u);
+    float qv[AV];
+#pragma unroll
+    for (int k = 0; k < AV; ++k) qv[k] = sQ[lane + 32 * k];
+    const float* slab = sU + (size_t)ub * T * A;
+    for (int t = wid; t < T; t += NW) {
+      const float* urow = slab + (size_t)t * A + lane;
+      float e = 0.f;
+#pragma unroll
+      for (int k = 0; k < AV; ++k) e = fmaf(wv[k], tanh_sel<FAST>(qv[k] + urow[32 * k]), e);
+      e = warp_sum(e);
+      if (lane == 0) {
+        if (a.mask && !a.mask[b * a.m_sb + t * a.m_st]) e = -INFINITY;
+        sE[t] = e;
+      }
+    }
+    __syncthreads();
+    if (wid == 0) {                 // soft-max over T (T <= 72: at most three values per lane)
+      float v[3];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int t = lane + 32 * i;
+        v[i] = t < T ? sE[t] : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+      }
+      mx = warp_max(mx);
+      float sm = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int t = lane + 32 * i;
+        v[i] = t < T ? (FAST ? __expf(v[i] - mx) : expf(v[i] - mx)) : 0.f;
+        sm += v[i];
+      }
+      sm = warp_sum(sm);
+      const float inv = 1.f / sm;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int t = lane + 32 * i;
+        if (t < T) {
+          const float pv = v[i] * inv;
+          sP[t] = pv;
+          a.alpha[(int64_t)b * T + t] = pv;
+        }
+      }
+    }
+    __syncthreads();
+    // context sum, frame half by frame half; each half's stage is handed back to the TMA engine as soon as every
+    // thread has read it
+    const int nvec = F / VN;
+    const int v = tid;
+    float acc[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+    mbar_wait(bar_k0, (uint32_t)it & 1u);
+    if (v < nvec) {
+#pragma unroll 5
+      for (int t = 0; t < Th; ++t) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(sK + (size_t)t * F + v * VN);
+        float x[VN];
+        VecOf<KT>::unpack(raw, x);
+        const float pw = sP[t];
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[i] = fmaf(pw, x[i], acc[i]);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && nxt < nblk) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads above, async-proxy writes next
+      load_keys(nxt, 0);
+    }
+    mbar_wait(bar_k1, (uint32_t)it & 1u);
+    if (v < nvec) {
+#pragma unroll 5
+      for (int t = Th; t < T; ++t) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(sK + (size_t)t * F + v * VN);
+        float x[VN];
+        VecOf<KT>::unpack(raw, x);
+        const float pw = sP[t];
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[i] = fmaf(pw, x[i], acc[i]);
+      }
+      const int f = v * VN;
+      if (a.ctx_f32) {
+        float4* dst = reinterpret_cast<float4*>(a.ctx_f32 + b * a.ctx_ld + f);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      if (a.ctx_bf16) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.ctx_bf16) + b * a.ctxb_ld + f;
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]), h3 = __floats2bfloat162_rn(acc[6], acc[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst) = pk;
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && nxt < nblk) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      load_keys(nxt, 1);
+    }
+  }
+}
+
 // Multi-query variant (beam search: the `nq` beams of one video share its staged key block).  Up to QB queries are
 // processed per pass: the U.k row of a frame is read once for all their scores, every staged key vector once for all
 // their context sums, and the soft-max of query q runs on warp q -- instead of nq sequential single-query passes,
@@ -854,6 +1037,17 @@ static const void* pick_fwd_staged(int A) {
   }
 }
 // queries per pass of the multi-query kernel: 5 (the reference's beam width, features_captioning.py:131) or 8
+template <bool FAST>
+static const void* pick_fwd_stream(int A) {
+  switch (A) {
+    case 32: return (const void*)attn_fwd_stream_kernel<FAST, 1, 288>;
+    case 64: return (const void*)attn_fwd_stream_kernel<FAST, 2, 288>;
+    case 128: return (const void*)attn_fwd_stream_kernel<FAST, 4, 288>;
+    case 256: return (const void*)attn_fwd_stream_kernel<FAST, 8, 288>;
+    default: return nullptr;
+  }
+}
+
 template <int QB>
 static const void* pick_fwd_staged_mq(int A) {
   switch (A) {
@@ -905,6 +1099,21 @@ int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
   const void* kern_mq = qb == 5 ? pick_fwd_staged_mq<5>(A) : pick_fwd_staged_mq<8>(A);
   const bool mq = kern && nq > 1 && a.keys_bf16 && a.fast_math && kern_mq;
   if (mq) kern = kern_mq;
+  // several waves of key blocks, one query each (greedy decode): the streaming kernel, one persistent CTA per SM
+  if (kern && !mq && nq == 1 && a.keys_bf16 && a.k_st == F && a.keys_batch > kNumSMs && F / 8 <= 288 &&
+      !getenv("MVC_B200_ATTN_NOSTREAM")) {
+    const void* ks = a.fast_math ? pick_fwd_stream<true>(A) : pick_fwd_stream<false>(A);
+    const size_t tp = (size_t)((T + 3) & ~3);
+    const size_t smem = (((size_t)T * F * 2 + 127) & ~size_t(127)) + sizeof(float) * (2 * (size_t)T * A + 2 * (size_t)A + 2 * tp) + 64;
+    if (ks && smem <= kAttnMaxSmem) {
+      MVC_TRY(ensure_big_smem(ks));
+      AttnFwdArgs args = a;
+      void* params[] = {(void*)&args};
+      MVC_TRY(launch_ex(ks, dim3(kNumSMs), dim3(288), smem, pdl, params, st, 1));
+      MVC_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   if (kern) {
     const size_t tp = (size_t)((T + 3) & ~3);
     const size_t tail0 = mq ? sizeof(float) * ((qb + 1) * (size_t)A + 3 * qb * tp) + 16

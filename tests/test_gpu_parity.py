@@ -316,7 +316,8 @@ def test_attention_golden(dev):
 
 
 @pytest.mark.parametrize("B,T,A,F,bf16", [(3, 5, 8, 12, 0), (128, 44, 256, 2176, 0), (128, 44, 256, 2176, 1),
-                                          (7, 30, 256, 128, 1), (16, 24, 256, 512, 0), (2, 1, 8, 8, 1), (5, 9, 24, 37, 0)])
+                                          (7, 30, 256, 128, 1), (16, 24, 256, 512, 0), (2, 1, 8, 8, 1), (5, 9, 24, 37, 0),
+                                          (300, 30, 256, 2176, 1), (333, 7, 32, 64, 1)])   # > 148 rows: streaming kernel
 def test_attention_kernels_vs_oracle(dev, B, T, A, F, bf16):
     """mvc_soft_attention_fwd / _bwd (masked and not) against autograd through the oracle."""
     from salstm import cabi
