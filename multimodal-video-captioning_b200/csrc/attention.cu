@@ -451,8 +451,8 @@ attn_fwd_stream_kernel(const AttnFwdArgs a) {
   const size_t stage_bytes = ((size_t)T * F * sizeof(KT) + 127) & ~size_t(127);
   KT* sK = reinterpret_cast<KT*>(smem_raw);
   float* sU = reinterpret_cast<float*>(smem_raw + stage_bytes);     // [2][T][A]
-  float* sQ = sU + 2 * (size_t)T * A;
-  float* sW = sQ + A;
+  float* sQ = sU + 2 * (size_t)T * A;                               // [2][A] query + bias, double buffered
+  float* sW = sQ + 2 * A;
   float* sE = sW + A;                                               // [Tp]
   float* sP = sE + Tp;                                              // [Tp]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sP + Tp);
@@ -494,6 +494,8 @@ attn_fwd_stream_kernel(const AttnFwdArgs a) {
   float wv[AV];
 #pragma unroll
   for (int k = 0; k < AV; ++k) wv[k] = sW[lane + 32 * k];
+  if ((int)blockIdx.x < nblk)
+    for (int i = tid; i < A; i += NT) sQ[i] = a.wq[(int64_t)blockIdx.x * A + i] + a.bias[i];
   int it = 0;
   for (int kb = blockIdx.x; kb < nblk; kb += gridDim.x, ++it) {
     const int b = kb;
@@ -505,12 +507,19 @@ attn_fwd_stream_kernel(const AttnFwdArgs a) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of that buffer, async-proxy writes next
       load_slab(nxt, ub ^ 1);
     }
-    for (int i = tid; i < A; i += NT) sQ[i] = a.wq[(int64_t)b * A + i] + a.bias[i];
-    __syncthreads();
+    // the query of the NEXT block is fetched now (global round trip hidden behind this block's work) and parked
+    // in the other sQ buffer at the end of the iteration
+    float qnext[(AV * 32 + NT - 1) / NT];
+#pragma unroll
+    for (int r = 0; r < (AV * 32 + NT - 1) / NT; ++r) {
+      const int i = tid + r * NT;
+      qnext[r] = (nxt < nblk && i < A) ? a.wq[(int64_t)nxt * A + i] + a.bias[i] : 0.f;
+    }
+    __syncthreads();                // sQ[ub] (written at the end of the previous iteration / in the prologue) is visible
     mbar_wait(bar_u0 + 8u * ub, (uint32_t)(it >> 1) & 1u);
     float qv[AV];
 #pragma unroll
-    for (int k = 0; k < AV; ++k) qv[k] = sQ[lane + 32 * k];
+    for (int k = 0; k < AV; ++k) qv[k] = sQ[ub * A + lane + 32 * k];
     const float* slab = sU + (size_t)ub * T * A;
     for (int t = wid; t < T; t += NW) {
       const float* urow = slab + (size_t)t * A + lane;
@@ -604,6 +613,11 @@ attn_fwd_stream_kernel(const AttnFwdArgs a) {
         pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
         *reinterpret_cast<uint4*>(dst) = pk;
       }
+    }
+#pragma unroll
+    for (int r = 0; r < (AV * 32 + NT - 1) / NT; ++r) {
+      const int i = tid + r * NT;
+      if (i < A) sQ[(ub ^ 1) * A + i] = qnext[r];
     }
     __syncthreads();
     if (tid == 0 && nxt < nblk) {
@@ -1104,7 +1118,7 @@ int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
       !getenv("MVC_B200_ATTN_NOSTREAM")) {
     const void* ks = a.fast_math ? pick_fwd_stream<true>(A) : pick_fwd_stream<false>(A);
     const size_t tp = (size_t)((T + 3) & ~3);
-    const size_t smem = (((size_t)T * F * 2 + 127) & ~size_t(127)) + sizeof(float) * (2 * (size_t)T * A + 2 * (size_t)A + 2 * tp) + 64;
+    const size_t smem = (((size_t)T * F * 2 + 127) & ~size_t(127)) + sizeof(float) * (2 * (size_t)T * A + 3 * (size_t)A + 2 * tp) + 64;
     if (ks && smem <= kAttnMaxSmem) {
       MVC_TRY(ensure_big_smem(ks));
       AttnFwdArgs args = a;
