@@ -432,7 +432,11 @@ def roofline_pass(lib, args, step, resident, shape, pk, arm=True):
         bound, peak, unit, scale = "tensor", pk["tensor"], "TFLOP/s", 1e12
         name = (f"recur_fwd_kernel (persistent SA-LSTM recurrence, {S} steps/launch: attention + tcgen05 gate GEMM "
                 f"128x{4 * H}x{F + H} + LSTM cell), B={B}")
-        extra = {"algorithmic_flops_per_launch": alg, "peak_source": pk["src"] + " (bf16_tflops_sustained)",
+        # DRAM bytes per launch of this kernel (dram__bytes_read.sum + dram__bytes_write.sum, one `ncu --set full`
+        # capture of this command at the C2 shape: profiles/ncu_final_kernels_r1.txt); None for other shapes
+        traffic = 66175232 + 6105088 if (B, T, L, V) == SHAPES["msvd"] and args.workload == "train" else None
+        extra = {"traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes read+write)",
+                 "algorithmic_flops_per_launch": alg, "peak_source": pk["src"] + " (bf16_tflops_sustained)",
                  "note": "latency/sync-bound by construction: 2 grid barriers + one L2 round trip per phase per step "
                          "(see profiles/recur_phases_r1.txt); tensor pipe is idle between steps"}
     else:
@@ -443,7 +447,10 @@ def roofline_pass(lib, args, step, resident, shape, pk, arm=True):
         alg = B * T * (F * es + A * 4) + rows * (F * es + T * 4 + A * 4)
         bound, peak, unit, scale = "hbm", pk["hbm"], "GB/s", 1e9
         name = f"attn_fwd_staged_kernel B={rows} T={T} F={F} ({'bf16' if es == 2 else 'fp32'} keys)"
-        extra = {"algorithmic_bytes_per_launch": alg, "peak_source": pk["src"] + " (hbm_gbs)",
+        # greedy at the C3 shape: ncu capture of attn_fwd_stream_kernel (profiles/ncu_final_kernels_r1.txt)
+        traffic = 83130624 + 2630656 if args.workload == "greedy" and (B, T, L, V) == SHAPES["msrvtt"] and es == 2 else None
+        extra = {"traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes read+write)",
+                 "algorithmic_bytes_per_launch": alg, "peak_source": pk["src"] + " (hbm_gbs)",
                  "note": "keys are L2 resident across steps, so achieved can exceed DRAM traffic"}
     if arm:
         lib.mvc_prof_arm(kid, m, n, k)
