@@ -370,7 +370,8 @@ def test_attention_kernels_vs_oracle(dev, B, T, A, F, bf16):
         close(dk, k_.grad, atol=1e-5, rtol=1e-3)
 
 
-@pytest.mark.parametrize("NB,nq,T,A,F", [(16, 5, 30, 256, 2176), (3, 8, 7, 32, 64), (20, 11, 24, 256, 512)])
+@pytest.mark.parametrize("NB,nq,T,A,F", [(16, 5, 30, 256, 2176), (3, 8, 7, 32, 64), (20, 11, 24, 256, 512),
+                                         (6, 5, 44, 256, 2176)])   # last: row too large for one CTA -> cluster of 2
 def test_attention_multi_query_shared_keys(dev, NB, nq, T, A, F):
     """Beam-search layout: query row q*NB + b attends over key block b (keys_batch = NB).  bf16 keys + fast math take
     the multi-query kernel (up to 8 queries per pass, so nq = 11 needs two passes); checked against the closed form
