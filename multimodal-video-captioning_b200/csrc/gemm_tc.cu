@@ -24,13 +24,25 @@
 // its own shared memory (the idle operand ring); after a cluster barrier CTA z reads rows
 // [z*128/S, (z+1)*128/S) of all S partials through distributed shared memory, sums them in rank
 // order (deterministic) and runs the epilogue for that row block -- no global scratch, no atomics.
+// The reduction is warp-per-row: BN/4 lanes x float4 read one parked row of one partial per
+// request (conflict-free, contiguous), and the result is stored as contiguous row segments
+// (DSMEM moves ~17 B/clk/SM: a thread-per-row mapping with 4-way bank conflicts took 8.4 us
+// per tile, this one 3 us).  Tile width and S come from a small cost model (tc_gemm()).
 //
 // Epilogues:
 //   plain : + bias, + beta*C, fp32 store, optional bf16 copy;
 //   cell  : BN = 128 and the weight rows are permuted so that one tile holds gates i,f,g,o of 32
-//           hidden units (col = (j/16)*64 + gate*16 + j%16): the epilogue adds the hoisted input
-//           projection / embedding-table row / bias, applies sigmoid/tanh, updates c and h and
-//           writes h in fp32 and bf16 -- the LSTM step never materialises pre-activations.
+//           hidden units (col = (j/16)*64 + gate*16 + j%16).  The tile is parked UNIT-major (the
+//           four gates of a unit adjacent) whether K is split or not, and finished by a looped
+//           warp-per-row pass with lane <-> hidden unit (cell_reduce_rows): hoisted input
+//           projection / embedding-table row / bias / c_prev loads in flight together with the
+//           DSMEM loads, ex2-based sigmoid / tanh, c and h (fp32 + bf16) stored as 128-byte row
+//           segments -- the LSTM step never materialises pre-activations.  Multi-wave launches
+//           (beam search) use a 3-stage ring so that two CTAs are resident per SM.
+//
+// The persistent 128x256 kernel further down serves the large GEMMs, with arg-max / top-k +
+// log-sum-exp epilogues for the vocabulary projection of the decode loops (optionally carrying the
+// next step's attention query projection as an auxiliary column block, TcAux).
 //
 // Programmatic dependent launch: when launched with the PDL attribute the producer prefetches
 // the loop-invariant operand B (weights) before griddepcontrol.wait, so the weight traffic of
@@ -153,88 +165,11 @@ __device__ __forceinline__ void plain_store(const TcEpilogue& ep, int64_t gm, in
   }
 }
 
-// fused LSTM cell for NU hidden units [tile*32 + u0, +NU) of row gm, in two halves so that the split-K path can
-// fetch everything that does not depend on the accumulator while the MMAs are still running:
-//   cell_addends: g[gate][j] (+)= hoisted input projection + gathered embedding-table row + bias; cp[j] = c_prev
-//   cell_finish : activations (ex2-based), c / h update and all stores; g must hold the complete pre-activations
-template <int NU, bool ACCUM, typename Arr>
-__device__ __forceinline__ void cell_addends(const TcEpilogue& ep, int64_t gm, int tile, int u0, Arr& g, float* cp) {
-  const int H = ep.H;
-  const int n0 = tile * 128, ug = tile * 32 + u0;
-  const float* gxr = ep.gx ? ep.gx + gm * ep.gx_ld + n0 : nullptr;
-  const float* etr = ep.embtab ? ep.embtab + ep.tokens[gm] * (int64_t)(4 * H) + n0 : nullptr;
-  const float* br = ep.bias ? ep.bias + n0 : nullptr;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-#pragma unroll
-    for (int j = 0; j < NU; j += 4) {
-      const int lc = gate_lcol(c, u0 + j);          // 4 consecutive units stay inside one 16-unit block
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gxr) { const float4 t = *reinterpret_cast<const float4*>(gxr + lc); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-      if (etr) { const float4 t = *reinterpret_cast<const float4*>(etr + lc); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-      if (br) { const float4 t = *reinterpret_cast<const float4*>(br + lc); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
-      if constexpr (ACCUM) { g[c][j] += a.x; g[c][j + 1] += a.y; g[c][j + 2] += a.z; g[c][j + 3] += a.w; }
-      else { g[c][j] = a.x; g[c][j + 1] = a.y; g[c][j + 2] = a.z; g[c][j + 3] = a.w; }
-    }
-  }
-  const float* cpp = ep.c_prev ? ep.c_prev + gm * H + ug : nullptr;
-#pragma unroll
-  for (int j = 0; j < NU; j += 4) {
-    const float4 c4 = cpp ? *reinterpret_cast<const float4*>(cpp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
-  }
-}
-
-template <int NU, typename Arr>
-__device__ __forceinline__ void cell_finish(const TcEpilogue& ep, int64_t gm, int tile, int u0, Arr& g, const float* cpv) {
-  const int H = ep.H;
-  const int n0 = tile * 128, ug = tile * 32 + u0;
-  float* co = ep.c_out + gm * H + ug;
-  float* actr = ep.act ? ep.act + gm * (int64_t)(4 * H) + n0 : nullptr;
-  float* h1 = ep.h32 ? ep.h32 + gm * ep.h_ld + ug : nullptr;
-  float* h2 = ep.h32b ? ep.h32b + gm * ep.h2_ld + ug : nullptr;
-  __nv_bfloat16* hb = ep.hb ? ep.hb + gm * ep.hb_ld + ug : nullptr;
-#pragma unroll
-  for (int j = 0; j < NU; j += 4) {
-    float cn[4], hn[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float ig = sigmoid_ex2(g[0][j + e]), fg = sigmoid_ex2(g[1][j + e]);
-      const float gg = tanh_ex2(g[2][j + e]), og = sigmoid_ex2(g[3][j + e]);
-      g[0][j + e] = ig; g[1][j + e] = fg; g[2][j + e] = gg; g[3][j + e] = og;
-      cn[e] = fg * cpv[j + e] + ig * gg;
-      hn[e] = og * tanh_ex2(cn[e]);
-    }
-    *reinterpret_cast<float4*>(co + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-    if (h1) *reinterpret_cast<float4*>(h1 + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-    if (h2) *reinterpret_cast<float4*>(h2 + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-    if (hb) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(hn[0], hn[1]), p1 = __floats2bfloat162_rn(hn[2], hn[3]);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&p0);
-      pk.y = *reinterpret_cast<uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(hb + j) = pk;
-    }
-  }
-  if (actr) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int j = 0; j < NU; j += 4)
-        *reinterpret_cast<float4*>(actr + gate_lcol(c, u0 + j)) = make_float4(g[c][j], g[c][j + 1], g[c][j + 2], g[c][j + 3]);
-  }
-}
-
-template <int NU, typename Arr>
-__device__ __forceinline__ void cell_store(const TcEpilogue& ep, int64_t gm, int tile, int u0, Arr& g) {
-  float cp[NU];
-  cell_addends<NU, true>(ep, gm, tile, u0, g, cp);
-  cell_finish<NU>(ep, gm, tile, u0, g, cp);
-}
-
-// ---- split-K cell epilogue: warp e of the 4 epilogue warps finishes rows z*R + e, e + 4, ... (R = 128 / S) of the
-// tile, lane <-> hidden unit, so a warp touches 32 consecutive units of one row (c / h: one 128-byte segment; packed
-// gate columns: two 64-byte segments per gate).
+// ---- fused LSTM cell epilogue (TC_MODE_CELL): the accumulator tile is parked UNIT-major in shared memory and finished
+// by a warp-per-row pass (cell_reduce_rows below), split-K or not.
+// Warp e of the 4 epilogue warps finishes rows z*R + e, e + 4, ... (R = 128 / S) of the tile, lane <-> hidden unit, so
+// a warp touches 32 consecutive units of one row (c / h: one 128-byte segment; packed gate columns: two 64-byte
+// segments per gate).
 __device__ __forceinline__ void cell_finish_unit(const TcEpilogue& ep, int64_t gm, int tile, int u, const float (&g)[4], float cp) {
   const int H = ep.H;
   const int ug = tile * 32 + u;
