@@ -218,6 +218,9 @@ def main():
     ap.add_argument("--workload", default="train", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-format", default="fp32", choices=["fp32", "bf16"],
+                    help="feature buffers handed to the model: fp32 as the reference's loader produces them (default), or "
+                         "pre-packed bf16 shards (SURVEY 8f-2; bf16 precision, workloads without reconstructor)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     shape = SHAPES[w["shape"]]
@@ -257,6 +260,10 @@ def main():
     model = build_model(args.workload, dev, args.precision)
     training = args.workload in ("train", "recnet_global", "recnet_local")
     host = make_batches(shape, N_ROT, seed0=1 + 100 * rank)
+    if args.host_format == "bf16":
+        if args.precision != "bf16" or w["rec"] != "none":
+            sys.exit("--host-format bf16 needs --precision bf16 and a workload without reconstructor")
+        host = [(a.bfloat16(), v.bfloat16(), c) for a, v, c in host]
     pinned = [tuple(t.pin_memory() for t in b) for b in host]
     resident = [tuple(t.to(dev) for t in b) for b in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
@@ -403,7 +410,7 @@ def main():
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world, "T": T, "L": L, "V": V,
                        "parallelism": f"dp{world}" if training else f"batch-sharded x{world} (no comm)",
-                       "master_weights": "fp32", "l2": f"rotating {N_ROT} distinct input batches "
+                       "master_weights": "fp32", "host_format": args.host_format, "l2": f"rotating {N_ROT} distinct input batches "
                        f"({N_ROT * h2d_bytes / 1e6:.0f} MB > 126 MB L2) + weights/activations rewritten every step"},
             "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,

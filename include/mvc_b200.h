@@ -92,6 +92,18 @@ int mvc_gemm_bf16_ex(int M, int N, int K, const void* A, int64_t lda, int a_tran
  * source may be NULL with width 0.  captioning.py:109 (torch.cat, audio first). */
 int mvc_concat_cast(const float* a, int Fa, const float* v, int Fv, int64_t rows, void* dst,
                     int dst_bf16, void* stream);
+
+/* Feature input format (get_loader.py:242-268 hands fp32 .npy features): MVC_INPUT_BF16 declares that the
+ * `audio` / `visual` buffers passed to the following mvc_decoder_forward / _greedy / _beam calls OF THIS HOST THREAD
+ * hold bf16 values (pre-packed shards: half the host-to-device bytes, no cast pass); the decoder must then run with
+ * precision MVC_BF16.  Rounding fp32 features to bf16 on the host (round-to-nearest-even) and passing them this way
+ * is bit-identical to passing the fp32 features.  Default MVC_INPUT_F32. */
+#define MVC_INPUT_F32 0
+#define MVC_INPUT_BF16 1
+int mvc_set_input_format(int fmt);
+int mvc_get_input_format(void);
+/* dst[r, :] = concat(a[r, :Fa], v[r, :Fv]), all bf16 (Fa, Fv multiples of 8; 16-byte aligned buffers). */
+int mvc_concat_bf16(const void* a, int Fa, const void* v, int Fv, int64_t rows, void* dst, void* stream);
 int mvc_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* dst[c, r] = bf16(src[r, c]); src [R,C] ld=lds fp32 (src_bf16=0) or bf16, dst [C,R] ld=ldd bf16. */
 int mvc_transpose_to_bf16(const void* src, int src_bf16, int64_t R, int64_t C, int64_t lds, void* dst,

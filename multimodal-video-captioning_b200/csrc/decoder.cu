@@ -238,7 +238,13 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
     if (need_embtab) MVC_TRY(launch_cast_pad_bf16(p->embedding, V, E, E, Ep, w.embb, 0, ss));
   }
   MVC_CUDA(cudaEventRecord(side->join, ss));
-  MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, bf, st));
+  if (mvc_get_input_format() == MVC_INPUT_BF16) {
+    // pre-packed bf16 feature shards: half the H2D bytes upstream, no cast pass here
+    MVC_CHECK(bf, "decoder: bf16 input features need precision = MVC_BF16");
+    MVC_TRY(mvc_concat_bf16(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, st));
+  } else {
+    MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, bf, st));
+  }
   if (bf) MVC_TRY(mvc_cast_bf16(p->att_U, w.U, (int64_t)A * F, st));
   // uk = feats . U^T      (temporal_attention.py:21, hoisted)
   MVC_TRY(gemm_nt(d->precision, B * T, A, F, w.feats, F, bf ? w.U : (const void*)p->att_U, F, 0.f, w.uk, A, nullptr, st));

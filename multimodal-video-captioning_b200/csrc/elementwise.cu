@@ -70,6 +70,19 @@ __global__ void concat_cast_bf16x8_kernel(const float* __restrict__ a, int Fa, c
   }
 }
 
+// bf16 feature shards: both inputs already bf16 -> 16-byte copies into the concatenated layout
+__global__ void concat_bf16x8_kernel(const __nv_bfloat16* __restrict__ a, int Fa, const __nv_bfloat16* __restrict__ v,
+                                     int Fv, int64_t rows, __nv_bfloat16* __restrict__ dst) {
+  const int F8 = (Fa + Fv) / 8, Fa8 = Fa / 8;
+  const int64_t total = rows * F8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F8;
+    const int g = (int)(i - r * F8);
+    const uint4* src = reinterpret_cast<const uint4*>(g < Fa8 ? a + r * Fa + g * 8 : v + r * Fv + (g - Fa8) * 8);
+    reinterpret_cast<uint4*>(dst)[i] = __ldcs(src);
+  }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16(src[i]);
@@ -452,6 +465,28 @@ extern "C" int mvc_concat_cast(const float* a, int Fa, const float* v, int Fv, i
     concat_cast_bf16x8_kernel<<<grid_for(n / 8), 256, 0, st>>>(a, Fa, v, Fv, rows, (__nv_bfloat16*)dst);
   else if (dst_bf16) concat_cast_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(a, Fa, v, Fv, rows, (__nv_bfloat16*)dst);
   else concat_cast_kernel<float><<<grid_for(n), 256, 0, st>>>(a, Fa, v, Fv, rows, (float*)dst);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+static thread_local int g_input_format = MVC_INPUT_F32;
+
+extern "C" int mvc_set_input_format(int fmt) {
+  MVC_CHECK(fmt == MVC_INPUT_F32 || fmt == MVC_INPUT_BF16, "mvc_set_input_format: unknown format %d", fmt);
+  g_input_format = fmt;
+  return 0;
+}
+extern "C" int mvc_get_input_format(void) { return g_input_format; }
+
+extern "C" int mvc_concat_bf16(const void* a, int Fa, const void* v, int Fv, int64_t rows, void* dst, void* stream) {
+  MVC_CHECK((Fa == 0 || a) && (Fv == 0 || v) && dst && Fa + Fv > 0, "mvc_concat_bf16: bad arguments");
+  MVC_CHECK(Fa % 8 == 0 && Fv % 8 == 0, "mvc_concat_bf16: feature widths must be multiples of 8 (Fa=%d Fv=%d)", Fa, Fv);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+  MVC_CHECK(al16, "mvc_concat_bf16: buffers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  concat_bf16x8_kernel<<<grid_for(rows * (Fa + Fv) / 8), 256, 0, st>>>((const __nv_bfloat16*)a, Fa, (const __nv_bfloat16*)v, Fv,
+                                                                       rows, (__nv_bfloat16*)dst);
   MVC_LAUNCH_CHECK();
   return 0;
 }

@@ -16,6 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmvc_b200.so")
 
 F32, BF16 = 0, 1
+MVC_F32, MVC_BF16 = F32, BF16
+MVC_INPUT_F32, MVC_INPUT_BF16 = 0, 1      # mvc_set_input_format (include/mvc_b200.h)
 PRECISIONS = {"fp32": F32, "f32": F32, "float32": F32, "bf16": BF16, "bfloat16": BF16}
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
@@ -69,6 +71,9 @@ SIGNATURES = {
     "mvc_gemm_bf16": (i32, [i32, i32, i32, vp, i64, vp, i64, f32, vp, i64, vp, vp, i64, vp]),
     "mvc_gemm_bf16_ex": (i32, [i32, i32, i32, vp, i64, i32, vp, i64, i32, f32, vp, i64, vp, vp]),
     "mvc_concat_cast": (i32, [vp, i32, vp, i32, i64, vp, i32, vp]),
+    "mvc_set_input_format": (i32, [i32]),
+    "mvc_get_input_format": (i32, []),
+    "mvc_concat_bf16": (i32, [vp, i32, vp, i32, i64, vp, vp]),
     "mvc_cast_bf16": (i32, [vp, vp, i64, vp]),
     "mvc_transpose_to_bf16": (i32, [vp, i32, i64, i64, i64, vp, i64, vp]),
     "mvc_soft_attention_fwd": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i64, i64, vp, i64, i64, vp, i64,

@@ -48,6 +48,38 @@ def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
     return t.contiguous()
 
 
+def _feats(audio, visual, prec):
+    """Decoder feature inputs: fp32 as the reference's loader hands them (get_loader.py:242-268), or -- bf16 compute
+    path only -- bf16 tensors (pre-packed feature shards), passed to the library uncast.
+    Returns (audio, visual, input_format)."""
+    given = [t for t in (audio, visual) if t is not None]
+    if given and prec == cabi.MVC_BF16 and all(t.dtype == torch.bfloat16 for t in given):
+        for t in given:
+            if not t.is_cuda:
+                raise RuntimeError(f"mvc_b200: features live on {t.device}; this path runs on CUDA only (no CPU fallback)")
+            if t.shape[-1] % 8:
+                raise ValueError("bf16 feature shards need feature widths that are multiples of 8")
+        return (None if audio is None else audio.contiguous(), None if visual is None else visual.contiguous(),
+                cabi.MVC_INPUT_BF16)
+    return _f32c(audio, "audio"), _f32c(visual, "visual"), cabi.MVC_INPUT_F32
+
+
+class _input_format:
+    """Declares the feature format for the library calls inside the block (thread-local in the library)."""
+
+    def __init__(self, fmt):
+        self.fmt = fmt
+
+    def __enter__(self):
+        if self.fmt != cabi.MVC_INPUT_F32:
+            cabi.check(cabi.lib().mvc_set_input_format(self.fmt), "mvc_set_input_format")
+
+    def __exit__(self, *exc):
+        if self.fmt != cabi.MVC_INPUT_F32:
+            cabi.lib().mvc_set_input_format(cabi.MVC_INPUT_F32)
+        return False
+
+
 def _dec_structs(dims, params: Sequence[torch.Tensor]):
     d = cabi.DecoderDims(*dims)
     p = cabi.DecoderParams(*[C.c_void_p(t.data_ptr()) for t in params])
@@ -75,7 +107,7 @@ class DecoderFn(torch.autograd.Function):
         lib = cabi.lib()
         B, T, F, H, E, A, V, L, prec = dims
         params = [_f32c(p.detach(), "parameter") for p in params]
-        audio, visual = _f32c(audio, "audio"), _f32c(visual, "visual")
+        audio, visual, fmt = _feats(audio, visual, prec)
         dev = params[0].device
         Fa = 0 if audio is None else audio.shape[-1]
         Fv = 0 if visual is None else visual.shape[-1]
@@ -88,9 +120,10 @@ class DecoderFn(torch.autograd.Function):
         nbytes = lib.mvc_decoder_fwd_workspace_bytes(C.byref(d), 1)
         ws = cabi.workspace(nbytes, dev)
         fl = (C.c_uint8 * max(L - 1, 1))(*[1 if f else 0 for f in flags])
-        cabi.check(lib.mvc_decoder_forward(C.byref(d), C.byref(p), cabi.ptr(audio), Fa, cabi.ptr(visual), Fv,
-                                           cabi.ptr(captions), fl, cabi.ptr(out), cabi.ptr(hid), cabi.ptr(tokens),
-                                           cabi.ptr(ws), nbytes, 1, cabi.stream_ptr()), "mvc_decoder_forward")
+        with _input_format(fmt):
+            cabi.check(lib.mvc_decoder_forward(C.byref(d), C.byref(p), cabi.ptr(audio), Fa, cabi.ptr(visual), Fv,
+                                               cabi.ptr(captions), fl, cabi.ptr(out), cabi.ptr(hid), cabi.ptr(tokens),
+                                               cabi.ptr(ws), nbytes, 1, cabi.stream_ptr()), "mvc_decoder_forward")
         ctx.dims = dims
         ctx.save_for_backward(out, tokens, ws, *params)
         return out, hid.unsqueeze(1)
@@ -118,15 +151,16 @@ def decoder_greedy(dims, audio, visual, params) -> torch.Tensor:
     lib = cabi.lib()
     B, L = dims[0], dims[7]
     params = [_f32c(p.detach(), "parameter") for p in params]
-    audio, visual = _f32c(audio, "audio"), _f32c(visual, "visual")
+    audio, visual, fmt = _feats(audio, visual, dims[8])
     dev = params[0].device
     d, p = _dec_structs(dims, params)
     ids = torch.empty(B, L, device=dev, dtype=torch.int64)
     nbytes = lib.mvc_decoder_greedy_workspace_bytes(C.byref(d))
     ws = cabi.workspace(nbytes, dev)
-    cabi.check(lib.mvc_decoder_greedy(C.byref(d), C.byref(p), cabi.ptr(audio), 0 if audio is None else audio.shape[-1],
-                                      cabi.ptr(visual), 0 if visual is None else visual.shape[-1], cabi.ptr(ids),
-                                      cabi.ptr(ws), nbytes, cabi.stream_ptr()), "mvc_decoder_greedy")
+    with _input_format(fmt):
+        cabi.check(lib.mvc_decoder_greedy(C.byref(d), C.byref(p), cabi.ptr(audio), 0 if audio is None else audio.shape[-1],
+                                          cabi.ptr(visual), 0 if visual is None else visual.shape[-1], cabi.ptr(ids),
+                                          cabi.ptr(ws), nbytes, cabi.stream_ptr()), "mvc_decoder_greedy")
     return ids
 
 
@@ -135,15 +169,17 @@ def decoder_beam(dims, audio, visual, params, width: int, alpha: float) -> torch
     lib = cabi.lib()
     B, L = dims[0], dims[7]
     params = [_f32c(p.detach(), "parameter") for p in params]
-    audio, visual = _f32c(audio, "audio"), _f32c(visual, "visual")
+    audio, visual, fmt = _feats(audio, visual, dims[8])
     dev = params[0].device
     d, p = _dec_structs(dims, params)
     ids = torch.empty(B, L + 2, device=dev, dtype=torch.int64)
     nbytes = lib.mvc_decoder_beam_workspace_bytes(C.byref(d), int(width))
     ws = cabi.workspace(nbytes, dev)
-    cabi.check(lib.mvc_decoder_beam(C.byref(d), C.byref(p), cabi.ptr(audio), 0 if audio is None else audio.shape[-1],
-                                    cabi.ptr(visual), 0 if visual is None else visual.shape[-1], int(width), float(alpha),
-                                    cabi.ptr(ids), cabi.ptr(ws), nbytes, cabi.stream_ptr()), "mvc_decoder_beam")
+    with _input_format(fmt):
+        cabi.check(lib.mvc_decoder_beam(C.byref(d), C.byref(p), cabi.ptr(audio), 0 if audio is None else audio.shape[-1],
+                                        cabi.ptr(visual), 0 if visual is None else visual.shape[-1], int(width),
+                                        float(alpha), cabi.ptr(ids), cabi.ptr(ws), nbytes, cabi.stream_ptr()),
+                   "mvc_decoder_beam")
     return ids
 
 

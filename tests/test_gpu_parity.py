@@ -779,6 +779,34 @@ def test_greedy_bf16_fused_argmax_matches_decode(dev):
     assert (ids[:, 0] == 0).all()
 
 
+def test_bf16_feature_shards_are_bit_identical(dev):
+    """features rounded to bf16 on the host and passed as bf16 tensors (half the H2D bytes, no cast pass)
+    must give exactly the results of passing the fp32 features to the bf16 path: teacher-forced log-probs, greedy ids
+    and beam ids."""
+    from models import AVCaptioning
+    B, T, V, L = 96, 30, 3201, 16
+    torch.manual_seed(5)
+    model = AVCaptioning(Vocab(V), 0.0, "none", device=dev, precision="bf16").to(dev)
+    audio, visual, caps = (t.to(dev) for t in O.synth_batch(B, T, L, V, seed=21, min_frames=6))
+    ab, vb = audio.bfloat16(), visual.bfloat16()
+    with torch.no_grad():
+        out32, _, _ = model(audio, visual, caps, teacher_forcing_ratio=1.0)
+        outbf, _, _ = model(ab, vb, caps, teacher_forcing_ratio=1.0)
+        assert torch.equal(out32, outbf)
+        assert model.predict_ids(audio, visual, L) == model.predict_ids(ab, vb, L)
+        assert model.predict_ids(audio, visual, L, mode="beam") == model.predict_ids(ab, vb, L, mode="beam")
+    # gradients flow through the shard path too
+    model.zero_grad()
+    out, _, _ = model(ab, vb, caps, teacher_forcing_ratio=1.0)
+    out[1:].mean().backward()
+    assert model.decoder.out.weight.grad is not None and torch.isfinite(model.decoder.out.weight.grad).all()
+    # the fp32 exact path accepts them too: bf16 tensors are widened to fp32 (values unchanged)
+    m32 = AVCaptioning(Vocab(V), 0.0, "none", device=dev).to(dev)
+    with torch.no_grad():
+        o = m32(ab, vb, caps, teacher_forcing_ratio=1.0)[0]
+    assert o.shape == out32.shape
+
+
 def test_greedy_ids_fp32_vs_oracle_full_width(dev):
     """Exact greedy-caption agreement with the fp32 reference arithmetic at full width (peaky logits)."""
     from models import AVCaptioning
