@@ -180,12 +180,28 @@ def cpu_arm(workload, steps, warmup):
     w = WORKLOADS[workload]
     shape = SHAPES[w["shape"]]
     threads = os.cpu_count() or 1
-    if workload in ("greedy", "beam"):
-        sample_B = 64 if workload == "greedy" else 16
-        fn = cpu_decode_step_fn(shape, sample_B, threads, workload == "beam")
-    else:
-        sample_B = shape[0] if steps + warmup <= 12 else 32
-        fn = cpu_train_step_fn(shape, w["rec"], sample_B, threads)
+
+    def make(sample_B):
+        if workload in ("greedy", "beam"):
+            return cpu_decode_step_fn(shape, sample_B, threads, workload == "beam")
+        return cpu_train_step_fn(shape, w["rec"], sample_B, threads)
+
+    # Bounded sample: the largest batch (up to the workload's own) whose steps + warm-up fit ~2 minutes of CPU time,
+    # estimated from one probe step at a small batch (larger batches are kinder to the CPU arm: better GEMM shapes).
+    sample_B = {"greedy": 64, "beam": 16}.get(workload, 32)
+    fn = make(sample_B)
+    fn()                                          # thread-pool / allocator warm-up
+    t0 = time.perf_counter()
+    fn()
+    per_sample = (time.perf_counter() - t0) / sample_B
+    budget_s = 120.0
+    best = sample_B
+    for cand in (64, 128, 256, 512):
+        if sample_B < cand <= shape[0] and per_sample * cand * (steps + warmup) <= budget_s:
+            best = cand
+    if best != sample_B:
+        sample_B = best
+        fn = make(sample_B)
     for _ in range(warmup):
         fn()
     t0 = time.perf_counter()
