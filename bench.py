@@ -48,6 +48,8 @@ WORKLOADS = {
                           desc="C5: AVCaptioning + global reconstructor train step, MSVD-shaped B=128/GPU"),
     "recnet_local": dict(shape="msvd", rec="local", metric="train_samples_per_sec", unit="samples/s",
                          desc="C5: AVCaptioning + local reconstructor train step, MSVD-shaped B=128/GPU"),
+    "train_dual": dict(shape="msvd", rec="none", dual=True, metric="train_samples_per_sec", unit="samples/s",
+                       desc="C5: AVCaptioningDual (visual + audio decoders, late fusion) train step, MSVD-shaped B=128/GPU"),
     "greedy": dict(shape="msrvtt", rec="none", metric="greedy_captions_per_sec", unit="captions/s",
                    desc="C3: AVCaptioning.predict(mode='direct') ids, MSR-VTT-shaped B=512/GPU T=30 L=30 V=10547"),
     "beam": dict(shape="msrvtt", rec="none", metric="beam5_captions_per_sec", unit="captions/s",
@@ -135,28 +137,33 @@ def make_batches(shape, n, seed0=1):
 
 
 # --------------------------------------------------------------------------- reference / CPU arm
-def cpu_train_step_fn(shape, rec, sample_B, threads):
+def cpu_train_step_fn(shape, rec, sample_B, threads, dual=False):
     """The reference's arithmetic for one train step on the CPU: oracle restatement with the same ATen LSTM
     call and the per-step U.feats recompute the reference does (hoist=False), torch.optim.Adam(amsgrad)."""
     from oracle import salstm_oracle as O
     torch.set_num_threads(threads)
     B, T, L, V = shape
     gen = torch.Generator().manual_seed(0)
-    p = O.init_decoder_params("decoder.", 2176, V, gen=gen)
-    if rec != "none":
-        p.update(O.init_recon_params("reconstructor.", rec, 512, 2176, gen=gen))
+    if dual:
+        p = O.init_decoder_params("v_decoder.", 2048, V, gen=gen)
+        p.update(O.init_decoder_params("a_decoder.", 128, V, gen=gen))
+    else:
+        p = O.init_decoder_params("decoder.", 2176, V, gen=gen)
+        if rec != "none":
+            p.update(O.init_recon_params("reconstructor.", rec, 512, 2176, gen=gen))
     p = {k: v.requires_grad_() for k, v in p.items()}
+    fwd = O.av_dual_forward if dual else O.av_forward
     opt = torch.optim.Adam(list(p.values()), lr=1e-4, weight_decay=1e-5, amsgrad=True)
     audio, visual, caps = O.synth_batch(sample_B, T, L, V, seed=1)
 
     def step():
         opt.zero_grad()
-        out, ar, vr = O.av_forward(p, audio, visual, caps, 1.0, rec, hoist=False, aten_lstm=True)
+        out, ar, vr = fwd(p, audio, visual, caps, 1.0, rec, hoist=False, aten_lstm=True)
         terms = O.modality_wise_loss(out, caps, audio, ar, visual, vr, rec_type=rec, **LAMBDAS)
         terms[0].mean().backward()
         torch.nn.utils.clip_grad_value_(list(p.values()), 5.0)
         opt.step()
-        return float(terms[0])
+        return float(terms[0].detach())
     return step
 
 
@@ -184,7 +191,7 @@ def cpu_arm(workload, steps, warmup):
     def make(sample_B):
         if workload in ("greedy", "beam"):
             return cpu_decode_step_fn(shape, sample_B, threads, workload == "beam")
-        return cpu_train_step_fn(shape, w["rec"], sample_B, threads)
+        return cpu_train_step_fn(shape, w["rec"], sample_B, threads, dual=bool(w.get("dual")))
 
     # Bounded sample: the largest batch (up to the workload's own) whose steps + warm-up fit ~2 minutes of CPU time,
     # estimated from one probe step at a small batch (larger batches are kinder to the CPU arm: better GEMM shapes).
@@ -216,12 +223,13 @@ def cpu_arm(workload, steps, warmup):
 
 # --------------------------------------------------------------------------- B200 arm
 def build_model(workload, dev, precision):
-    from models import AVCaptioning
+    from models import AVCaptioning, AVCaptioningDual
     w = WORKLOADS[workload]
     B, T, L, V = SHAPES[w["shape"]]
     torch.manual_seed(0)
-    model = AVCaptioning(Vocab(V), teacher_forcing_ratio=1.0, reconstructor_type=w["rec"], device=dev,
-                         precision=precision).to(dev)
+    cls = AVCaptioningDual if w.get("dual") else AVCaptioning
+    model = cls(Vocab(V), teacher_forcing_ratio=1.0, reconstructor_type=w["rec"], device=dev,
+                precision=precision).to(dev)
     return model
 
 
@@ -274,7 +282,7 @@ def main():
     lib = cabi.lib()
 
     model = build_model(args.workload, dev, args.precision)
-    training = args.workload in ("train", "recnet_global", "recnet_local")
+    training = args.workload in ("train", "train_dual", "recnet_global", "recnet_local")
     host = make_batches(shape, N_ROT, seed0=1 + 100 * rank)
     if args.host_format == "bf16":
         if args.precision != "bf16" or w["rec"] != "none":
@@ -444,13 +452,15 @@ def roofline_pass(lib, args, step, resident, shape, pk, arm=True):
     F, H, A, E = 2176, 512, 256, 300
     S = L - 1
     es = 2 if args.precision == "bf16" else 4
-    training = args.workload in ("train", "recnet_global", "recnet_local")
+    training = args.workload in ("train", "train_dual", "recnet_global", "recnet_local")
     if training and args.precision == "bf16":
         # dominant kernel: the persistent forward recurrence (recur_fwd.cu), ONE launch for all S steps.
         # Algorithmic flops per launch (SURVEY 8d per-step figures x B x S): gate GEMM 2*B*4H*(F+H) + query
         # projection 2*B*A*H + scores 2*B*T*A + context sum 2*B*T*F, per step.
         kid, m, n, k = 8, B, S, -1
-        per_step = 2 * B * 4 * H * (F + H) + 2 * B * A * H + 2 * B * T * A + 2 * B * T * F
+        per_f = lambda f: 2 * B * 4 * H * (f + H) + 2 * B * A * H + 2 * B * T * A + 2 * B * T * f
+        # the dual model launches the kernel once per decoder (F = 2048 and F = 128): mean work per launch
+        per_step = (per_f(2048) + per_f(128)) / 2 if WORKLOADS[args.workload].get("dual") else per_f(F)
         alg = per_step * S
         bound, peak, unit, scale = "tensor", pk["tensor"], "TFLOP/s", 1e12
         name = (f"recur_fwd_kernel (persistent SA-LSTM recurrence, {S} steps/launch: attention + tcgen05 gate GEMM "
