@@ -131,9 +131,9 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- synthetic data
 def make_batches(shape, n, seed0=1):
-    from oracle import salstm_oracle as O     # synthetic-input generator only
+    from salstm.synth import synth_batch      # product-side generator; nothing from oracle/ on this arm
     B, T, L, V = shape
-    return [O.synth_batch(B, T, L, V, seed=seed0 + i) for i in range(n)]
+    return [synth_batch(B, T, L, V, seed=seed0 + i) for i in range(n)]
 
 
 # --------------------------------------------------------------------------- reference / CPU arm
@@ -183,12 +183,55 @@ def cpu_decode_step_fn(shape, sample_B, threads, beam):
     return step
 
 
-def cpu_arm(workload, steps, warmup):
+def ref_step_fn(workload, shape, sample_B, threads):
+    """One step of the UNMODIFIED reference (oracle/_ref: byte copies of src/models/*.py + src/losses.py staged by
+    oracle/build_ref.py) on the host CPU: for training the body of Trainer.train's loop (train.py:186-210), for
+    decoding AVCaptioning.predict (captioning.py:131-144)."""
+    import contextlib
+    from oracle import build_ref
+    from oracle import salstm_oracle as O
+    ref = build_ref.load()
+    w = WORKLOADS[workload]
+    torch.set_num_threads(threads)
+    B, T, L, V = shape
+    torch.manual_seed(0)
+    cls = ref.AVCaptioningDual if w.get("dual") else ref.AVCaptioning
+    with contextlib.redirect_stdout(sys.stderr):                 # the reference prints its configuration
+        model = cls(Vocab(V), teacher_forcing_ratio=1.0, reconstructor_type=w["rec"], device="cpu")
+    audio, visual, caps = O.synth_batch(sample_B, T, L, V, seed=1)
+    if workload in ("greedy", "beam"):
+        model.eval()
+        mode = "beam" if workload == "beam" else "direct"
+
+        def step():
+            with torch.no_grad():
+                return model.predict(audio, visual, max_caption_len=L, mode=mode, beam_alpha=0, beam_width=5)
+        return step
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-5, amsgrad=True)      # train.py:86-88
+    loss_fn = ref.losses.ModalityWiseReconstructionLossBuilder(rec_type=w["rec"], **LAMBDAS)   # train.py:103-108
+
+    def step():
+        opt.zero_grad()
+        out, ar, vr = model(audio, visual, caps)
+        loss, ce, e, a_rec, v_rec = loss_fn(out, caps, audio, ar, visual, vr)
+        loss.mean().backward()
+        torch.nn.utils.clip_grad_value_(model.parameters(), clip_value=5.0)
+        opt.step()
+        return loss.mean().item()
+    return step
+
+
+def cpu_arm(workload, steps, warmup, budget_s=120.0):
+    from oracle import build_ref
     w = WORKLOADS[workload]
     shape = SHAPES[w["shape"]]
     threads = os.cpu_count() or 1
+    staged = build_ref.available()
 
     def make(sample_B):
+        if staged:
+            return ref_step_fn(workload, shape, sample_B, threads)
         if workload in ("greedy", "beam"):
             return cpu_decode_step_fn(shape, sample_B, threads, workload == "beam")
         return cpu_train_step_fn(shape, w["rec"], sample_B, threads, dual=bool(w.get("dual")))
@@ -201,7 +244,6 @@ def cpu_arm(workload, steps, warmup):
     t0 = time.perf_counter()
     fn()
     per_sample = (time.perf_counter() - t0) / sample_B
-    budget_s = 120.0
     best = sample_B
     for cand in (64, 128, 256, 512):
         if sample_B < cand <= shape[0] and per_sample * cand * (steps + warmup) <= budget_s:
@@ -216,9 +258,13 @@ def cpu_arm(workload, steps, warmup):
         fn()
     dt = time.perf_counter() - t0
     value = sample_B * steps / dt
-    sample = (f"{steps} step(s) of batch {sample_B} (of {shape[0]}) of the same workload, oracle port "
-              f"(torch {torch.__version__} CPU ops, ATen LSTM, U.feats recomputed per step as the reference does)")
-    return value, dt * 1e3 / steps, dict(value=value, unit=w["unit"], cores=threads, kind="port", sample=sample)
+    what = ("the UNMODIFIED reference modules (oracle/_ref: src/models/*.py + src/losses.py; train.py:186-210 loop body / "
+            "AVCaptioning.predict)" if staged else
+            "oracle port (same ATen LSTM call, U.feats recomputed per step as the reference does)")
+    sample = (f"{steps} step(s) of batch {sample_B} (of {shape[0]}) of the same workload after {warmup} warm-up, {what}, "
+              f"torch {torch.__version__} CPU, {threads} threads")
+    return value, dt * 1e3 / steps, dict(value=value, unit=w["unit"], cores=threads,
+                                         kind="reference" if staged else "port", sample=sample)
 
 
 # --------------------------------------------------------------------------- B200 arm
@@ -233,60 +279,37 @@ def build_model(workload, dev, precision):
     return model
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="train", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--host-format", default="fp32", choices=["fp32", "bf16"],
-                    help="feature buffers handed to the model: fp32 as the reference's loader produces them (default), or "
-                         "pre-packed bf16 shards (SURVEY 8f-2; bf16 precision, workloads without reconstructor)")
-    args = ap.parse_args()
-    w = WORKLOADS[args.workload]
-    shape = SHAPES[w["shape"]]
-    B, T, L, V = shape
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+def config_block(workload, world, host_format):
+    """`config` of the JSON line: identical keys and values in the B200 arm and the reference arm (which times the
+    reference on THIS configuration)."""
+    w = WORKLOADS[workload]
+    B, T, L, V = SHAPES[w["shape"]]
+    training = workload in TRAINING
+    es = 2 if host_format == "bf16" else 4
+    in_bytes = B * T * 2176 * es + (B * L * 8 if training else 0)
+    return {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world, "T": T, "L": L, "V": V,
+            "parallelism": f"dp{world}" if training else f"batch-sharded x{world} (no comm)",
+            "master_weights": "fp32", "host_format": host_format,
+            "l2": f"rotating {N_ROT} distinct input batches ({N_ROT * in_bytes / 1e6:.0f} MB > 126 MB L2) + "
+                  "weights/activations rewritten every step"}
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        value, ms, cb = cpu_arm(args.workload, args.steps, max(args.warmup, 1))
-        print(json.dumps({"impl": "reference", "metric": w["metric"], "value": value, "unit": w["unit"],
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": {"workload": w["desc"], "parallelism": "host CPU threads"},
-                          "cpu_baseline": cb,
-                          "e2e": {"value": value, "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
 
-    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+TRAINING = ("train", "train_dual", "recnet_global", "recnet_local")
+
+
+def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, world, lib, sampler=None):
+    """Device-resident value, end-to-end value, roofline of the dominant kernel for one workload -> dict."""
     import torch.distributed as dist
-    if world > 1:
-        import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
-    import __graft_entry__ as G
-    if not os.path.exists(G.LIB):
-        G.build()
-    from salstm import cabi
+    from salstm import functional as Fn
     from salstm.trainer import FlatClipAdam
     import losses as Lm
-    lib = cabi.lib()
-
-    model = build_model(args.workload, dev, args.precision)
-    training = args.workload in ("train", "train_dual", "recnet_global", "recnet_local")
+    w = WORKLOADS[workload]
+    shape = SHAPES[w["shape"]]
+    B, T, L, V = shape
+    model = build_model(workload, dev, precision)
+    training = workload in TRAINING
     host = make_batches(shape, N_ROT, seed0=1 + 100 * rank)
-    if args.host_format == "bf16":
-        if args.precision != "bf16" or w["rec"] != "none":
-            sys.exit("--host-format bf16 needs --precision bf16 and a workload without reconstructor")
+    if host_format == "bf16":
         host = [(a.bfloat16(), v.bfloat16(), c) for a, v, c in host]
     pinned = [tuple(t.pin_memory() for t in b) for b in host]
     resident = [tuple(t.to(dev) for t in b) for b in host]
@@ -309,30 +332,22 @@ def main():
             opt.step()
             return terms[0]
         d2h_bytes = 4
-    elif args.workload == "greedy":
+    elif workload == "greedy":
         def step(batch):
             return model.decoder.greedy_ids((batch[0], batch[1]), L)
         d2h_bytes = B * L * 8
     else:
         def step(batch):
-            return cabi_beam(model, batch, L)
+            dec = model.decoder
+            return Fn.decoder_beam(dec._dims(batch[0].shape[0], batch[0].shape[1], L), batch[0], batch[1], dec._params(),
+                                   5, 0.0)
         d2h_bytes = B * (L + 2) * 8
-
-    def cabi_beam(model, batch, L):
-        from salstm import functional as Fn
-        dec = model.decoder
-        return Fn.decoder_beam(dec._dims(batch[0].shape[0], batch[0].shape[1], L), batch[0], batch[1], dec._params(), 5, 0.0)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # clocks are sampled (nvidia-smi, 100 ms period) from before the warm-up until after the last timed
-    # region, so the samples "under load" cover every timed loop of this process
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     # ---- device-resident timing
     for i in range(warmup):
         step(resident[i % N_ROT])
@@ -340,7 +355,7 @@ def main():
     l0 = lib.mvc_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(resident[i % N_ROT])
     e1.record()
     barrier()
@@ -350,7 +365,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    value = world * B * args.steps / (ms_total / 1e3)
+    value = world * B * steps / (ms_total / 1e3)
 
     # ---- end-to-end timing: pinned host inputs -> H2D -> step -> D2H of the result, every step.
     # Inputs of step i+1 are prefetched on a copy stream while step i computes (double buffering);
@@ -373,7 +388,7 @@ def main():
     # event; the host consumes the value of step i-1 before it issues step i+1, so it runs (at most) one step ahead
     # of the device instead of stalling the pipeline on .item() (the reference's per-step logging, train.py:201-205,
     # made asynchronous -- SURVEY 8f-1).  All copies and all reads are inside the timed region.
-    res_shape = (1,) if training else ((B, L) if args.workload == "greedy" else (B, L + 2))
+    res_shape = (1,) if training else ((B, L) if workload == "greedy" else (B, L + 2))
     res_dtype = torch.float32 if training else torch.int64
     host_res = [torch.empty(res_shape, dtype=res_dtype).pin_memory() for _ in range(2)]
     res_done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -403,7 +418,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    run_e2e(args.steps)
+    run_e2e(steps)
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -411,12 +426,83 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    e2e_value = world * B * steps / (e2e_ms / 1e3)
 
     # ---- roofline of the dominant kernel, timed in situ over K more steps
     pk = peaks()
     # every rank runs the extra steps (the train step contains the gradient all-reduce); rank 0 arms the timers
-    roof = roofline_pass(lib, args, step, resident, shape, pk, arm=(rank == 0))
+    roof = roofline_pass(lib, workload, precision, steps, step, resident, shape, pk, arm=(rank == 0))
+    cfg = config_block(workload, world, host_format)
+    return {"metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": precision, "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms / steps, "wall_ms_per_step": wall_ms / steps,
+                    "note": "pinned host inputs, double-buffered H2D on a copy stream; result of every step copied D2H "
+                            "asynchronously and consumed one step later"},
+            "gpu_launches": int(launches), "roofline": roof, "peaks": pk["src"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the greedy-decode block the default (train) line carries as `secondary`")
+    ap.add_argument("--host-format", default="fp32", choices=["fp32", "bf16"],
+                    help="feature buffers handed to the model: fp32 as the reference's loader produces them (default), or "
+                         "pre-packed bf16 shards (SURVEY 8f-2; bf16 precision, workloads without reconstructor)")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        value, ms, cb = cpu_arm(args.workload, args.steps, max(args.warmup, 1))
+        print(json.dumps({"impl": "reference", "metric": w["metric"], "value": value, "unit": w["unit"],
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": config_block(args.workload, args.gpus, args.host_format),
+                          "cpu_baseline": cb,
+                          "e2e": {"value": value, "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    import __graft_entry__ as G
+    if not os.path.exists(G.LIB):
+        G.build()
+    from salstm import cabi
+    lib = cabi.lib()
+    if args.host_format == "bf16" and (args.precision != "bf16" or w["rec"] != "none"):
+        sys.exit("--host-format bf16 needs --precision bf16 and a workload without reconstructor")
+
+    # clocks are sampled (nvidia-smi, 100 ms period) from before the warm-up until after the last timed
+    # region, so the samples "under load" cover every timed loop of this process
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    line = measure_b200(args.workload, args.precision, args.host_format, args.steps, warmup, dev, rank, world, lib)
+    secondary = None
+    if args.workload == "train" and not args.no_secondary:
+        # the second half of BASELINE.json's metric: greedy-decode captions/s (configs[2] per-GPU shape), same process
+        sec = measure_b200("greedy", args.precision, args.host_format, max(5, args.steps // 2), 3, dev, rank, world, lib)
+        secondary = {k: sec[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "config", "e2e",
+                                         "gpu_launches", "roofline")}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -426,48 +512,37 @@ def main():
 
     cb = None
     if world == 1 and not args.no_cpu_baseline:
-        cb_steps = 1 if training else 1
-        _, _, cb = cpu_arm(args.workload, cb_steps, 1)
-
-    line = {"metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world, "T": T, "L": L, "V": V,
-                       "parallelism": f"dp{world}" if training else f"batch-sharded x{world} (no comm)",
-                       "master_weights": "fp32", "host_format": args.host_format, "l2": f"rotating {N_ROT} distinct input batches "
-                       f"({N_ROT * h2d_bytes / 1e6:.0f} MB > 126 MB L2) + weights/activations rewritten every step"},
-            "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-                    "note": "pinned host inputs, double-buffered H2D on a copy stream; result of every step copied D2H "
-                            "asynchronously and consumed one step later"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "peaks": pk["src"]}
+        _, _, cb = cpu_arm(args.workload, 3 if args.workload in TRAINING else 1, 1, budget_s=30.0)
+    line.update({"clocks": clocks, "cpu_baseline": cb})
+    if secondary is not None:
+        line["secondary"] = secondary
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def roofline_pass(lib, args, step, resident, shape, pk, arm=True):
+def roofline_pass(lib, workload, precision, steps, step, resident, shape, pk, arm=True):
     """Arm in-situ event timing for the dominant kernel class and run the timed loop again."""
     B, T, L, V = shape
     F, H, A, E = 2176, 512, 256, 300
     S = L - 1
-    es = 2 if args.precision == "bf16" else 4
-    training = args.workload in ("train", "train_dual", "recnet_global", "recnet_local")
-    if training and args.precision == "bf16":
+    es = 2 if precision == "bf16" else 4
+    training = workload in TRAINING
+    if training and precision == "bf16":
         # dominant kernel: the persistent forward recurrence (recur_fwd.cu), ONE launch for all S steps.
         # Algorithmic flops per launch (SURVEY 8d per-step figures x B x S): gate GEMM 2*B*4H*(F+H) + query
         # projection 2*B*A*H + scores 2*B*T*A + context sum 2*B*T*F, per step.
         kid, m, n, k = 8, B, S, -1
         per_f = lambda f: 2 * B * 4 * H * (f + H) + 2 * B * A * H + 2 * B * T * A + 2 * B * T * f
         # the dual model launches the kernel once per decoder (F = 2048 and F = 128): mean work per launch
-        per_step = (per_f(2048) + per_f(128)) / 2 if WORKLOADS[args.workload].get("dual") else per_f(F)
+        per_step = (per_f(2048) + per_f(128)) / 2 if WORKLOADS[workload].get("dual") else per_f(F)
         alg = per_step * S
         bound, peak, unit, scale = "tensor", pk["tensor"], "TFLOP/s", 1e12
         name = (f"recur_fwd_kernel (persistent SA-LSTM recurrence, {S} steps/launch: attention + tcgen05 gate GEMM "
                 f"128x{4 * H}x{F + H} + LSTM cell), B={B}")
         # DRAM bytes per launch of this kernel (dram__bytes_read.sum + dram__bytes_write.sum, one `ncu --set full`
         # capture of this command at the C2 shape: profiles/ncu_final_kernels_r1.txt); None for other shapes
-        traffic = 66175232 + 6105088 if (B, T, L, V) == SHAPES["msvd"] and args.workload == "train" else None
+        traffic = 66175232 + 6105088 if (B, T, L, V) == SHAPES["msvd"] and workload == "train" else None
         extra = {"traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes read+write)",
                  "algorithmic_flops_per_launch": alg, "peak_source": pk["src"] + " (bf16_tflops_sustained)",
                  "note": "latency/sync-bound by construction: 2 grid barriers + one L2 round trip per phase per step "
@@ -475,19 +550,19 @@ def roofline_pass(lib, args, step, resident, shape, pk, arm=True):
     else:
         # launch-chain paths: soft-attention forward kernel, reads keys [B,T,F] + U.k [B,T,A] once per launch
         # (beam: the 5 beams of a video share ONE staged key block and U.k slab; only queries / outputs are per beam)
-        rows = B if args.workload != "beam" else 5 * B
+        rows = B if workload != "beam" else 5 * B
         kid, m, n, k = 3, rows, T, F
         alg = B * T * (F * es + A * 4) + rows * (F * es + T * 4 + A * 4)
         bound, peak, unit, scale = "hbm", pk["hbm"], "GB/s", 1e9
         name = f"attn_fwd_staged_kernel B={rows} T={T} F={F} ({'bf16' if es == 2 else 'fp32'} keys)"
         # greedy at the C3 shape: ncu capture of attn_fwd_stream_kernel (profiles/ncu_final_kernels_r1.txt)
-        traffic = 83130624 + 2630656 if args.workload == "greedy" and (B, T, L, V) == SHAPES["msrvtt"] and es == 2 else None
+        traffic = 83130624 + 2630656 if workload == "greedy" and (B, T, L, V) == SHAPES["msrvtt"] and es == 2 else None
         extra = {"traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes read+write)",
                  "algorithmic_bytes_per_launch": alg, "peak_source": pk["src"] + " (hbm_gbs)",
                  "note": "keys are L2 resident across steps, so achieved can exceed DRAM traffic"}
     if arm:
         lib.mvc_prof_arm(kid, m, n, k)
-    for i in range(args.steps):
+    for i in range(steps):
         step(resident[i % N_ROT])
     torch.cuda.synchronize()
     if not arm:

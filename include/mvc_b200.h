@@ -361,15 +361,24 @@ int mvc_caption_loss(const float* logp, const int64_t* captions, int L, int B, i
 
 /* GlobalReconstructionLoss (losses.py:20-36): x [B,T,F] slice (ld x_ld),
  * xrec [B,L,F] slice (ld r_ld), captions [L,B].  result[0] = mse.
- * dxrec ([B,L,F], row pitch d_ld, may be NULL) += scale * dloss/dxrec. */
+ * dxrec ([B,L,F], row pitch d_ld, may be NULL) = scale * dloss/dxrec (OVERWRITTEN, zeros on PAD rows). */
 int mvc_global_recon_loss(const float* x, int64_t x_ld, const float* xrec, int64_t r_ld, int B,
                           int T, int L, int F, const int64_t* captions, float* result,
                           float* dxrec, int64_t d_ld, float scale, void* workspace, void* stream);
 size_t mvc_global_recon_loss_workspace_bytes(int B, int F);
-/* LocalReconstructionLoss (losses.py:39-40): mse over [B,T,F] slices. */
+/* LocalReconstructionLoss (losses.py:39-40): mse over [B,T,F] slices; dxrec (may be NULL) is OVERWRITTEN. */
 int mvc_local_recon_loss(const float* x, int64_t x_ld, const float* xrec, int64_t r_ld,
                          int64_t rows, int F, float* result, float* dxrec, int64_t d_ld,
                          float scale, void* workspace, void* stream);
+
+/* Total of ModalityWiseReconstructionLoss (losses.py:122-124) on the device: result[0..4] = ce, entropy, n_tokens,
+ * audio_rec, visual_rec as the calls above left them (a missing reconstruction term is set to 0, :100-101);
+ * result[5] = ce + reg*entropy + a_lambda*audio_rec + v_lambda*visual_rec, summed in the reference's order. */
+int mvc_loss_combine(float* result, float reg_lambda, float a_lambda, float v_lambda, int have_a, int have_v,
+                     void* stream);
+/* x[0..n) *= *g_dev (g_dev: one fp32 on the device -- the upstream gradient of the loss scalar; exits at once when
+ * it is 1.0, as in `loss.mean().backward()`, train.py:198).  x 16-byte aligned. */
+int mvc_scale_by_scalar(float* x, int64_t n, const float* g_dev, void* stream);
 
 /* ------------------------------------------------------------------ */
 /* Trainer step tail (train.py:207-210): clip_grad_value_ + Adam(amsgrad, */

@@ -196,7 +196,7 @@ __global__ void global_recon_loss_kernel(const float* __restrict__ x, int64_t x_
     if (dxrec) {
       const float g = scale * 2.f * (xr - xm) / ((float)B * (float)F) / n;
       for (int l = 0; l < L; ++l)
-        if (cap[(int64_t)l * B + b] != MVC_PAD) dxrec[((int64_t)b * L + l) * d_ld + f] += g;
+        dxrec[((int64_t)b * L + l) * d_ld + f] = cap[(int64_t)l * B + b] != MVC_PAD ? g : 0.f;
     }
   }
   sq = block_sum(sq, red);
@@ -214,7 +214,7 @@ __global__ void local_recon_loss_kernel(const float* __restrict__ x, int64_t x_l
     const int f = (int)(i - r * F);
     const float d = xrec[r * r_ld + f] - x[r * x_ld + f];
     sq = fmaf(d, d, sq);
-    if (dxrec) dxrec[r * d_ld + f] += gscale * d;
+    if (dxrec) dxrec[r * d_ld + f] = gscale * d;
   }
   sq = block_sum(sq, red);
   if (threadIdx.x == 0) atomicAdd(acc, (double)sq);
@@ -222,6 +222,30 @@ __global__ void local_recon_loss_kernel(const float* __restrict__ x, int64_t x_l
 
 __global__ void mse_finish_kernel(const double* __restrict__ acc, double n, float* __restrict__ result) {
   result[0] = (float)(*acc / n);
+}
+
+// loss = ce + reg*entropy; loss += a_lambda*a_rec; loss += v_lambda*v_rec  (losses.py:122-124, same fp32 order)
+__global__ void loss_combine_kernel(float* __restrict__ r, float reg, float a_lambda, float v_lambda, int have_a,
+                                    int have_v) {
+  if (!have_a) r[3] = 0.f;
+  if (!have_v) r[4] = 0.f;
+  float loss = r[0] + reg * r[1];
+  loss += a_lambda * r[3];
+  loss += v_lambda * r[4];
+  r[5] = loss;
+}
+
+// x *= *g (g on the device: the upstream gradient of the loss, 1.0 in the reference's train loop -> nothing to do)
+__global__ void scale_by_scalar_kernel(float4* __restrict__ x, int64_t n4, float* __restrict__ tail, int ntail,
+                                       const float* __restrict__ g) {
+  const float s = *g;
+  if (s == 1.f) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    x[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] *= s;
 }
 
 }  // namespace mvc
@@ -286,6 +310,27 @@ extern "C" int mvc_local_recon_loss(const float* x, int64_t x_ld, const float* x
                                                        scale * 2.f / (float)n);
   MVC_LAUNCH_CHECK();
   mse_finish_kernel<<<1, 1, 0, st>>>(acc, (double)n, result);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_loss_combine(float* result, float reg_lambda, float a_lambda, float v_lambda, int have_a, int have_v,
+                                void* stream) {
+  MVC_CHECK(result, "mvc_loss_combine: null argument");
+  loss_combine_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(result, reg_lambda, a_lambda, v_lambda, have_a, have_v);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_scale_by_scalar(float* x, int64_t n, const float* g_dev, void* stream) {
+  if (n == 0) return 0;
+  MVC_CHECK(x && g_dev, "mvc_scale_by_scalar: null argument");
+  MVC_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0, "mvc_scale_by_scalar: x must be 16-byte aligned");
+  const int64_t n4 = n / 4;
+  int64_t g = cdiv(n4 > 0 ? n4 : 1, 256);
+  if (g > kNumSMs * 8) g = kNumSMs * 8;
+  scale_by_scalar_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(x), n4, x + n4 * 4,
+                                                                        (int)(n - n4 * 4), g_dev);
   MVC_LAUNCH_CHECK();
   return 0;
 }

@@ -1,7 +1,11 @@
 """Drop-in for the hot-path half of the reference's `losses` module (src/losses.py:12-137):
 same function names and signatures, evaluated by the fused CUDA loss kernels of libmvc_b200
-(forward value and gradient).  NLPScore (string metrics, losses.py:140-160) is out of scope and
-stays the reference's."""
+(forward value and gradient).  NLPScore (string metrics over pycocoevalcap, losses.py:140-160) is not
+GPU work: the name is re-exported here so that `from losses import ..., NLPScore` (train.py:12) resolves,
+and forwards to the reference's own implementation found further down sys.path."""
+import importlib.util
+import os
+import sys
 from functools import partial
 
 import torch
@@ -30,6 +34,8 @@ def TotalReconstructionLoss(output, captions, features=None, features_recons=Non
     """losses.py:43-69 (single-stream twin) -> (loss, ce, entropy, rec_loss)."""
     loss, ce, ent, _, rec = Fn.ModalityLossFn.apply(output, captions, None, None, features, features_recons,
                                                     float(reg_lambda), 0.0, float(recon_lambda), reconstruction_type)
+    if features_recons is None or reconstruction_type not in ("global", "local"):
+        loss, rec = loss.reshape(1), rec.reshape(1)         # the reference's torch.zeros(1) term broadcasts (:58-66)
     return loss, ce, ent, rec
 
 
@@ -49,3 +55,34 @@ def EntropyLoss(x, ignore_mask):
     _, _, ent, _, _ = Fn.ModalityLossFn.apply(torch.cat([pad, x.detach()], 0), caps, None, None, None, None, 0.0, 0.0,
                                               0.0, "none")
     return ent
+
+
+_REF_LOSSES = None
+
+
+def _reference_losses():
+    """The reference's own losses.py: the next `losses.py` on sys.path after this one (the launcher and
+    INTEGRATION.md put the reference's src/ and repository root behind this package)."""
+    global _REF_LOSSES
+    if _REF_LOSSES is None:
+        here = os.path.dirname(os.path.abspath(__file__))
+        for d in sys.path:
+            cand = os.path.join(d or os.getcwd(), "losses.py")
+            if os.path.isfile(cand) and os.path.abspath(os.path.dirname(cand)) != here:
+                root = os.path.dirname(os.path.dirname(os.path.abspath(cand)))       # <reference>/ holds pycocoevalcap/
+                if os.path.isdir(os.path.join(root, "pycocoevalcap")) and root not in sys.path:
+                    sys.path.append(root)
+                spec = importlib.util.spec_from_file_location("_mvc_reference_losses", cand)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _REF_LOSSES = mod
+                break
+        else:
+            raise ImportError("NLPScore is the reference's pycocoevalcap wrapper (src/losses.py:140-160): put the "
+                              "reference's src/ directory on sys.path behind multimodal-video-captioning_b200/")
+    return _REF_LOSSES
+
+
+def NLPScore(ref, hypo):
+    """losses.py:140-160 (BLEU / METEOR / ROUGE-L / CIDEr over pycocoevalcap): forwarded to the reference."""
+    return _reference_losses().NLPScore(ref, hypo)

@@ -117,6 +117,8 @@ SIGNATURES = {
     "mvc_global_recon_loss_workspace_bytes": (sz, [i32, i32]),
     "mvc_global_recon_loss": (i32, [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, i64, f32, vp, vp]),
     "mvc_local_recon_loss": (i32, [vp, i64, vp, i64, i64, i32, vp, vp, i64, f32, vp, vp]),
+    "mvc_loss_combine": (i32, [vp, f32, f32, f32, i32, i32, vp]),
+    "mvc_scale_by_scalar": (i32, [vp, i64, vp, vp]),
     "mvc_clip_adam_step": (i32, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, i32, f32, vp]),
 }
 

@@ -43,31 +43,20 @@ class TemporalAttention(nn.Module):
         self.b = nn.Parameter(torch.ones(bottleneck_size), requires_grad=True)
         self.w = nn.Linear(bottleneck_size, 1, bias=False)
 
-    @torch.no_grad()
     def forward(self, hidden, feats, masks=None):
-        """(attn_feats [B,F], weights [B,T,1]); temporal_attention.py:19-33.  Inference-only entry:
-        inside the decoder / reconstructor the attention runs fused in the step kernels."""
-        lib = cabi.lib()
-        B, T, F = feats.shape
-        A, H = self.W.weight.shape
-        hidden, feats = Fn._f32c(hidden, "hidden"), Fn._f32c(feats, "feats")
-        dev, st = feats.device, cabi.stream_ptr()
-        wq = torch.empty(B, A, device=dev)
-        uk = torch.empty(B * T, A, device=dev)
-        W, U = self.W.weight.detach().contiguous(), self.U.weight.detach().contiguous()
-        cabi.check(lib.mvc_gemm_f32(B, A, H, 1.0, cabi.ptr(hidden), H, 1, cabi.ptr(W), H, 1, 0.0, cabi.ptr(wq), A, None, st))
-        cabi.check(lib.mvc_gemm_f32(B * T, A, F, 1.0, cabi.ptr(feats), F, 1, cabi.ptr(U), F, 1, 0.0, cabi.ptr(uk), A, None, st))
-        ctx = torch.empty(B, F, device=dev)
-        alpha = torch.empty(B, T, device=dev)
-        m = None if masks is None else masks.to(device=dev, dtype=torch.uint8).contiguous()
-        cabi.check(lib.mvc_soft_attention_fwd(B, T, A, F, cabi.ptr(wq), cabi.ptr(uk), cabi.ptr(self.b.detach()),
-                                              cabi.ptr(self.w.weight.detach()), cabi.ptr(feats), 0, B, T * F, F,
-                                              cabi.ptr(m), T, 1, cabi.ptr(ctx), F, None, 0, cabi.ptr(alpha), 0, st))
+        """(attn_feats [B,F], weights [B,T,1]); temporal_attention.py:19-33.  Differentiable w.r.t. hidden,
+        feats and the four parameters (Fn.SoftAttentionFn); inside the decoder / reconstructor time loops the
+        attention runs fused in the step kernels instead."""
+        ctx, alpha = Fn.SoftAttentionFn.apply(hidden, feats, masks, self.W.weight, self.U.weight, self.b,
+                                              self.w.weight)
         return ctx, alpha.unsqueeze(2)
 
 
 class FeaturesCaptioning(nn.Module):
     """SA-LSTM caption decoder; features_captioning.py:9-228."""
+    # class-level default: modules unpickled from a checkpoint the REFERENCE saved (torch.save(model),
+    # train.py:162-173) carry no `precision` in their __dict__ and run the exact fp32 path
+    precision = _DEFAULT_PRECISION
 
     def __init__(self, in_feature_size, output_size, rnn_type="LSTM", rnn_num_layers=1, rnn_bidirectional=False,
                  rnn_hidden_size=128, rnn_dropout=0.5, embedding_size=128, attn_size=128, device="cpu",
@@ -104,8 +93,9 @@ class FeaturesCaptioning(nn.Module):
 
     def _init_hidden(self, batch_size):
         dev = self.out.weight.device
-        return (torch.zeros(1, batch_size, self.hidden_size, device=dev),
-                torch.zeros(1, batch_size, self.hidden_size, device=dev))
+        h, c = (torch.zeros(1, batch_size, self.hidden_size, device=dev) for _ in range(2))
+        h._mvc_zero_state = True            # forward_sentence: this state takes the fused time loop
+        return h, c
 
     # ---- reference API
     def decode(self, features, captions=None, max_caption_len=30, teacher_forcing_ratio=1):
@@ -117,45 +107,39 @@ class FeaturesCaptioning(nn.Module):
         return Fn.DecoderFn.apply(self._dims(B, T, max_caption_len), flags, a, v, captions, *self._params())
 
     def forward_sentence(self, features, captions, hidden, max_caption_len=30, teacher_forcing_ratio=1):
-        """features_captioning.py:91-119.  The reference only ever passes the zero state from
-        _init_hidden here (:124-125); a non-zero initial state is not supported by the fused path."""
-        return self.decode(features, captions, max_caption_len, teacher_forcing_ratio)
+        """features_captioning.py:91-119.  The zero state of _init_hidden (the only state the reference ever
+        passes, :124-125) takes the fused time-loop kernels; any other initial state is stepped word by word
+        through forward_word (same arithmetic and RNG draws, differentiable, one launch chain per word)."""
+        if hidden is None or getattr(hidden[0], "_mvc_zero_state", False):
+            return self.decode(features, captions, max_caption_len, teacher_forcing_ratio)
+        feats = features if not isinstance(features, (tuple, list)) else torch.cat(list(features), -1)
+        B = feats.shape[0]
+        dev = feats.device
+        zeros_o = torch.zeros(B, self.output_size, device=dev)
+        zeros_h = torch.zeros(1, B, self.hidden_size, device=dev)
+        words = torch.full((1, B), 1, dtype=torch.int64, device=dev)                 # <SOS>, :101
+        sentence, hiddens = [zeros_o], [zeros_h]
+        for t in range(1, max_caption_len):
+            logp, hidden, _ = self.forward_word(feats, hidden, words)
+            sentence.append(logp)
+            hiddens.append(hidden[0])
+            teacher = captions is not None and bool(torch.rand(1) < teacher_forcing_ratio)   # :113-116
+            words = (captions[t] if teacher else logp.detach().argmax(1)).reshape(1, B)
+        return torch.stack(sentence), torch.stack(hiddens)
 
     forward = decode
 
-    @torch.no_grad()
     def forward_word(self, features, hidden, previous_words):
         """One decoder step from an arbitrary state: (log_probs [B,V], (h,c), attn_weights [B,T,1]);
-        features_captioning.py:77-89.  Inference-only convenience built from the block kernels."""
-        lib = cabi.lib()
-        st = cabi.stream_ptr()
+        features_captioning.py:77-89.  Built from the fp32 block kernels as two autograd nodes
+        (Fn.SoftAttentionFn, Fn.WordStepFn), so stepping the decoder word by word is differentiable
+        like the reference's."""
         h0, c0 = hidden
-        feats = Fn._f32c(features, "features")
-        B, T, F = feats.shape
-        H, E, V = self.hidden_size, self.embedding_size, self.output_size
-        dev = feats.device
+        feats = features if not isinstance(features, (tuple, list)) else torch.cat(list(features), -1)
         ctx, alpha = self.attention(h0[-1], feats)
-        emb = torch.empty(B, E, device=dev)
-        words = previous_words.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
-        cabi.check(lib.mvc_embedding_gather(cabi.ptr(self.embedding.weight.detach()), E, cabi.ptr(words), B, cabi.ptr(emb),
-                                            E, 0, st))
-        w_ih, w_hh = self.rnn.weight_ih_l0.detach(), self.rnn.weight_hh_l0.detach()
-        pre = torch.empty(B, 4 * H, device=dev)
-        hprev = Fn._f32c(h0[-1], "hidden")
-        cabi.check(lib.mvc_gemm_f32(B, 4 * H, E, 1.0, cabi.ptr(emb), E, 1, cabi.ptr(w_ih), E + F, 1, 0.0, cabi.ptr(pre),
-                                    4 * H, cabi.ptr(self.rnn.bias_ih_l0.detach()), st))
-        cabi.check(lib.mvc_gemm_f32(B, 4 * H, F, 1.0, cabi.ptr(ctx), F, 1, C.c_void_p(w_ih.data_ptr() + 4 * E), E + F, 1,
-                                    1.0, cabi.ptr(pre), 4 * H, cabi.ptr(self.rnn.bias_hh_l0.detach()), st))
-        cabi.check(lib.mvc_gemm_f32(B, 4 * H, H, 1.0, cabi.ptr(hprev), H, 1, cabi.ptr(w_hh), H, 1, 1.0, cabi.ptr(pre),
-                                    4 * H, None, st))
-        h1, c1 = torch.empty(B, H, device=dev), torch.empty(B, H, device=dev)
-        cprev = Fn._f32c(c0[-1], "cell")
-        cabi.check(lib.mvc_lstm_cell_fwd(B, H, cabi.ptr(pre), None, 0, None, None, None, cabi.ptr(cprev), None,
-                                         cabi.ptr(c1), cabi.ptr(h1), H, None, 0, None, 0, st))
-        logp = torch.empty(B, V, device=dev)
-        cabi.check(lib.mvc_gemm_f32(B, V, H, 1.0, cabi.ptr(h1), H, 1, cabi.ptr(self.out.weight.detach()), H, 1, 0.0,
-                                    cabi.ptr(logp), V, cabi.ptr(self.out.bias.detach()), st))
-        cabi.check(lib.mvc_log_softmax_rows(cabi.ptr(logp), B, V, None, st))
+        logp, h1, c1 = Fn.WordStepFn.apply(previous_words, ctx, h0[-1], c0[-1], self.embedding.weight,
+                                           self.rnn.weight_ih_l0, self.rnn.weight_hh_l0, self.rnn.bias_ih_l0,
+                                           self.rnn.bias_hh_l0, self.out.weight, self.out.bias)
         return logp, (h1.unsqueeze(0), c1.unsqueeze(0)), alpha
 
     @torch.no_grad()
@@ -180,6 +164,8 @@ class FeaturesCaptioning(nn.Module):
 
 
 class _ReconBase(nn.Module):
+    precision = _DEFAULT_PRECISION      # see FeaturesCaptioning.precision
+
     def _dims(self, B, L, T):
         return (B, L, self.decoder_size, self.hidden_size, getattr(self, "attn_size", 0) or 0, T,
                 cabi.precision_id(self.precision))
@@ -285,8 +271,8 @@ class AVCaptioning(nn.Module):
         if self.reconstructor is None:
             return outputs, None, None
         rec = self.reconstructor.reconstruct(rnn_hiddens, outputs, captions, visual_features.shape[1])
-        Fa = audio_features.shape[2]
-        return outputs, rec[:, :, 0:Fa], rec[:, :, Fa:]                       # :125-126
+        a_rec, v_rec = Fn.SplitFeaturesFn.apply(rec, audio_features.shape[2])     # :125-126
+        return outputs, a_rec, v_rec
 
     @torch.no_grad()
     def predict_ids(self, audio_features, visual_features, max_caption_len=30, mode="direct", beam_alpha=0,
@@ -360,3 +346,14 @@ class AVCaptioningDual(nn.Module):
     def predict(self, audio_features, visual_features, max_caption_len=30, mode="direct", beam_alpha=0, beam_width=5):
         ids = self.predict_ids(audio_features, visual_features, max_caption_len, mode, beam_alpha, beam_width)
         return [self.vocab.decode_indexes(o[1:]) for o in ids]
+
+
+# Pickle identity.  torch.save(model) (train.py:162-173) records each class as module path + name; the reference's
+# classes live in models.captioning / models.features_captioning / models.reconstructor / models.temporal_attention.
+# Reporting the same paths makes (i) whole-module pickles written by the reference load into these classes and
+# (ii) pickles written from here resolve through `models.*` wherever they are loaded.
+for _cls, _mod in ((TemporalAttention, "models.temporal_attention"), (FeaturesCaptioning, "models.features_captioning"),
+                   (GlobalReconstructor, "models.reconstructor"), (LocalReconstructor, "models.reconstructor"),
+                   (AVCaptioning, "models.captioning"), (AVCaptioningDual, "models.captioning")):
+    _cls.__module__ = _mod
+del _cls, _mod

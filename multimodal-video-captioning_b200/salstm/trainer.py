@@ -5,31 +5,54 @@
 re-laid out for one GPU per process: parameters and gradients live in ONE flat fp32 buffer each
 (the module's ``nn.Parameter``s become views, so ``state_dict`` / checkpoints are unchanged), the
 clip + Adam update is one kernel launch over that buffer (``mvc_clip_adam_step``) and, under data
-parallelism, the gradient exchange is one NCCL all-reduce of the flat gradient buffer over
-NVLink/NVSwitch with the 1/world averaging folded into the same kernel.
+parallelism, the gradient exchange is an NCCL all-reduce of the flat gradient buffer over
+NVLink/NVSwitch -- in buckets, launched on a communication stream as the backward
+pass finishes each group of gradients (``GradBuckets``) -- with the 1/world averaging folded into
+the update kernel.
 
+``FlatClipAdam`` is a ``torch.optim.Optimizer`` (one param group): ``ReduceLROnPlateau(optimizer)``
+(train.py:90-97) drives its ``lr`` like any other optimizer's, and ``state_dict`` round-trips.
 Parameters that never receive a gradient (``AVCaptioningDual.output_fc``, captioning.py:185) are
 left untouched, as ``torch.optim.Adam`` does for ``grad is None``.
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional
+from typing import Iterable, List, Optional, Tuple
 
 import torch
 
 from . import functional as Fn
 
 
-class FlatClipAdam:
+class FlatClipAdam(torch.optim.Optimizer):
     def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5,
-                 clip_value: float = 5.0, process_group=None, world_size: Optional[int] = None):
-        self.params = [p for p in params if p.requires_grad]
-        self.lr, self.betas, self.eps, self.weight_decay, self.clip_value = lr, betas, eps, weight_decay, clip_value
+                 clip_value: float = 5.0, process_group=None, world_size: Optional[int] = None, amsgrad: bool = True):
+        if not amsgrad:
+            raise NotImplementedError("FlatClipAdam implements the reference's Adam(amsgrad=True) (train.py:86-88)")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip_value=clip_value)
+        super().__init__([p for p in params if p.requires_grad], defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError("FlatClipAdam takes one parameter group (the reference trains model.parameters())")
+        self.params: List[torch.nn.Parameter] = self.param_groups[0]["params"]
         self.group = process_group
         self.world = world_size
         self.step_count = 0
         self.flat_p = self.flat_g = self.m = self.v = self.vmax = None
-        self._live = None
+        self._live: Optional[List[torch.nn.Parameter]] = None
+        self._live_set = set()
+        self._views: List[torch.Tensor] = []
+        self._offsets: List[int] = []
+        self._arena = None
+        self._pending = []          # async all-reduce work handles of this step (bucketed mode)
+
+    # convenience mirrors of the single param group (kept in sync with lr schedulers)
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, value):
+        self.param_groups[0]["lr"] = value
 
     # ---- lazy flattening: after the first backward we know which parameters get gradients
     def _flatten(self):
@@ -37,68 +60,130 @@ class FlatClipAdam:
         if not live:
             raise RuntimeError("FlatClipAdam.step() before any backward()")
         dev = live[0].device
+        old = None
+        if self.flat_p is not None:       # a parameter received its first gradient later: re-flatten, keep the moments
+            old = {id(p): (o, p.numel()) for p, o in zip(self._live, self._offsets)}
+            old_m, old_v, old_vmax = self.m, self.v, self.vmax
         n = sum(p.numel() for p in live)
-        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
-        self.flat_g = torch.empty(n, device=dev, dtype=torch.float32)
-        off = 0
+        flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        flat_g = torch.empty(n, device=dev, dtype=torch.float32)
+        m, v, vmax = (torch.zeros(n, device=dev, dtype=torch.float32) for _ in range(3))
+        off, offsets = 0, []
         for p in live:
             k = p.numel()
-            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
-            self.flat_g[off:off + k].copy_(p.grad.reshape(-1))
-            p.data = self.flat_p[off:off + k].view_as(p)
-            p.grad = self.flat_g[off:off + k].view_as(p)
+            flat_p[off:off + k].copy_(p.data.reshape(-1))
+            flat_g[off:off + k].copy_(p.grad.reshape(-1))
+            if old is not None and id(p) in old:
+                o = old[id(p)][0]
+                m[off:off + k].copy_(old_m[o:o + k]); v[off:off + k].copy_(old_v[o:o + k])
+                vmax[off:off + k].copy_(old_vmax[o:o + k])
+            p.data = flat_p[off:off + k].view_as(p)
+            p.grad = flat_g[off:off + k].view_as(p)
+            offsets.append(off)
             off += k
-        self.m, self.v, self.vmax = (torch.zeros_like(self.flat_p) for _ in range(3))
-        self._live = live
+        self.flat_p, self.flat_g, self.m, self.v, self.vmax = flat_p, flat_g, m, v, vmax
+        self._live, self._offsets = live, offsets
+        self._live_set = {id(p) for p in live}
         self._views = [p.grad for p in live]
         if dev.type == "cuda":
-            # backward kernels write gradients straight into these views (functional._GRAD_ARENA)
-            Fn.register_grad_arena({p.data_ptr(): g for p, g in zip(live, self._views)})
+            # backward kernels write gradients straight into these views (functional.GradArena)
+            self._arena = Fn.GradArena(live, self._views)
+            Fn.register_grad_arena(self._arena)
 
-    def zero_grad(self):
+    def zero_grad(self, set_to_none: bool = True):
         """Before the first step: plain ``grad = None``.  Afterwards gradients live in the flat buffer; on CUDA the
         backward kernels OVERWRITE their arena views (and autograd adopts them because ``grad is None``), so no
-        zero-fill is needed; elsewhere (CPU plumbing tests) the buffer is cleared and autograd accumulates."""
-        if self.flat_g is None or self.flat_g.device.type == "cuda":
+        zero-fill is needed; with ``set_to_none=False`` (or on CPU, in the plumbing tests) the buffer is cleared and
+        autograd accumulates into it."""
+        if self._arena is not None:
+            self._arena.new_step()
+        if self.flat_g is None or (set_to_none and self.flat_g.device.type == "cuda"):
             for p in self.params:
                 p.grad = None
         else:
             self.flat_g.zero_()
+            for p, v in zip(self._live, self._views):
+                p.grad = v
 
-    def _adopt(self):
-        """Make sure every live parameter's .grad IS its arena view (copy in anything autograd allocated itself)."""
-        for p, v in zip(self._live, self._views):
+    def _sync_views(self) -> List[Tuple[int, int]]:
+        """Make every live parameter's .grad its arena view (copy in anything autograd allocated itself) and return
+        the [lo, hi) element ranges of the flat buffer that hold a gradient this step.  A parameter whose grad is
+        None is skipped by torch.optim.Adam (no weight decay, no moment update): its range is left out."""
+        if self._live is None or any(p.grad is not None and id(p) not in self._live_set for p in self.params):
+            self._flatten()
+        ranges: List[Tuple[int, int]] = []
+        for p, v, o in zip(self._live, self._views, self._offsets):
             g = p.grad
             if g is None:
-                v.zero_()
-            elif g.data_ptr() != v.data_ptr():
+                continue
+            if g.data_ptr() != v.data_ptr():
                 v.copy_(g)
-            p.grad = v
+                p.grad = v
+            if ranges and ranges[-1][1] == o:
+                ranges[-1] = (ranges[-1][0], o + p.numel())
+            else:
+                ranges.append((o, o + p.numel()))
+        return ranges
 
+    # ---- gradient exchange
     def all_reduce_grads(self):
-        """One NCCL all-reduce (sum) over the flat gradient buffer; averaging happens in step()."""
+        """NCCL all-reduce (sum) of the flat gradient buffer; averaging happens in step().  Buckets already
+        exchanged by the backward-pass hook (GradBuckets) are only waited for."""
         import torch.distributed as dist
-        if self.flat_g is None:
-            self._flatten()
-        else:
-            self._adopt()
+        self._sync_views()
+        if self._pending:
+            for w in self._pending:
+                w.wait()
+            self._pending = []
+            return
         dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
 
-    def step(self):
-        if self.flat_g is None:
-            self._flatten()
-        else:
-            self._adopt()
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        ranges = self._sync_views()
         if self.flat_p.device.type != "cuda":
             raise RuntimeError("FlatClipAdam.step: parameters must live on CUDA (the update is a CUDA kernel; "
                                "there is no CPU fallback)")
+        for w in self._pending:
+            w.wait()
+        self._pending = []
         self.step_count += 1
-        scale = 1.0
-        if self.world is not None and self.world > 1:
-            scale = 1.0 / self.world
-        Fn.clip_adam_step(self.flat_p, self.flat_g, self.m, self.v, self.vmax, lr=self.lr, betas=self.betas,
-                          eps=self.eps, weight_decay=self.weight_decay, clip_value=self.clip_value,
-                          step=self.step_count, grad_scale=scale)
+        g = self.param_groups[0]
+        scale = 1.0 / self.world if (self.world is not None and self.world > 1) else 1.0
+        for lo, hi in ranges:
+            Fn.clip_adam_step(self.flat_p[lo:hi], self.flat_g[lo:hi], self.m[lo:hi], self.v[lo:hi], self.vmax[lo:hi],
+                              lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"],
+                              clip_value=g["clip_value"], step=self.step_count, grad_scale=scale)
+        if self._arena is not None:
+            self._arena.new_step()
+        return loss
+
+    # ---- checkpointing: the flat moments, addressed by parameter order
+    def state_dict(self):
+        sd = {"step": self.step_count, "param_group": {k: v for k, v in self.param_groups[0].items() if k != "params"}}
+        if self.flat_p is not None:
+            sd.update(exp_avg=self.m.clone(), exp_avg_sq=self.v.clone(), max_exp_avg_sq=self.vmax.clone(),
+                      live=[self.params.index(p) for p in self._live])
+        return sd
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.param_groups[0].update(sd["param_group"])
+        if "exp_avg" in sd:
+            live = [self.params[i] for i in sd["live"]]
+            for p in live:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            for p in self.params:
+                if p not in live:
+                    p.grad = None
+            self.flat_p = None
+            self._flatten()
+            self.m.copy_(sd["exp_avg"]); self.v.copy_(sd["exp_avg_sq"]); self.vmax.copy_(sd["max_exp_avg_sq"])
 
 
 def shard_batch(audio, visual, captions, rank: int, world: int):
