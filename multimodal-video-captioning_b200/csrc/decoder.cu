@@ -17,7 +17,10 @@
 //     backward and dh += dwq.W stay inside the loop.
 #include <mutex>
 
+#include <unordered_map>
+
 #include "recur.cuh"
+#include "recur2.cuh"
 #include "step.cuh"
 
 namespace mvc {
@@ -45,9 +48,27 @@ struct DecWs {
   float* gx;      // [S*B, 4H]
   float* embtab;  // [V, 4H]
   float* hzero;   // [B, H] zeros (c_0 / fp32 h_0)
-  unsigned* sync; // grid-barrier counter of the persistent recurrence kernel
+  unsigned* sync; // grid-barrier counters of the persistent recurrence kernels
+  void* P;        // [B*T, 4H] fp16: keys . W_ih[:, E:]^T, unit-major gate columns (recur2 path)
+  float* gh;      // [128, 4H]  h_s . W_hh^T of the current step (recur2 path)
   size_t bytes;
 };
+
+// Which time-loop implementation a forward call ran, keyed by its workspace: the backward call must read the saved
+// activations in the layout that forward wrote (tile-interleaved vs unit-major gate columns, ctx present or not).
+enum { DEC_LOOP_CHAIN = 0, DEC_LOOP_RECUR1 = 1, DEC_LOOP_RECUR2 = 2 };
+static std::mutex g_loop_mu;
+static std::unordered_map<const void*, int> g_loop_mode;
+static void set_loop_mode(const void* ws, int mode) {
+  std::lock_guard<std::mutex> lk(g_loop_mu);
+  if (g_loop_mode.size() > 4096) g_loop_mode.clear();
+  g_loop_mode[ws] = mode;
+}
+static int get_loop_mode(const void* ws) {
+  std::lock_guard<std::mutex> lk(g_loop_mu);
+  auto it = g_loop_mode.find(ws);
+  return it == g_loop_mode.end() ? -1 : it->second;
+}
 
 // A library-owned side stream per device (+ fork / join events): work that does not feed the recurrence (the weight
 // gradients of the vocabulary projection) runs there, on the SMs the persistent backward kernel leaves idle.
@@ -103,7 +124,9 @@ static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
   w.gx = ar.take<float>(S * B * 4 * H);
   w.embtab = ar.take<float>(V * 4 * H);
   w.hzero = ar.take<float>(B * H);
-  w.sync = ar.take<unsigned>(64);
+  w.sync = ar.take<unsigned>(128);
+  w.P = bf ? ar.take<char>(B * T * 4 * H * 2) : nullptr;
+  w.gh = bf ? ar.take<float>(128 * 4 * H) : nullptr;
   w.bytes = ar.off + 256;
   return w;
 }
@@ -118,7 +141,7 @@ __global__ void pack_wcat_kernel(const float* __restrict__ w_x, int64_t wx_ld, c
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t ro = i / K;
     const int k = (int)(i - ro * K);
-    const int64_t r = perm ? gate_unperm(H, (int)ro) : ro;
+    const int64_t r = perm == 2 ? gate_unperm(-H, (int)ro) : (perm ? gate_unperm(H, (int)ro) : ro);   // 2: unit-major
     const float v = k < F ? w_x[r * wx_ld + k] : w_hh[r * H + (k - F)];
     if constexpr (sizeof(OutT) == 2) out[i] = __float2bfloat16(v);
     else out[i] = v;
@@ -215,11 +238,12 @@ int launch_add_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int6
 
 // Prepare weights/features in the compute dtype + U.feats.  Shared by forward, greedy and beam.
 static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const float* audio, int Fa,
-                       const float* visual, int Fv, DecWs& w, bool need_embtab, cudaStream_t st) {
+                       const float* visual, int Fv, DecWs& w, bool need_embtab, cudaStream_t st, bool unit_major = false) {
   const int B = d->B, T = d->T, F = d->F, H = d->H, E = d->E, A = d->A, V = d->V;
   const bool bf = d->precision == MVC_BF16;
   const int Ep = bf ? pad8(E) : E;
-  const int perm = dec_perm(d);
+  const int perm = unit_major ? 2 : dec_perm(d);
+  const int permH = perm == 2 ? -H : (perm ? H : 0);
   MVC_CHECK(Fa + Fv == F, "decoder: Fa (%d) + Fv (%d) != in_feature_size (%d)", Fa, Fv, F);
   // weight packing / casting on the side stream, concurrent with the feature cast and the U.k GEMM
   SideStream* side = nullptr;
@@ -227,10 +251,10 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
   MVC_CUDA(cudaEventRecord(side->fork, st));
   MVC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
   cudaStream_t ss = side->stream;
-  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, perm ? H : 0, ss));
+  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, permH, ss));
   MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, bf, perm, ss));
   if (bf) {
-    MVC_TRY(launch_cast_pad_bf16(p->w_ih, 4 * H, E, E + F, Ep, w.wie, perm ? H : 0, ss));
+    MVC_TRY(launch_cast_pad_bf16(p->w_ih, 4 * H, E, E + F, Ep, w.wie, permH, ss));
     MVC_TRY(mvc_cast_bf16(p->att_W, w.W, (int64_t)A * H, ss));
     MVC_TRY(mvc_cast_bf16(p->out_w, w.outw, (int64_t)V * H, ss));
     if (tc_aux_row0(V) > V)
@@ -339,7 +363,9 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
     for (int i = 0; i + 1 < S; ++i) all_tf = all_tf && tf_flags_host[i];
   }
 
-  MVC_TRY(dec_prepare(d, p, audio, Fa, visual, Fv, w, !all_tf, st));
+  // fully teacher-forced bf16 sequences take the projected-keys persistent kernels (recur2.cuh)
+  const bool use_r2 = bf && all_tf && recur2_supported(B, T, F, H, A);
+  MVC_TRY(dec_prepare(d, p, audio, Fa, visual, Fv, w, !all_tf, st, use_r2));
   MVC_CUDA(cudaMemsetAsync(out_logp, 0, sizeof(float) * (size_t)B * V, st));      // sentence[0] = 0  (:96)
   MVC_CUDA(cudaMemsetAsync(out_hid, 0, sizeof(float) * (size_t)B * H, st));       // hidden_states[0] = 0 (:98)
   MVC_CUDA(cudaMemsetAsync(w.c, 0, sizeof(float) * (size_t)B * H, st));           // c_0 = 0 (:66-75)
@@ -358,8 +384,27 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
   }
 
   const StepCfg cfg = dec_cfg(d, p, w, nullptr);
-  const bool persistent = cfg.perm && recur_fwd_supported(B, T, F, H, A);
-  if (persistent && all_tf) {
+  const bool persistent = use_r2 || (cfg.perm && recur_fwd_supported(B, T, F, H, A));
+  set_loop_mode(workspace, use_r2 ? DEC_LOOP_RECUR2 : (persistent && all_tf ? DEC_LOOP_RECUR1 : DEC_LOOP_CHAIN));
+  if (use_r2) {
+    // P = keys . W_ih[:, E:]^T  ([B*T, F] x [F, 4H], bf16 out, unit-major gate columns): the context half of every
+    // step's gate pre-activation becomes sum_t alpha_t P[b,t,:], accumulated out of tensor memory by the row owner
+    // (stored as fp16, saturating: |P| beyond 65504 means fully saturated gates anyway, and the 11-bit mantissa keeps
+    // the rounding error of the pre-activation 4x below bf16's on unnormalised features)
+    {
+      TcEpilogue ep{};
+      ep.mode = TC_MODE_PLAIN;
+      ep.Cb = (__nv_bfloat16*)w.P; ep.ldcb = 4 * H; ep.cb_f16 = 1;
+      MVC_TRY(tc_gemm(B * T, 4 * H, F, w.feats, F, w.wcat, ldx, ep, 0, st));
+    }
+    Recur2FwdParams rp{};
+    rp.B = B; rp.T = T; rp.F = F; rp.K = F + H; rp.S = S;
+    rp.P = (const __nv_bfloat16*)w.P; rp.uk = w.uk; rp.attW = (const __nv_bfloat16*)w.W;
+    rp.att_b = p->att_b; rp.att_w = p->att_w; rp.gx = w.gx;
+    rp.xh = (__nv_bfloat16*)w.xh; rp.c = w.c; rp.act = w.act; rp.alpha = w.alpha; rp.wq_out = w.wq;
+    rp.out_hid = out_hid; rp.gh = w.gh; rp.sync = w.sync + 32;
+    MVC_TRY(recur2_fwd_launch(rp, cptr(w.wcat, F, 2), ldx, st));
+  } else if (persistent && all_tf) {
     // the whole teacher-forced time loop in ONE persistent cluster-cooperative launch (recur_fwd.cu)
     RecurFwdParams rp{};
     rp.B = B; rp.T = T; rp.F = F; rp.H = H; rp.A = A; rp.K = F + H; rp.S = S; rp.s0 = 0; rp.s1 = S;
@@ -444,6 +489,8 @@ struct DecBwdWs {
   void* dwqT;       // [A, SBp]
   void* dwq_b;      // [S*B, A]
   void* attWT;      // [H, A]
+  void* whhT;       // [H, 4H] W_hh^T, unit-major gate columns (recur2 path)
+  float* ghb;       // [128, H] dG_s . W_hh of the current step (recur2 path)
   size_t bytes;
 };
 
@@ -479,6 +526,8 @@ static DecBwdWs dec_bwd_layout(const MvcDecoderDims* d, void* base) {
     w.dwqT = ar.take<char>(A * SBp * 2);
     w.dwq_b = ar.take<char>(S * B * A * 2);
     w.attWT = ar.take<char>(H * A * 2);
+    w.whhT = ar.take<char>(H * 4 * H * 2);
+    w.ghb = ar.take<float>(128 * H);
   }
   w.bytes = ar.off + 256;
   return w;
@@ -506,6 +555,9 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   // fp32 h_1..h_S (contiguous [S*B,H]) are not saved separately: they are the h-parts of xh slots 1..S.
   const char* hall = cptr(w.xh, (int64_t)B * ldx + F, es);    // rows = slots 1..S, ld = ldx
   const char* hprev = cptr(w.xh, F, es);                      // rows = slots 0..S-1
+  int loop_mode = get_loop_mode(fwd_workspace);
+  MVC_CHECK(loop_mode >= 0, "mvc_decoder_backward: fwd_workspace was not written by mvc_decoder_forward in this process");
+  const bool use_r2 = loop_mode == DEC_LOOP_RECUR2;
 
   // ---- vocabulary projection backward (all steps at once)
   SideStream* side = nullptr;
@@ -531,6 +583,8 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_TRY(mvc_gemm_bf16(V, H, SB, q.dlogitsT, SBp, q.hallT, SBp, 0.f, g->out_w, H, nullptr, nullptr, 0, ss));
       MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, ss));
       // operand transposes of the post-loop weight-gradient GEMMs that only need forward data
+      // (recur2 forward never formed ctx: rebuild the ctx halves of the xh slots from the saved alpha first)
+      if (use_r2) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, ss));
       MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, ss));
       MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, ss));
       MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
@@ -558,15 +612,26 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   MVC_CUDA(cudaMemsetAsync(q.duk, 0, sizeof(float) * (size_t)B * T * A, st));
   MVC_CUDA(cudaMemsetAsync(q.dwpart, 0, sizeof(float) * (size_t)B * A, st));
   if (bf) {
-    MVC_TRY(mvc_transpose_to_bf16(w.wcat, 1, 4 * H, F + H, ldx, q.wcatT, 4 * H, st));
+    if (use_r2) MVC_TRY(mvc_transpose_to_bf16(cptr(w.wcat, F, 2), 1, 4 * H, H, ldx, q.whhT, 4 * H, st));
+    else MVC_TRY(mvc_transpose_to_bf16(w.wcat, 1, 4 * H, F + H, ldx, q.wcatT, 4 * H, st));
     MVC_TRY(mvc_transpose_to_bf16(w.W, 1, A, H, H, q.attWT, A, st));
   }
   StepCfg cfg = dec_cfg(d, p, w, nullptr);
   cfg.wcatT = q.wcatT;
   cfg.attWT = q.attWT;
-  const int permH = cfg.perm ? H : 0;
-  const bool persistent_bwd = bf && cfg.perm && recur_bwd_supported(B, T, F, H, A);
-  if (persistent_bwd) {
+  const int permH = use_r2 ? -H : (cfg.perm ? H : 0);
+  const bool persistent_bwd = use_r2 || (bf && cfg.perm && recur_bwd_supported(B, T, F, H, A));
+  if (use_r2) {
+    if (!dlogp) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, st));   // (otherwise done on the side stream)
+    Recur2BwdParams rp{};
+    rp.B = B; rp.T = T; rp.F = F; rp.K = F + H; rp.S = S;
+    rp.P = (const __nv_bfloat16*)w.P; rp.uk = w.uk; rp.att_b = p->att_b; rp.att_w = p->att_w;
+    rp.act = w.act; rp.c = w.c; rp.wq = w.wq; rp.alpha = w.alpha; rp.dh_ext = q.dhall;
+    rp.attWT = (const __nv_bfloat16*)q.attWT;
+    rp.dG = q.dG; rp.dG_b = (__nv_bfloat16*)q.dG_b; rp.dwq = q.dwq; rp.dwq_b = (__nv_bfloat16*)q.dwq_b;
+    rp.duk = q.duk; rp.dwpart = q.dwpart; rp.ghb = q.ghb; rp.sync = w.sync + 64;
+    MVC_TRY(recur2_bwd_launch(rp, q.whhT, st));
+  } else if (persistent_bwd) {
     // the whole BPTT time loop in ONE persistent cluster-cooperative launch (recur_bwd.cu)
     RecurBwdParams rp{};
     rp.B = B; rp.T = T; rp.F = F; rp.H = H; rp.A = A; rp.K = F + H; rp.S = S;

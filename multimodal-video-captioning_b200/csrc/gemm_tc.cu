@@ -48,6 +48,7 @@
 // the loop-invariant operand B (weights) before griddepcontrol.wait, so the weight traffic of
 // step s+1 overlaps the tail of the kernel that produces its activations.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -122,6 +123,15 @@ __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
   return v;
 }
 
+// 16-bit copy of an output value: bf16, or fp16 with saturation (TcEpilogue::cb_f16)
+__device__ __forceinline__ __nv_bfloat16 to_b16(float r, int f16) {
+  if (f16) {
+    const __half h = __float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f));
+    return *reinterpret_cast<const __nv_bfloat16*>(&h);
+  }
+  return __float2bfloat16(r);
+}
+
 // plain epilogue for NC (compile-time capacity; `n` live) consecutive columns of one row
 template <int NC, typename Arr>
 __device__ __forceinline__ void plain_store(const TcEpilogue& ep, int64_t gm, int gn0, int N, Arr& o, int n = NC) {
@@ -143,8 +153,8 @@ __device__ __forceinline__ void plain_store(const TcEpilogue& ep, int64_t gm, in
         }
         *dst = r;
         if (brow) {
-          brow[gn0 + j] = __float2bfloat16(r.x); brow[gn0 + j + 1] = __float2bfloat16(r.y);
-          brow[gn0 + j + 2] = __float2bfloat16(r.z); brow[gn0 + j + 3] = __float2bfloat16(r.w);
+          brow[gn0 + j] = to_b16(r.x, ep.cb_f16); brow[gn0 + j + 1] = to_b16(r.y, ep.cb_f16);
+          brow[gn0 + j + 2] = to_b16(r.z, ep.cb_f16); brow[gn0 + j + 3] = to_b16(r.w, ep.cb_f16);
         }
       }
     }
@@ -159,7 +169,7 @@ __device__ __forceinline__ void plain_store(const TcEpilogue& ep, int64_t gm, in
           if (ep.beta != 0.f) r += ep.beta * crow[gn];
           crow[gn] = r;
         }
-        if (brow) brow[gn] = __float2bfloat16(r);
+        if (brow) brow[gn] = to_b16(r, ep.cb_f16);
       }
     }
   }
@@ -754,7 +764,7 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
               dst += ep.ldc;
             }
             if (dstb) {
-              *dstb = __float2bfloat16(r);
+              *dstb = to_b16(r, ep.cb_f16);
               dstb += ep.ldcb;
             }
           }

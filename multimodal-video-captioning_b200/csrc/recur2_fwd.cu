@@ -1,0 +1,585 @@
+// recur2_fwd.cu -- teacher-forced SA-LSTM time loop (features_captioning.py:77-119) as ONE persistent kernel with
+// projected keys resident in tensor memory (design notes: recur2.cuh).
+//
+//   grid = 32 clusters x 4 CTAs = 128 CTAs, one per SM.  CTA (cluster c, rank r):
+//     row owner of batch row b = 4c + r : attention + LSTM cell of that row, P[b] (T x 4H bf16) in TMEM columns
+//                                         [64, 64 + 8T), U.k rows and the cell state c in registers;
+//     query projection                  : attention.W units [64r, 64r+64) in shared memory, applied to the cluster's
+//                                         four h rows (mma.sync), results scattered to the row owners over DSMEM;
+//     recurrent GEMM                    : W_hh rows of units [16c, 16c+16) x K-slice r resident in shared memory as a
+//                                         128B-swizzled UMMA operand; gh[128, 64] partial = h_s[:, slice] . W^T on
+//                                         tcgen05 (A by TMA), the four K-slice partials reduced over DSMEM in rank
+//                                         order (deterministic) and written to global `gh`.
+//   step s:   compute warps 0-7                          |  GEMM warps 8-11
+//     wait h_s rows of the cluster (mbarrier)            |  wait Y >= rows*s   (h_s of every row published)
+//     wq slice -> owners (DSMEM) -> mbarrier             |  TMA h_s k-slices -> tcgen05.mma -> park partial
+//     scores, softmax, sum_t alpha_t P[b,t,:] (TMEM)     |  mbarrier (4 partials) -> reduce -> gh -> X += 1
+//     wait X >= 128*s; gates = gx + gh + P-sum; cell     |
+//     h_{s+1}: global (bf16 + fp32), DSMEM to the four ranks, mbarrier arrive, Y += 1
+#include <cuda_fp16.h>
+
+#include <mutex>
+
+#include "recur2.cuh"
+#include "step.cuh"
+
+namespace mvc {
+using namespace r2;
+
+constexpr int F2_NKB = R2_H / 64 / R2_CS;            // 2 k-blocks of h per rank
+constexpr int F2_BN = 64;                            // gate columns per cluster (16 units x 4 gates)
+constexpr int F2_KB_BYTES = F2_BN * 128;             // one resident W_hh k-block: 64 rows x 64 bf16
+constexpr int F2_B_BYTES = F2_NKB * F2_KB_BYTES;     // 16384
+constexpr int F2_STAGE_BYTES = 128 * 128;            // A stage: 128 rows x 64 bf16
+constexpr int F2_STAGES = 2;
+constexpr int F2_RING_BYTES = F2_STAGES * F2_STAGE_BYTES;
+constexpr int F2_PS = F2_BN + 4;                     // partial tile row pitch (floats)
+constexpr int F2_HP = R2_H + 8;                      // bf16 pitch of the resident attention.W slice / h rows
+constexpr int F2_UPR = R2_A / R2_CS;                 // 64 query units per rank
+constexpr int F2_GCP = 17;                           // pitch of the P-sum hand-over buffer (floats)
+
+__global__ void __launch_bounds__(R2_THREADS, 1)
+recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ Recur2FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int H = R2_H, A = R2_A, AV = R2_AV, HP = F2_HP, UPR = F2_UPR;
+  const int B = p.B, T = p.T, K = p.K, S = p.S;
+
+  uint8_t* ring = smem + F2_B_BYTES;
+  float* sPartial = reinterpret_cast<float*>(ring + F2_RING_BYTES);                       // [128][F2_PS]
+  __nv_bfloat16* sWatt = reinterpret_cast<__nv_bfloat16*>(sPartial + 128 * F2_PS);        // [UPR][HP]
+  __nv_bfloat16* sHb = sWatt + (size_t)UPR * HP;                                          // [4][HP] h rows of the cluster
+  float* sQ = reinterpret_cast<float*>(sHb + (size_t)R2_CS * HP);                         // [A] wq of my row
+  float* sWv = sQ + A;
+  float* sBias = sWv + A;
+  float* sE = sBias + A;                                                                  // [64] scores -> alpha
+  float* sGc = sE + 64;                                                                   // [128][F2_GCP]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sGc + 128 * F2_GCP);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (F2_STAGES + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * F2_STAGES);
+  const uint32_t w_bar = tmem_full_bar + 8u;
+  const uint32_t hb_full = w_bar + 8u;          // 4 arrivals: the owners of the cluster's rows published h_s here
+  const uint32_t q_full = hb_full + 8u;         // 4 arrivals: every rank delivered its slice of my row's query
+  const uint32_t part_full = q_full + 8u;       // 4 arrivals: the K-slice partials of the cluster are parked
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * F2_STAGES + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_rank();
+  const int cl = blockIdx.x / R2_CS;
+  const int brow = blockIdx.x;
+  const bool has_row = brow < B;
+  const int n0 = cl * F2_BN;
+  const int kb0 = rank * F2_NKB;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring_base = smem_base + F2_B_BYTES;
+  const unsigned nctas = gridDim.x;
+  const unsigned nlive = (unsigned)(B < (int)gridDim.x ? B : (int)gridDim.x);
+  unsigned* cntY = p.sync;
+  unsigned* cntX = p.sync + 16;
+
+  // ---------------------------------------------------------------- one-time setup
+  if (warp == 8 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_h) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < F2_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(w_bar, 1);
+    mbar_init(hb_full, R2_CS);
+    mbar_init(q_full, R2_CS);
+    mbar_init(part_full, R2_CS);
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t tmem_p = tmem_lane + R2_PCOL;
+
+  if (warp == 8 && lane == 0) {                  // resident W_hh slice, once
+    mbar_expect_tx(w_bar, (uint32_t)F2_B_BYTES);
+    for (int i = 0; i < F2_NKB; ++i) tma_load_2d(smem_base + i * F2_KB_BYTES, &map_w, w_bar, (kb0 + i) * 64, n0);
+  }
+  float ur[R2_R][AV];                            // U.k rows of my batch row (loop invariant)
+  if (warp < 8) {
+    const int vec_per_row = H / 8;
+    for (int i = tid; i < UPR * vec_per_row; i += 256) {
+      const int u = i / vec_per_row, k8 = i - u * vec_per_row;
+      const uint4 v = *reinterpret_cast<const uint4*>(p.attW + (size_t)(rank * UPR + u) * H + k8 * 8);
+      *reinterpret_cast<uint4*>(sWatt + (size_t)u * HP + k8 * 8) = v;
+    }
+    for (int i = tid; i < A; i += 256) { sWv[i] = p.att_w[i]; sBias[i] = p.att_b[i]; sQ[i] = 0.f; }
+    if (tid < 64) sE[tid] = 0.f;
+    for (int i = tid; i < R2_CS * HP / 2; i += 256) reinterpret_cast<uint32_t*>(sHb)[i] = 0u;       // h_0 = 0
+    const float* ukb = p.uk + (size_t)(has_row ? brow : 0) * T * A;
+#pragma unroll
+    for (int r = 0; r < R2_R; ++r) {
+      const int t = warp + r * 8;
+#pragma unroll
+      for (int k = 0; k < AV; ++k) ur[r][k] = (t < T) ? __ldg(ukb + (size_t)t * A + lane + 32 * k) : 0.f;
+    }
+  }
+  if (warp < 4) {
+    // P[b] -> TMEM, resident for the whole kernel: lane L keeps, for frame t, the 8 words (gate columns
+    // [16L, 16L+16) = i,f,g,o of units 4L..4L+3) at columns [64 + 8t, 64 + 8t + 8)
+    const uint4* prow = reinterpret_cast<const uint4*>(p.P + (size_t)(has_row ? brow : 0) * T * (4 * H)) + 2 * tid;
+#pragma unroll
+    for (int c = 0; c < R2_R * 2; ++c) {         // 12 chunks of 32 columns = 4 frames each
+      uint32_t v[32];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int t = c * 4 + f;
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b2 = a;
+        if (has_row && t < T) {
+          a = __ldg(prow + (size_t)t * (4 * H / 8));
+          b2 = __ldg(prow + (size_t)t * (4 * H / 8) + 1);
+        }
+        v[f * 8 + 0] = a.x; v[f * 8 + 1] = a.y; v[f * 8 + 2] = a.z; v[f * 8 + 3] = a.w;
+        v[f * 8 + 4] = b2.x; v[f * 8 + 5] = b2.y; v[f * 8 + 6] = b2.z; v[f * 8 + 7] = b2.w;
+      }
+      tmem_st32(tmem_p + (uint32_t)(c * 32), v);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();                            // every CTA's mbarriers are initialised before any remote arrive
+
+  long long* prof = (p.prof && blockIdx.x == 0) ? p.prof : nullptr;
+#define F2_STAMP(i) do { if (prof && tid == 0) prof[s * 10 + (i)] = clock64(); } while (0)
+#define F2_STAMP_G(i) do { if (prof && tid == 256) prof[s * 10 + (i)] = clock64(); } while (0)
+
+  if (warp < 8) {
+    // ================================================================= attention + cell (row owner)
+    float cst[4] = {0.f, 0.f, 0.f, 0.f};         // cell state of units 4*tid .. 4*tid+3 (threads < 128)
+    const int half = warp >> 2;
+    for (int s = 0; s < S; ++s) {
+      F2_STAMP(0);
+      const size_t grow = (size_t)s * B + brow;
+      float4 gx4[4];
+      if (tid < 128 && has_row) {
+        const float4* gxr = reinterpret_cast<const float4*>(p.gx + grow * (size_t)(4 * H)) + 4 * tid;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gx4[q] = __ldcs(gxr + q);
+      }
+      if (s > 0) {
+        mbar_wait_cl(hb_full, (uint32_t)((s - 1) & 1));        // h_s of the cluster's four rows is in sHb
+        F2_STAMP(1);
+        // wq[4 rows][rank*UPR + 8*warp + 0..7] = h . W_slice^T (mma.sync m16n8k16, rows 4..15 of the A tile are zero)
+        const int r4 = lane >> 2, kq = (lane & 3) * 2;
+        const __nv_bfloat16* arow = sHb + (size_t)(r4 & 3) * HP + kq;
+        const __nv_bfloat16* wrow = sWatt + (size_t)(warp * 8 + r4) * HP + kq;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        const bool live = r4 < R2_CS;
+#pragma unroll 8
+        for (int k0 = 0; k0 < H; k0 += 16) {
+          const uint32_t a0 = live ? *reinterpret_cast<const uint32_t*>(arow + k0) : 0u;
+          const uint32_t a2 = live ? *reinterpret_cast<const uint32_t*>(arow + k0 + 8) : 0u;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + k0);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + k0 + 8);
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                       : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+        }
+        if (live) st_dsmem_f32x2(mapa(smem_u32(sQ + rank * UPR + warp * 8 + kq), (uint32_t)r4), c0, c1);
+        named_bar<1, 256>();
+        if (tid == 0) {
+#pragma unroll
+          for (int d = 0; d < R2_CS; ++d) mbar_arrive_remote(mapa(q_full, (uint32_t)d));
+        }
+        mbar_wait_cl(q_full, (uint32_t)((s - 1) & 1));         // every rank's slice of my row's query has landed
+      }
+      F2_STAMP(2);
+      if (has_row) {
+        float* wq_out = p.wq_out + grow * A;
+        for (int i = tid; i < A; i += 256) wq_out[i] = sQ[i];
+        float qb[AV], wv[AV];
+#pragma unroll
+        for (int k = 0; k < AV; ++k) { qb[k] = sQ[lane + 32 * k] + sBias[lane + 32 * k]; wv[k] = sWv[lane + 32 * k]; }
+#pragma unroll
+        for (int r = 0; r < R2_R; ++r) {
+          const int t = warp + r * 8;
+          if (t < T) {
+            float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < AV; k += 2) {
+              e0 = fmaf(wv[k], tanh_fast(qb[k] + ur[r][k]), e0);
+              e1 = fmaf(wv[k + 1], tanh_fast(qb[k + 1] + ur[r][k + 1]), e1);
+            }
+            const float e = warp_sum(e0 + e1);
+            if (lane == 0) sE[t] = e;
+          }
+        }
+      }
+      named_bar<1, 256>();
+      if (has_row && warp == 0) {                 // softmax over T <= 48 frames
+        const float e0 = lane < T ? sE[lane] : -INFINITY, e1 = lane + 32 < T ? sE[lane + 32] : -INFINITY;
+        const float mx = warp_max(fmaxf(e0, e1));
+        const float p0 = lane < T ? __expf(e0 - mx) : 0.f, p1 = lane + 32 < T ? __expf(e1 - mx) : 0.f;
+        const float inv = 1.f / warp_sum(p0 + p1);
+        float* al = p.alpha + grow * T;
+        if (lane < T) { sE[lane] = p0 * inv; al[lane] = p0 * inv; }
+        if (lane + 32 < T) { sE[lane + 32] = p1 * inv; al[lane + 32] = p1 * inv; }
+      }
+      named_bar<1, 256>();
+      F2_STAMP(3);
+      // sum_t alpha_t P[b,t,:] straight out of TMEM: TMEM lane L owns gate columns [16L, 16L+16).  Warps w and w+4
+      // share a lane quarter: even 4-frame chunks go to warps 0-3, odd ones to warps 4-7.
+      float acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+      if (has_row) {
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < R2_R * 2; ++c) {
+          if ((c & 1) == half && c * 4 < T) {
+            uint32_t v[32];
+            tmem_ld32(tmem_p + (uint32_t)(c * 32), v);
+            const float4 al4 = *reinterpret_cast<const float4*>(sE + c * 4);       // zero beyond T
+            const float al[4] = {al4.x, al4.y, al4.z, al4.w};
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&v[f * 8 + k]));
+                acc[2 * k] = fmaf(al[f], x.x, acc[2 * k]);
+                acc[2 * k + 1] = fmaf(al[f], x.y, acc[2 * k + 1]);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        if (half == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sGc[(tid - 128) * F2_GCP + i] = acc[i];
+        }
+      }
+      named_bar<1, 256>();
+      F2_STAMP(4);
+      if (tid < 128) {
+        // ============================================================ LSTM cell of my row: units 4*tid .. 4*tid+3
+        if (s > 0) {
+          if (tid == 0) poll_counter(cntX, nctas * (unsigned)s);     // gh = h_s . W_hh^T is complete in global memory
+          named_bar<2, 128>();
+        }
+        F2_STAMP(5);
+        if (has_row) {
+          float pre[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pre[i] = acc[i] + sGc[tid * F2_GCP + i];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { pre[4 * q] += gx4[q].x; pre[4 * q + 1] += gx4[q].y; pre[4 * q + 2] += gx4[q].z; pre[4 * q + 3] += gx4[q].w; }
+          if (s > 0) {
+            const float4* ghr = reinterpret_cast<const float4*>(p.gh + (size_t)brow * (4 * H)) + 4 * tid;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 g4 = __ldcg(ghr + q);
+              pre[4 * q] += g4.x; pre[4 * q + 1] += g4.y; pre[4 * q + 2] += g4.z; pre[4 * q + 3] += g4.w;
+            }
+          }
+          float hn[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float ig = sigmoid_ex2(pre[4 * u]), fg = sigmoid_ex2(pre[4 * u + 1]), gg = tanh_ex2(pre[4 * u + 2]),
+                        og = sigmoid_ex2(pre[4 * u + 3]);
+            pre[4 * u] = ig; pre[4 * u + 1] = fg; pre[4 * u + 2] = gg; pre[4 * u + 3] = og;
+            cst[u] = fg * cst[u] + ig * gg;
+            hn[u] = og * tanh_ex2(cst[u]);
+          }
+          const size_t nrow = (size_t)(s + 1) * B + brow;
+          *reinterpret_cast<float4*>(p.c + nrow * H + 4 * tid) = make_float4(cst[0], cst[1], cst[2], cst[3]);
+          if (p.out_hid) *reinterpret_cast<float4*>(p.out_hid + nrow * H + 4 * tid) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          __nv_bfloat162 h01 = __floats2bfloat162_rn(hn[0], hn[1]), h23 = __floats2bfloat162_rn(hn[2], hn[3]);
+          const uint32_t w0 = *reinterpret_cast<uint32_t*>(&h01), w1 = *reinterpret_cast<uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(p.xh + nrow * K + p.F + 4 * tid) = make_uint2(w0, w1);
+          if (p.act) {
+            float4* ar = reinterpret_cast<float4*>(p.act + grow * (size_t)(4 * H)) + 4 * tid;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ar[q] = make_float4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
+          }
+          const uint32_t hloc = smem_u32(sHb + (size_t)rank * HP + 4 * tid);
+#pragma unroll
+          for (int d = 0; d < R2_CS; ++d) st_dsmem_u32x2(mapa(hloc, (uint32_t)d), w0, w1);
+        }
+        named_bar<2, 128>();
+        if (tid == 0) {
+#pragma unroll
+          for (int d = 0; d < R2_CS; ++d) mbar_arrive_remote(mapa(hb_full, (uint32_t)d));
+          if (has_row) signal_counter(cntY);
+        }
+        F2_STAMP(6);
+      }
+    }
+  } else {
+    // ================================================================= recurrent GEMM group (warps 8-11)
+    const int ge = tid - 256;                     // 0..127
+    uint32_t it_p = 0, it_c = 0;
+    for (int s = 1; s < S; ++s) {
+      if (warp == 8) {
+        if (lane == 0) {
+          poll_counter(cntY, nlive * (unsigned)s);              // h_s of every row is in xh slot s
+          asm volatile("fence.proxy.async;" ::: "memory");
+          for (int i = 0; i < F2_NKB; ++i, ++it_p) {
+            const int stage = (int)(it_p % F2_STAGES);
+            const uint32_t par = (it_p / F2_STAGES) & 1u;
+            mbar_wait(empty_bar(stage), par ^ 1u);
+            mbar_expect_tx(full_bar(stage), F2_STAGE_BYTES);
+            tma_load_2d(ring_base + stage * F2_STAGE_BYTES, &map_h, full_bar(stage), (kb0 + i) * 64, s * B);
+          }
+        }
+        __syncwarp();
+      } else if (warp == 9) {
+        if (lane == 0) {
+          constexpr uint32_t idesc = idesc_bf16(128, F2_BN);
+          if (s == 1) mbar_wait(w_bar, 0);
+          for (int i = 0; i < F2_NKB; ++i, ++it_c) {
+            const int stage = (int)(it_c % F2_STAGES);
+            const uint32_t par = (it_c / F2_STAGES) & 1u;
+            mbar_wait(full_bar(stage), par);
+            tc_fence_after();
+            const uint64_t adesc = sw128_desc(ring_base + stage * F2_STAGE_BYTES);
+            const uint64_t bdesc = sw128_desc(smem_base + i * F2_KB_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+            umma_commit(empty_bar(stage));
+          }
+          umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+      }
+      F2_STAMP_G(7);
+      // park this K-slice's partial tile [128 x 64]
+      mbar_wait(tmem_full_bar, (uint32_t)((s - 1) & 1));
+      tc_fence_after();
+      {
+        const int prow = (warp & 3) * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < F2_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_lane + (uint32_t)(c * 32), v);
+          float4* dst = reinterpret_cast<float4*>(sPartial + (size_t)prow * F2_PS + c * 32);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                      __uint_as_float(v[j + 3]));
+        }
+      }
+      tc_fence_before();
+      named_bar<3, 128>();
+      if (ge == 0) {
+#pragma unroll
+        for (int d = 0; d < R2_CS; ++d) mbar_arrive_remote(mapa(part_full, (uint32_t)d));
+      }
+      mbar_wait_cl(part_full, (uint32_t)((s - 1) & 1));
+      F2_STAMP_G(8);
+      {
+        // rank r finishes rows [32r, 32r+32): thread = (row, 16 columns); partials summed in rank order
+        const int rl = ge >> 2, cq = ge & 3;
+        const int row = rank * 32 + rl;
+        const uint32_t pbase = smem_u32(sPartial + (size_t)row * F2_PS + cq * 16);
+        float4 a4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int sr = 0; sr < R2_CS; ++sr) {
+          const uint32_t src = mapa(pbase, (uint32_t)sr);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t4 = ld_dsmem4(src + 16u * q);
+            a4[q].x += t4.x; a4[q].y += t4.y; a4[q].z += t4.z; a4[q].w += t4.w;
+          }
+        }
+        if (row < B) {
+          float4* out = reinterpret_cast<float4*>(p.gh + (size_t)row * (4 * H) + n0 + cq * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) out[q] = a4[q];
+        }
+      }
+      named_bar<3, 128>();
+      if (ge == 0) signal_counter(cntX);
+      F2_STAMP_G(9);
+    }
+  }
+#undef F2_STAMP
+#undef F2_STAMP_G
+
+  // ---------------------------------------------------------------- teardown (no CTA may exit while a peer can still
+  // address its shared memory)
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFnR2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnR2 encode_fn_r2() {
+  static EncodeTiledFnR2 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFnR2>(q);
+  });
+  return fn;
+}
+int r2_make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+  EncodeTiledFnR2 enc = encode_fn_r2();
+  MVC_CHECK(enc, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MVC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+static size_t recur2_fwd_smem() {
+  return 1024 + F2_B_BYTES + F2_RING_BYTES + sizeof(float) * 128 * F2_PS + (size_t)(F2_UPR + R2_CS) * F2_HP * 2 +
+         sizeof(float) * (3 * R2_A + 64 + 128 * F2_GCP) + 8 * (2 * F2_STAGES + 5) + 16;
+}
+size_t recur2_bwd_smem();
+const void* recur2_bwd_kernel_ptr();
+
+// Both persistent kernels need their 32 clusters of 4 CTAs co-resident (the counters and mbarriers spin): checked once
+// per process with the occupancy calculator; MVC_B200_PERSISTENT=0 forces the launch chain.
+bool recur2_supported(int B, int T, int F, int H, int A) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("MVC_B200_PERSISTENT");
+    const char* e2 = getenv("MVC_B200_RECUR2");          // =0: keep the first-generation persistent kernels (A/B runs)
+    disabled = ((e && e[0] == '0') || (e2 && e2[0] == '0')) ? 1 : 0;
+  }
+  if (disabled) return false;
+  if (!(B >= 1 && B <= 128 && T >= 1 && T <= 8 * R2_R && F >= 8 && F % 8 == 0 && H == R2_H && A == R2_A)) return false;
+  static std::mutex mu;
+  static int ok = -1;
+  std::lock_guard<std::mutex> lk(mu);
+  if (ok < 0) {
+    ok = 1;
+    const void* kerns[2] = {(const void*)recur2_fwd_kernel, recur2_bwd_kernel_ptr()};
+    const size_t smems[2] = {recur2_fwd_smem(), recur2_bwd_smem()};
+    for (int i = 0; i < 2 && ok; ++i) {
+      if (smems[i] > 227 * 1024 ||
+          cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smems[i]) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        break;
+      }
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(R2_CS);
+      cfg.blockDim = dim3(R2_THREADS);
+      cfg.dynamicSmemBytes = smems[i];
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = R2_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kerns[i], &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      if (n < R2_H / 16) ok = 0;
+    }
+  }
+  return ok == 1;
+}
+
+static long long* g_recur2_prof = nullptr;
+void r2_set_fwd_prof(long long* p) { g_recur2_prof = p; }
+
+int recur2_fwd_launch(const Recur2FwdParams& p, const void* whh_um, int64_t ldw, cudaStream_t st) {
+  MVC_CHECK(recur2_supported(p.B, p.T, p.F, R2_H, R2_A), "persistent recurrence: unsupported dims");
+  CUtensorMap mh, mw;
+  // A operand: the h halves of the xh slots, [(S+1)*B rows, H cols], row pitch K
+  MVC_TRY(r2_make_map(p.xh + p.F, (int64_t)(p.S + 1) * p.B, R2_H, p.K, 128, &mh));
+  MVC_TRY(r2_make_map(whh_um, (int64_t)4 * R2_H, R2_H, ldw, F2_BN, &mw));
+  MVC_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned) * 32, st));
+  const size_t smem = recur2_fwd_smem();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(R2_H / 16) * R2_CS);
+  cfg.blockDim = dim3(R2_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = R2_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  Recur2FwdParams pp = p;
+  pp.prof = g_recur2_prof;
+  void* args[] = {(void*)&mh, (void*)&mw, (void*)&pp};
+  ProfScope prof(PK_STEP_FUSED, p.B, p.S, p.K, st);
+  MVC_CUDA(cudaLaunchKernelExC(&cfg, (const void*)recur2_fwd_kernel, args));
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ ctx rows (backward only)
+// ctx[s,b,:] = sum_t alpha[s,b,t] feats[b,t,:] for all s: block = (feature chunk of 512, row b); alpha[.,b,.] staged in
+// shared memory, every thread owns 2 adjacent features and 8 steps at a time.
+constexpr int CR_S = 8;
+__global__ void __launch_bounds__(256)
+r2_ctx_rows_kernel(const __nv_bfloat16* __restrict__ feats, const float* __restrict__ alpha, int B, int T, int F, int S,
+                   __nv_bfloat16* __restrict__ xh, int64_t ldx) {
+  extern __shared__ float sAl[];                  // [S][T]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < S * T; i += blockDim.x) {
+    const int s = i / T, t = i - s * T;
+    sAl[i] = alpha[((size_t)s * B + b) * T + t];
+  }
+  __syncthreads();
+  const int f = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (f >= F) return;
+  const __nv_bfloat162* kr = reinterpret_cast<const __nv_bfloat162*>(feats + (size_t)b * T * F + f);
+  for (int s0 = 0; s0 < S; s0 += CR_S) {
+    float ax[CR_S], ay[CR_S];
+#pragma unroll
+    for (int i = 0; i < CR_S; ++i) { ax[i] = 0.f; ay[i] = 0.f; }
+    for (int t = 0; t < T; ++t) {
+      const float2 k2 = __bfloat1622float2(kr[(size_t)t * (F / 2)]);
+#pragma unroll
+      for (int i = 0; i < CR_S; ++i) {
+        const float a = (s0 + i < S) ? sAl[(s0 + i) * T + t] : 0.f;
+        ax[i] = fmaf(a, k2.x, ax[i]);
+        ay[i] = fmaf(a, k2.y, ay[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CR_S; ++i)
+      if (s0 + i < S)
+        *reinterpret_cast<__nv_bfloat162*>(xh + ((size_t)(s0 + i) * B + b) * ldx + f) = __floats2bfloat162_rn(ax[i], ay[i]);
+  }
+}
+
+int r2_ctx_rows(const void* feats_bf16, const float* alpha, int B, int T, int F, int S, void* xh_bf16, int64_t ldx,
+                cudaStream_t st) {
+  MVC_CHECK(F % 2 == 0 && (size_t)S * T * sizeof(float) <= 48 * 1024, "r2_ctx_rows: unsupported dims S=%d T=%d F=%d", S, T, F);
+  dim3 grid((unsigned)cdiv(F, 512), (unsigned)B);
+  r2_ctx_rows_kernel<<<grid, 256, sizeof(float) * S * T, st>>>((const __nv_bfloat16*)feats_bf16, alpha, B, T, F, S,
+                                                              (__nv_bfloat16*)xh_bf16, ldx);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mvc

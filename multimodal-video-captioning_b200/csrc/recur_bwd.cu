@@ -649,7 +649,9 @@ int recur_bwd_launch(const RecurBwdParams& p, const void* wcatT, cudaStream_t st
 
 }  // namespace mvc
 
+namespace mvc { void r2_set_bwd_prof(long long* p); }
 extern "C" int mvc_debug_set_recur_bwd_prof(long long* dev_buf) {
   mvc::g_recur_bwd_prof = dev_buf;
+  mvc::r2_set_bwd_prof(dev_buf);
   return 0;
 }

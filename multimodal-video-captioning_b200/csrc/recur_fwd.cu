@@ -626,7 +626,9 @@ int recur_fwd_launch(const RecurFwdParams& p, const void* wcat, cudaStream_t st)
 }  // namespace mvc
 
 // debugging / profiles: device buffer of >= 10 * steps int64 receiving CTA 0's phase timestamps (null = off)
+namespace mvc { void r2_set_fwd_prof(long long* p); }
 extern "C" int mvc_debug_set_recur_prof(long long* dev_buf) {
   mvc::g_recur_prof = dev_buf;
+  mvc::r2_set_fwd_prof(dev_buf);
   return 0;
 }

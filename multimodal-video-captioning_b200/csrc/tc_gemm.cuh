@@ -23,6 +23,8 @@ struct TcEpilogue {
   const float* bias;          // also the (permuted) gate bias in cell mode, may be null
   __nv_bfloat16* Cb;
   int64_t ldcb;
+  int cb_f16;                 // the 16-bit copy is IEEE fp16 (saturating) instead of bf16: 3 more mantissa bits for
+                              // the projected keys of the persistent recurrence kernels (recur2.cuh)
   // fused row arg-max (mode == TC_MODE_ARGMAX): per (row, 256-column tile) partial maximum of acc + bias
   float* amax_val;            // [ceil(N/256), M]
   int* amax_idx;              // [ceil(N/256), M]
@@ -91,8 +93,10 @@ constexpr int kGateU = 16;
 __host__ __device__ inline int gate_col(int perm, int H, int gate, int j) {
   return perm ? (j >> 4) * 64 + gate * 16 + (j & 15) : gate * H + j;
 }
-// inverse: natural row (gate*H + j) of permuted column c
+// inverse: natural row (gate*H + j) of permuted column c.  H > 0: the tile-interleaved order above; H < 0 selects the
+// UNIT-MAJOR order of the persistent recurrence kernels (recur2.cuh) for hidden size -H: column 4j + gate.
 __host__ __device__ inline int gate_unperm(int H, int c) {
+  if (H < 0) return (c & 3) * (-H) + (c >> 2);
   const int blk = c >> 6, gate = (c >> 4) & 3, u = c & 15;
   return gate * H + blk * 16 + u;
 }

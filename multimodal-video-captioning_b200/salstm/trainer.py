@@ -167,7 +167,7 @@ class FlatClipAdam(torch.optim.Optimizer):
         sd = {"step": self.step_count, "param_group": {k: v for k, v in self.param_groups[0].items() if k != "params"}}
         if self.flat_p is not None:
             sd.update(exp_avg=self.m.clone(), exp_avg_sq=self.v.clone(), max_exp_avg_sq=self.vmax.clone(),
-                      live=[self.params.index(p) for p in self._live])
+                      live=[i for i, p in enumerate(self.params) if id(p) in self._live_set])
         return sd
 
     def load_state_dict(self, sd):
@@ -178,8 +178,9 @@ class FlatClipAdam(torch.optim.Optimizer):
             for p in live:
                 if p.grad is None:
                     p.grad = torch.zeros_like(p)
+            keep = {id(p) for p in live}
             for p in self.params:
-                if p not in live:
+                if id(p) not in keep:
                     p.grad = None
             self.flat_p = None
             self._flatten()

@@ -637,13 +637,14 @@ def test_full_width_wrappers_golden(dev, kind, rec_type):
 def test_bf16_path_vs_fp64_oracle(dev, rec_type, inputs):
     """bf16 tensor-core path against the oracle run in fp64 (default init, no peaky logits).
 
-    "unit": features scaled to O(1) (audio/255, visual/10).  Gradient direction must agree to
-    cosine >= 0.999 and norms to 5 %.
-    "raw": the loader's raw magnitudes (audio up to 255, captioning.py normalize_inputs=False).  Gate
-    pre-activations are then ~+-36 with bf16 rounding error ~0.1, and tanh'/sigmoid' of the few
-    unsaturated units move by ~10-20 % -- measured cosine 0.93 on W_ih, 0.96-0.98 on the attention
-    parameters: a property of bf16 on unnormalised features, not of the kernels (the fp32 path on the same
-    inputs meets rtol 1e-3, test_full_width_wrappers_golden).  Bound: cosine >= 0.9, norms within 20 %."""
+    "unit": features scaled to O(1) (audio/255, visual/10).  Gradient direction must agree with the EXACT fp64
+    oracle to cosine >= 0.999 and norms to 5 %.
+    "raw": the loader's raw magnitudes (audio up to 255, captioning.py normalize_inputs=False).  Gate pre-activations
+    are then ~+-36, and merely ROUNDING THE OPERANDS (weights, features) to bf16 -- which is what "bf16 compute" means --
+    moves tanh'/sigmoid' of the few unsaturated units by 10-20 %: the fp64 oracle evaluated on bf16-rounded operands
+    has cosine 0.69-0.93 against the exact one at this size (tools/r2_ab.py).  The kernels are therefore held to the
+    model they actually compute: the fp64 oracle ON THE bf16-ROUNDED OPERANDS, cosine >= 0.999 / norms 5 % (measured
+    0.99997), and to the exact oracle only loosely (cosine >= 0.5: same direction)."""
     from models import AVCaptioning
     import losses as L
     B, T, Lc, V = 6, 9, 8, 211
@@ -658,23 +659,33 @@ def test_bf16_path_vs_fp64_oracle(dev, rec_type, inputs):
     terms = L.ModalityWiseReconstructionLoss(out, caps.to(dev), audio.to(dev), arec, visual.to(dev), vrec, 0.0005, 0.00005,
                                              0.5, rec_type)
     terms[0].backward()
-    pd = {k: v.double().requires_grad_() for k, v in p.items()}
-    o_out, o_ar, o_vr = O.av_forward(pd, audio.double(), visual.double(), caps, 1.0, rec_type, hoist=True)
-    o_terms = O.modality_wise_loss(o_out, caps, audio.double(), o_ar, visual.double(), o_vr, 0.0005, 0.00005, 0.5, rec_type)
-    o_terms[0].backward()
+
+    def oracle(params, a, v):
+        pd = {k: t.double().requires_grad_() for k, t in params.items()}
+        o_out, o_ar, o_vr = O.av_forward(pd, a.double(), v.double(), caps, 1.0, rec_type, hoist=True)
+        o_terms = O.modality_wise_loss(o_out, caps, audio.double(), o_ar, visual.double(), o_vr, 0.0005, 0.00005, 0.5, rec_type)
+        o_terms[0].backward()
+        return pd, o_out, o_vr, o_terms
+
+    pd, o_out, o_vr, o_terms = oracle(p, audio, visual)
     close(out, o_out, atol=5e-2, rtol=5e-2)
     close(terms[0], o_terms[0], rtol=2e-2, atol=1e-3)
     if rec_type != "none":
         close(vrec, o_vr, atol=5e-2, rtol=5e-2)
-    cmin, ntol = (0.999, 5e-2) if inputs == "unit" else (0.9, 0.2)
+    if inputs == "raw":
+        # the decoder's operands as the bf16 path sees them (reconstructor weights likewise)
+        pr, _, _, _ = oracle({k: t.bfloat16().float() for k, t in p.items()}, audio.bfloat16().float(), visual.bfloat16().float())
     bad = []
     for k, v in model.named_parameters():
         if pd[k].grad is None:
             continue
-        c = cos(v.grad, pd[k].grad)
-        n1, n2 = float(v.grad.norm()), float(pd[k].grad.norm())
-        if c < cmin or abs(n1 - n2) > ntol * n2 + 1e-7:
+        ref = pd[k].grad if inputs == "unit" else pr[k].grad
+        c = cos(v.grad, ref)
+        n1, n2 = float(v.grad.norm()), float(ref.norm())
+        if c < 0.999 or abs(n1 - n2) > 5e-2 * n2 + 1e-7:
             bad.append(f"{k}: cosine {c:.5f}, norm {n1:.4e} vs {n2:.4e}")
+        if inputs == "raw" and cos(v.grad, pd[k].grad) < 0.5:
+            bad.append(f"{k}: cosine {cos(v.grad, pd[k].grad):.5f} against the exact oracle")
     assert not bad, "\n".join(bad)
 
 
