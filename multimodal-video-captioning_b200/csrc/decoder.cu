@@ -50,7 +50,7 @@ struct DecWs {
   float* hzero;   // [B, H] zeros (c_0 / fp32 h_0)
   unsigned* sync; // grid-barrier counters of the persistent recurrence kernels
   void* P;        // [B*T, 4H] fp16: keys . W_ih[:, E:]^T, unit-major gate columns (recur2 path)
-  float* gh;      // [128, 4H]  h_s . W_hh^T of the current step (recur2 path)
+  float* gh;      // [4, 128, 4H]  K-slice partials of h_s . W_hh^T of the current step (recur2 path)
   size_t bytes;
 };
 
@@ -124,9 +124,9 @@ static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
   w.gx = ar.take<float>(S * B * 4 * H);
   w.embtab = ar.take<float>(V * 4 * H);
   w.hzero = ar.take<float>(B * H);
-  w.sync = ar.take<unsigned>(128);
+  w.sync = ar.take<unsigned>(1024);   // recur1: [0,32); recur2 forward flags: [256,512); recur2 backward flags: [512,768)
   w.P = bf ? ar.take<char>(B * T * 4 * H * 2) : nullptr;
-  w.gh = bf ? ar.take<float>(128 * 4 * H) : nullptr;
+  w.gh = bf ? ar.take<float>(4 * 128 * 4 * H) : nullptr;
   w.bytes = ar.off + 256;
   return w;
 }
@@ -402,7 +402,7 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
     rp.P = (const __nv_bfloat16*)w.P; rp.uk = w.uk; rp.attW = (const __nv_bfloat16*)w.W;
     rp.att_b = p->att_b; rp.att_w = p->att_w; rp.gx = w.gx;
     rp.xh = (__nv_bfloat16*)w.xh; rp.c = w.c; rp.act = w.act; rp.alpha = w.alpha; rp.wq_out = w.wq;
-    rp.out_hid = out_hid; rp.gh = w.gh; rp.sync = w.sync + 32;
+    rp.out_hid = out_hid; rp.gh = w.gh; rp.sync = w.sync + 256;
     MVC_TRY(recur2_fwd_launch(rp, cptr(w.wcat, F, 2), ldx, st));
   } else if (persistent && all_tf) {
     // the whole teacher-forced time loop in ONE persistent cluster-cooperative launch (recur_fwd.cu)
@@ -490,7 +490,7 @@ struct DecBwdWs {
   void* dwq_b;      // [S*B, A]
   void* attWT;      // [H, A]
   void* whhT;       // [H, 4H] W_hh^T, unit-major gate columns (recur2 path)
-  float* ghb;       // [128, H] dG_s . W_hh of the current step (recur2 path)
+  float* ghb;       // [4, 128, H] K-slice partials of dG_s . W_hh of the current step (recur2 path)
   size_t bytes;
 };
 
@@ -527,7 +527,7 @@ static DecBwdWs dec_bwd_layout(const MvcDecoderDims* d, void* base) {
     w.dwq_b = ar.take<char>(S * B * A * 2);
     w.attWT = ar.take<char>(H * A * 2);
     w.whhT = ar.take<char>(H * 4 * H * 2);
-    w.ghb = ar.take<float>(128 * H);
+    w.ghb = ar.take<float>(4 * 128 * H);
   }
   w.bytes = ar.off + 256;
   return w;
@@ -629,7 +629,7 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     rp.act = w.act; rp.c = w.c; rp.wq = w.wq; rp.alpha = w.alpha; rp.dh_ext = q.dhall;
     rp.attWT = (const __nv_bfloat16*)q.attWT;
     rp.dG = q.dG; rp.dG_b = (__nv_bfloat16*)q.dG_b; rp.dwq = q.dwq; rp.dwq_b = (__nv_bfloat16*)q.dwq_b;
-    rp.duk = q.duk; rp.dwpart = q.dwpart; rp.ghb = q.ghb; rp.sync = w.sync + 64;
+    rp.duk = q.duk; rp.dwpart = q.dwpart; rp.ghb = q.ghb; rp.sync = w.sync + 512;
     MVC_TRY(recur2_bwd_launch(rp, q.whhT, st));
   } else if (persistent_bwd) {
     // the whole BPTT time loop in ONE persistent cluster-cooperative launch (recur_bwd.cu)

@@ -9,12 +9,12 @@
 //     query-projection backward         : attention.W^T units [128r, 128r+128) in shared memory:
 //         dh_att[4 rows, my units] = dwq . W (mma.sync), scattered to the row owners over DSMEM;
 //     recurrent GEMM                    : W_hh^T rows [16c, 16c+16) x gate-K-slice r resident in shared memory;
-//         ghb[128, 16] partial = dG_s[:, slice] . W_hh on tcgen05 (A = bf16 gate gradients by TMA), K-slice partials
-//         reduced over DSMEM in rank order, written to global `ghb`.
+//         ghb[128, 16] partial = dG_s[:, slice] . W_hh on tcgen05 (A = bf16 gate gradients by TMA); each K-slice partial
+//         goes straight from TMEM to its own plane of global `ghb` [4][128][H], summed by the row owner in rank order.
 //   step s = S-1 .. 0:   compute warps 0-7                         |  GEMM warps 8-11
 //     wait X (ghb of step s+1) and dh_att(s+1) (mbarrier)          |  wait Y >= rows*(S-s)   (dG_s of every row)
-//     dh_{s+1} = dh_ext + ghb + dh_att; cell backward -> dG_s; Y++ |  TMA dG_s k-slices -> tcgen05.mma -> park
-//     dalpha (TMEM), de, dpre, dwq_s -> cluster (DSMEM, mbarrier)  |  mbarrier (4 partials) -> reduce -> ghb; X++
+//     dh_{s+1} = dh_ext + ghb + dh_att; cell backward -> dG_s; Y++ |  TMA dG_s k-slices -> tcgen05.mma -> TMEM
+//     dalpha (TMEM), de, dpre, dwq_s -> cluster (DSMEM, mbarrier)  |  -> ghb plane r; X++
 //     dh_att slices -> owners (DSMEM, mbarrier)                    |
 //   All sums have a fixed order: deterministic.
 #include <cuda_fp16.h>
@@ -34,7 +34,6 @@ constexpr int B2_B_BYTES = B2_NKB * B2_KB_BYTES;     // 16384
 constexpr int B2_STAGE_BYTES = 128 * 128;
 constexpr int B2_STAGES = 6;
 constexpr int B2_RING_BYTES = B2_STAGES * B2_STAGE_BYTES;
-constexpr int B2_PS = B2_BN + 4;                     // partial pitch (floats)
 constexpr int B2_AP = R2_A + 8;                      // bf16 pitch of W^T slice rows / dwq exchange rows
 constexpr int B2_UPR = R2_H / R2_CS;                 // 128 hidden units per rank
 
@@ -47,8 +46,7 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
   const int B = p.B, T = p.T, S = p.S;
 
   uint8_t* ring = smem + B2_B_BYTES;
-  float* sPartial = reinterpret_cast<float*>(ring + B2_RING_BYTES);                       // [128][B2_PS]
-  __nv_bfloat16* sWT = reinterpret_cast<__nv_bfloat16*>(sPartial + 128 * B2_PS);          // [UPR][AP]  W^T slice
+  __nv_bfloat16* sWT = reinterpret_cast<__nv_bfloat16*>(ring + B2_RING_BYTES);            // [UPR][AP]  W^T slice
   __nv_bfloat16* sDq = sWT + (size_t)UPR * AP;                                            // [4][AP] dwq of the cluster's rows
   float* sDh = reinterpret_cast<float*>(sDq + R2_CS * AP);                                // [H] dh_att of my row
   float* sDg = sDh + H;                                                                   // [4H] dG_s of my row
@@ -64,10 +62,9 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
   auto empty_bar = [&](int s) { return bar0 + 8u * (B2_STAGES + s); };
   const uint32_t tmem_full_bar = bar0 + 8u * (2 * B2_STAGES);
   const uint32_t w_bar = tmem_full_bar + 8u;
-  const uint32_t dq_full = w_bar + 8u;          // 4 arrivals: the four rows' dwq_s are in my exchange buffer
-  const uint32_t dh_full = dq_full + 8u;        // 4 arrivals: every rank delivered its units of my row's dh_att
-  const uint32_t part_full = dh_full + 8u;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * B2_STAGES + 5);
+  const uint32_t dq_full = w_bar + 8u;          // 32 arrivals (8 warps x 4 owners): the four rows' dwq_s are in my exchange buffer
+  const uint32_t dh_full = dq_full + 8u;        // 32 arrivals (8 warps x 4 ranks): my row's dh_att is complete in sDh
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * B2_STAGES + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_rank();
@@ -80,8 +77,11 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
   const uint32_t ring_base = smem_base + B2_B_BYTES;
   const unsigned nctas = gridDim.x;
   const unsigned nlive = (unsigned)(B < (int)gridDim.x ? B : (int)gridDim.x);
-  unsigned* cntY = p.sync;
-  unsigned* cntX = p.sync + 16;
+  unsigned* cntY = p.sync;                        // Y[r] at cntY + 32 r: arrivals of the row owners of cluster rank r
+  unsigned* cntX = p.sync + 128;                  // X[r] at cntX + 32 r: arrivals of the GEMM groups of cluster rank r
+  // live rows per cluster rank (row b is owned by CTA b: rank b % 4), CTAs per rank
+  const unsigned nl0 = (unsigned)((nlive + 3) / 4), nl1 = (unsigned)((nlive + 2) / 4), nl2 = (unsigned)((nlive + 1) / 4),
+                 nl3 = (unsigned)(nlive / 4), ncr = nctas / R2_CS;
 
   // ---------------------------------------------------------------- setup
   if (warp == 8 && lane == 0) {
@@ -93,9 +93,8 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(w_bar, 1);
-    mbar_init(dq_full, R2_CS);
-    mbar_init(dh_full, R2_CS);
-    mbar_init(part_full, R2_CS);
+    mbar_init(dq_full, R2_CS * 8);
+    mbar_init(dh_full, R2_CS * 8);
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -200,14 +199,22 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
         float dh[4] = {dhe4.x, dhe4.y, dhe4.z, dhe4.w};
         if (j > 0) {
           // dh_{s+1} += dG_{s+1} . W_hh (global, all clusters) + dwq_{s+1} . W (my cluster)
-          if (tid == 0) poll_counter(cntX, nctas * (unsigned)j);
+          if (tid == 0) poll_counters4(cntX, ncr * j, ncr * j, ncr * j, ncr * j);
           named_bar<2, 128>();
+          float4 g4[R2_CS];
+          if (has_row) {
+#pragma unroll
+            for (int r = 0; r < R2_CS; ++r)
+              g4[r] = __ldcg(reinterpret_cast<const float4*>(p.ghb + ((size_t)r * 128 + brow) * H) + tid);
+          }
           mbar_wait_cl(dh_full, (uint32_t)((j - 1) & 1));
           B2_STAMP(1);
           if (has_row) {
-            const float4 g4 = __ldcg(reinterpret_cast<const float4*>(p.ghb + (size_t)brow * H) + tid);
             const float4 d4 = *reinterpret_cast<const float4*>(sDh + 4 * tid);
-            dh[0] += g4.x + d4.x; dh[1] += g4.y + d4.y; dh[2] += g4.z + d4.z; dh[3] += g4.w + d4.w;
+            float4 t4 = g4[0];
+#pragma unroll
+            for (int r = 1; r < R2_CS; ++r) { t4.x += g4[r].x; t4.y += g4[r].y; t4.z += g4[r].z; t4.w += g4[r].w; }
+            dh[0] += t4.x + d4.x; dh[1] += t4.y + d4.y; dh[2] += t4.z + d4.z; dh[3] += t4.w + d4.w;
           }
         }
         if (has_row) {
@@ -224,24 +231,25 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
             dg[4 * u + 3] = dh[u] * tc * og * (1.f - og);
             dcr[u] = dct * fg;
           }
-          float4* d32 = reinterpret_cast<float4*>(p.dG + grow * (size_t)(4 * H)) + 4 * tid;
+          // publish the bf16 row FIRST (A operand of the recurrent GEMM) and the fp32 copy for the attention backward
           float4* dsm = reinterpret_cast<float4*>(sDg) + 4 * tid;
           uint32_t pk[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 v4 = make_float4(dg[4 * q], dg[4 * q + 1], dg[4 * q + 2], dg[4 * q + 3]);
-            d32[q] = v4;
-            dsm[q] = v4;
-            __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y), hi = __floats2bfloat162_rn(v4.z, v4.w);
+            dsm[q] = make_float4(dg[4 * q], dg[4 * q + 1], dg[4 * q + 2], dg[4 * q + 3]);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(dg[4 * q], dg[4 * q + 1]), hi = __floats2bfloat162_rn(dg[4 * q + 2], dg[4 * q + 3]);
             pk[2 * q] = *reinterpret_cast<uint32_t*>(&lo);
             pk[2 * q + 1] = *reinterpret_cast<uint32_t*>(&hi);
           }
           uint4* d16 = reinterpret_cast<uint4*>(p.dG_b + grow * (size_t)(4 * H)) + 2 * tid;
           d16[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           d16[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          named_bar<2, 128>();
+          if (tid == 0) signal_counter(cntY + R2_CNT_STRIDE * rank);     // dG_s of my row is in global memory
+          float4* d32 = reinterpret_cast<float4*>(p.dG + grow * (size_t)(4 * H)) + 4 * tid;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d32[q] = make_float4(dg[4 * q], dg[4 * q + 1], dg[4 * q + 2], dg[4 * q + 3]);
         }
-        named_bar<2, 128>();
-        if (tid == 0 && has_row) signal_counter(cntY);          // dG_s of my row is published
       }
       named_bar<1, 256>();                          // sDg / sAl visible to all eight warps
       B2_STAMP(2);
@@ -254,12 +262,12 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
           const float4 v4 = *(reinterpret_cast<const float4*>(sDg) + 4 * L + q);
           dg[4 * q] = v4.x; dg[4 * q + 1] = v4.y; dg[4 * q + 2] = v4.z; dg[4 * q + 3] = v4.w;
         }
-        float pt[16];
+        float pt[32];                               // 24 live: chunk slot cs = i / 4 (chunk 2 cs + half), frame i % 4
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pt[i] = 0.f;
+        for (int i = 0; i < 32; ++i) pt[i] = 0.f;
         tc_fence_after();
 #pragma unroll
-        for (int cs = 0; cs < R2_R / 2; ++cs) {
+        for (int cs = 0; cs < R2_R; ++cs) {
           const int c = 2 * cs + half;
           if (c * 4 < T) {
             uint32_t v[32];
@@ -278,133 +286,126 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
           }
         }
         tc_fence_before();
-        // butterfly: after the five rounds lane l holds the warp total of value l >> 1
+        // butterfly over the warp: after the five rounds lane l holds the warp total of value l
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool up = lane & 16;
-          const float keep = up ? pt[8 + i] : pt[i], give = up ? pt[i] : pt[8 + i];
-          pt[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
-        }
+        for (int w = 16; w >= 1; w >>= 1) {
+          const bool up = (lane & w) != 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool up = lane & 8;
-          const float keep = up ? pt[4 + i] : pt[i], give = up ? pt[i] : pt[4 + i];
-          pt[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+          for (int i = 0; i < w; ++i) {
+            const float keep = up ? pt[w + i] : pt[i], give = up ? pt[i] : pt[w + i];
+            pt[i] = keep + __shfl_xor_sync(0xffffffffu, give, w);
+          }
         }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const bool up = lane & 4;
-          const float keep = up ? pt[2 + i] : pt[i], give = up ? pt[i] : pt[2 + i];
-          pt[i] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
-        }
-        {
-          const bool up = lane & 2;
-          const float keep = up ? pt[1] : pt[0], give = up ? pt[0] : pt[1];
-          pt[0] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
-        }
-        pt[0] += __shfl_xor_sync(0xffffffffu, pt[0], 1);
-        const int vi = lane >> 1;                   // value index 0..15: chunk slot vi / 4, frame vi % 4
-        if ((lane & 1) == 0 && vi < 4 * (R2_R / 2)) {
-          const int t = (2 * (vi >> 2) + half) * 4 + (vi & 3);
+        if (lane < 4 * R2_R) {
+          const int t = (2 * (lane >> 2) + half) * 4 + (lane & 3);
           sDa[warp * 64 + t] = pt[0];
         }
       }
       named_bar<1, 256>();
-      if (has_row && warp == 0) {
-        // softmax Jacobian: de_t = alpha_t (dalpha_t - sum alpha dalpha); frame t was covered by the warp group of
-        // its chunk parity ((t/4) & 1)
-        float da[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int t = lane + 32 * e;
-          const int w0 = ((t >> 2) & 1) * 4;
-          da[e] = sDa[(w0 + 0) * 64 + t] + sDa[(w0 + 1) * 64 + t] + sDa[(w0 + 2) * 64 + t] + sDa[(w0 + 3) * 64 + t];
-        }
-        const float a0 = sAl[lane], a1 = sAl[lane + 32];            // zero beyond T
-        const float dot = warp_sum(a0 * da[0] + a1 * da[1]);
-        sDe[lane] = a0 * (da[0] - dot);
-        sDe[lane + 32] = a1 * (da[1] - dot);
-      }
-      named_bar<1, 256>();
       B2_STAMP(3);
       if (has_row) {
+        // softmax Jacobian de_t = alpha_t (dalpha_t - sum alpha dalpha), redundantly in every warp (no barrier): lane l
+        // keeps frames l and l + 32; frame t was covered by the warp group of its chunk parity ((t/4) & 1)
+        float de2[2];
+        {
+          float da[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int t = lane + 32 * e;
+            const int w0 = ((t >> 2) & 1) * 4;
+            da[e] = sDa[(w0 + 0) * 64 + t] + sDa[(w0 + 1) * 64 + t] + sDa[(w0 + 2) * 64 + t] + sDa[(w0 + 3) * 64 + t];
+          }
+          const float a0 = sAl[lane], a1 = sAl[lane + 32];            // zero beyond T
+          const float dot = warp_sum(a0 * da[0] + a1 * da[1]);
+          de2[0] = a0 * (da[0] - dot);
+          de2[1] = a1 * (da[1] - dot);
+        }
         float wv[AV], sq[AV];
 #pragma unroll
         for (int k = 0; k < AV; ++k) { wv[k] = sWv[lane + 32 * k]; sq[k] = 0.f; }
 #pragma unroll
         for (int r = 0; r < R2_R; ++r) {
-          const int t = warp + r * 8;
-          if (t < T) {
-            const float de = sDe[t];
+          const int t = warp + r * 8;               // warp-uniform; t < 48
+          const float de = __shfl_sync(0xffffffffu, t < 32 ? de2[0] : de2[1], t & 31);     // zero beyond T
 #pragma unroll
-            for (int k = 0; k < AV; ++k) {
-              const float th = tanh_fast(qb[k] + ur[r][k]);
-              const float dpre = de * wv[k] * (1.f - th * th);
-              sq[k] += dpre;
-              dwr[k] = fmaf(de, th, dwr[k]);
-              dur[r][k] += dpre;
-            }
+          for (int k = 0; k < AV; ++k) {
+            const float th = tanh_fast(qb[k] + ur[r][k]);
+            const float dpre = de * wv[k] * (1.f - th * th);
+            sq[k] += dpre;
+            dwr[k] = fmaf(de, th, dwr[k]);
+            dur[r][k] += dpre;
           }
         }
 #pragma unroll
         for (int k = 0; k < AV; ++k) sAcc[warp * A + lane + 32 * k] = sq[k];
       }
       named_bar<1, 256>();
-      // dwq of my row: fixed-order sum over the 8 warps; fp32 + bf16 to global, bf16 into every rank's exchange row
-      {
-        float qsum = 0.f;
-        if (has_row) {
+      // dwq of my row: fixed-order sum over the 8 warps; bf16 into every rank's exchange row (critical path) first,
+      // fp32 + bf16 copies for the weight-gradient GEMMs to global afterwards
+      float qsum = 0.f;
+      if (has_row) {
 #pragma unroll
-          for (int w = 0; w < 8; ++w) qsum += sAcc[w * A + tid];
-          p.dwq[grow * A + tid] = qsum;
-          p.dwq_b[grow * A + tid] = __float2bfloat16(qsum);
-        }
-        if (s > 0) {
-          const float other = __shfl_down_sync(0xffffffffu, qsum, 1);
-          if ((tid & 1) == 0) {
-            __nv_bfloat162 pk2 = __floats2bfloat162_rn(qsum, other);
-            const uint32_t bits = *reinterpret_cast<uint32_t*>(&pk2);
-            const uint32_t local = smem_u32(sDq + (size_t)rank * AP + tid);
+        for (int w = 0; w < 8; ++w) qsum += sAcc[w * A + tid];
+      }
+      if (s > 0) {
+        const float other = __shfl_down_sync(0xffffffffu, qsum, 1);
+        if ((tid & 1) == 0) {
+          __nv_bfloat162 pk2 = __floats2bfloat162_rn(qsum, other);
+          const uint32_t bits = *reinterpret_cast<uint32_t*>(&pk2);
+          const uint32_t local = smem_u32(sDq + (size_t)rank * AP + tid);
 #pragma unroll
-            for (int d = 0; d < R2_CS; ++d) st_dsmem_u32(mapa(local, (uint32_t)d), bits);
-          }
+          for (int d = 0; d < R2_CS; ++d) st_dsmem_u32(mapa(local, (uint32_t)d), bits);
         }
+        __syncwarp();
+        if (lane < R2_CS) mbar_arrive_remote(mapa(dq_full, (uint32_t)lane));
+      }
+      if (has_row) {
+        p.dwq[grow * A + tid] = qsum;
+        p.dwq_b[grow * A + tid] = __float2bfloat16(qsum);
       }
       B2_STAMP(4);
       if (s > 0) {
-        named_bar<1, 256>();
-        if (tid == 0) {
-#pragma unroll
-          for (int d = 0; d < R2_CS; ++d) mbar_arrive_remote(mapa(dq_full, (uint32_t)d));
-        }
         mbar_wait_cl(dq_full, (uint32_t)(j & 1));   // the four rows' dwq_s are in sDq
         B2_STAMP(5);
         // dh_att[4 rows][my 128 units] = dwq . W : warp w owns n-tiles {2w, 2w+1} (8 units each); lanes 0..15 hold rows 0..3
         const int r4 = lane >> 2, kq = (lane & 3) * 2;
         const bool arow_live = r4 < R2_CS;
+        // four independent accumulator chains (2 n-tiles x even / odd k-steps) keep the tensor pipe busy
+        float acc4[2][2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc4[i][hf][e] = 0.f;
+        const __nv_bfloat16* arow = sDq + (size_t)(r4 & 3) * AP + kq;
+#pragma unroll
+        for (int k0 = 0; k0 < A; k0 += 32) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int k = k0 + 16 * hf;
+            const uint32_t a0 = arow_live ? *reinterpret_cast<const uint32_t*>(arow + k) : 0u;
+            const uint32_t a2 = arow_live ? *reinterpret_cast<const uint32_t*>(arow + k + 8) : 0u;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const __nv_bfloat16* wrow = sWT + (size_t)((2 * warp + i) * 8 + r4) * AP + kq;
+              const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + k);
+              const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + k + 8);
+              asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                           : "+f"(acc4[i][hf][0]), "+f"(acc4[i][hf][1]), "+f"(acc4[i][hf][2]), "+f"(acc4[i][hf][3])
+                           : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+            }
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int nt = 2 * warp + i;
-          const __nv_bfloat16* arow = sDq + (size_t)(r4 & 3) * AP + kq;
-          const __nv_bfloat16* wrow = sWT + (size_t)(nt * 8 + r4) * AP + kq;
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-#pragma unroll
-          for (int k0 = 0; k0 < A; k0 += 16) {
-            const uint32_t a0 = arow_live ? *reinterpret_cast<const uint32_t*>(arow + k0) : 0u;
-            const uint32_t a2 = arow_live ? *reinterpret_cast<const uint32_t*>(arow + k0 + 8) : 0u;
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + k0);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + k0 + 8);
-            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                         : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
-                         : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
-          }
-          if (arow_live) st_dsmem_f32x2(mapa(smem_u32(sDh + rank * UPR + nt * 8 + kq), (uint32_t)r4), c0, c1);
+          if (arow_live)
+            st_dsmem_f32x2(mapa(smem_u32(sDh + rank * UPR + nt * 8 + kq), (uint32_t)r4), acc4[i][0][0] + acc4[i][1][0],
+                           acc4[i][0][1] + acc4[i][1][1]);
         }
-        named_bar<1, 256>();
-        if (tid == 0) {
-#pragma unroll
-          for (int d = 0; d < R2_CS; ++d) mbar_arrive_remote(mapa(dh_full, (uint32_t)d));
-        }
+        __syncwarp();
+        if (lane < R2_CS) mbar_arrive_remote(mapa(dh_full, (uint32_t)lane));
       }
       B2_STAMP(6);
     }
@@ -432,13 +433,12 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
     }
   } else {
     // ================================================================= recurrent GEMM group (warps 8-11)
-    const int ge = tid - 256;
     uint32_t it_p = 0, it_c = 0;
     for (int j = 0; j + 1 < S; ++j) {
       const int s = S - 1 - j;                      // ghb(s) = dG_s . W_hh, consumed by the cell backward of step s-1
       if (warp == 8) {
         if (lane == 0) {
-          poll_counter(cntY, nlive * (unsigned)(j + 1));           // dG_s of every row is in global memory
+          poll_counters4(cntY, nl0 * (j + 1), nl1 * (j + 1), nl2 * (j + 1), nl3 * (j + 1));   // dG_s of every row is published
           asm volatile("fence.proxy.async;" ::: "memory");
           for (int i = 0; i < B2_NKB; ++i, ++it_p) {
             const int stage = (int)(it_p % B2_STAGES);
@@ -473,37 +473,22 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
       mbar_wait(tmem_full_bar, (uint32_t)(j & 1));
       tc_fence_after();
       {
+        // this K-slice's partial [128 x 16]: TMEM -> plane `rank` of ghb (row = TMEM lane)
         const int prow = (warp & 3) * 32 + lane;
         uint32_t v[32];
         tmem_ld32(tmem_lane, v);                    // 16 live accumulator columns
-        float4* dst = reinterpret_cast<float4*>(sPartial + (size_t)prow * B2_PS);
+        if (prow < B) {
+          float4* dst = reinterpret_cast<float4*>(p.ghb + ((size_t)rank * 128 + prow) * H + n0);
 #pragma unroll
-        for (int q = 0; q < B2_BN / 4; ++q)
-          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                               __uint_as_float(v[4 * q + 3]));
+          for (int q = 0; q < B2_BN / 4; ++q)
+            dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+        }
       }
       tc_fence_before();
-      named_bar<3, 128>();
-      if (ge == 0) {
-#pragma unroll
-        for (int d = 0; d < R2_CS; ++d) mbar_arrive_remote(mapa(part_full, (uint32_t)d));
-      }
-      mbar_wait_cl(part_full, (uint32_t)(j & 1));
       B2_STAMP_G(8);
-      {
-        const int rl = ge >> 2, cq = ge & 3;
-        const int row = rank * 32 + rl;
-        const uint32_t pbase = smem_u32(sPartial + (size_t)row * B2_PS + cq * 4);
-        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int sr = 0; sr < R2_CS; ++sr) {
-          const float4 t4 = ld_dsmem4(mapa(pbase, (uint32_t)sr));
-          a4.x += t4.x; a4.y += t4.y; a4.z += t4.z; a4.w += t4.w;
-        }
-        if (row < B) *reinterpret_cast<float4*>(p.ghb + (size_t)row * H + n0 + cq * 4) = a4;
-      }
       named_bar<3, 128>();
-      if (ge == 0) signal_counter(cntX);
+      if (tid == 256) signal_counter(cntX + R2_CNT_STRIDE * rank);
       B2_STAMP_G(9);
     }
   }
@@ -523,8 +508,8 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
 int r2_make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out);
 
 size_t recur2_bwd_smem() {
-  return 1024 + B2_B_BYTES + B2_RING_BYTES + sizeof(float) * 128 * B2_PS + (size_t)(B2_UPR + R2_CS) * B2_AP * 2 +
-         sizeof(float) * (R2_H + 4 * R2_H + 8 * R2_A + 8 * 64 + 64 + 64 + 2 * R2_A) + 8 * (2 * B2_STAGES + 5) + 16;
+  return 1024 + B2_B_BYTES + B2_RING_BYTES + (size_t)(B2_UPR + R2_CS) * B2_AP * 2 +
+         sizeof(float) * (R2_H + 4 * R2_H + 8 * R2_A + 8 * 64 + 64 + 64 + 2 * R2_A) + 8 * (2 * B2_STAGES + 4) + 16;
 }
 const void* recur2_bwd_kernel_ptr() { return (const void*)recur2_bwd_kernel; }
 
@@ -536,7 +521,7 @@ int recur2_bwd_launch(const Recur2BwdParams& p, const void* whhT_um, cudaStream_
   CUtensorMap mg, mw;
   MVC_TRY(r2_make_map(p.dG_b, (int64_t)p.S * p.B, 4 * (int64_t)R2_H, 4 * (int64_t)R2_H, 128, &mg));
   MVC_TRY(r2_make_map(whhT_um, R2_H, 4 * (int64_t)R2_H, 4 * (int64_t)R2_H, B2_BN, &mw));
-  MVC_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned) * 32, st));
+  MVC_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned) * 256, st));
   const size_t smem = recur2_bwd_smem();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(R2_H / 16) * R2_CS);

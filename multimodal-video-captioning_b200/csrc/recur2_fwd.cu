@@ -8,13 +8,14 @@
 //                                         four h rows (mma.sync), results scattered to the row owners over DSMEM;
 //     recurrent GEMM                    : W_hh rows of units [16c, 16c+16) x K-slice r resident in shared memory as a
 //                                         128B-swizzled UMMA operand; gh[128, 64] partial = h_s[:, slice] . W^T on
-//                                         tcgen05 (A by TMA), the four K-slice partials reduced over DSMEM in rank
-//                                         order (deterministic) and written to global `gh`.
+//                                         tcgen05 (A by TMA); each K-slice partial goes straight from TMEM to its own
+//                                         plane of global `gh` [4][128][4H]; the row owner adds the four planes in
+//                                         rank order (deterministic).
 //   step s:   compute warps 0-7                          |  GEMM warps 8-11
 //     wait h_s rows of the cluster (mbarrier)            |  wait Y >= rows*s   (h_s of every row published)
-//     wq slice -> owners (DSMEM) -> mbarrier             |  TMA h_s k-slices -> tcgen05.mma -> park partial
-//     scores, softmax, sum_t alpha_t P[b,t,:] (TMEM)     |  mbarrier (4 partials) -> reduce -> gh -> X += 1
-//     wait X >= 128*s; gates = gx + gh + P-sum; cell     |
+//     wq slice -> owners (DSMEM) -> mbarrier             |  TMA h_s k-slices -> tcgen05.mma -> TMEM -> gh plane r
+//     scores, softmax, sum_t alpha_t P[b,t,:] (TMEM)     |  X += 1 per warp
+//     wait X; gates = gx + sum_r gh[r] + P-sum; cell     |
 //     h_{s+1}: global (bf16 + fp32), DSMEM to the four ranks, mbarrier arrive, Y += 1
 #include <cuda_fp16.h>
 
@@ -33,7 +34,6 @@ constexpr int F2_B_BYTES = F2_NKB * F2_KB_BYTES;     // 16384
 constexpr int F2_STAGE_BYTES = 128 * 128;            // A stage: 128 rows x 64 bf16
 constexpr int F2_STAGES = 2;
 constexpr int F2_RING_BYTES = F2_STAGES * F2_STAGE_BYTES;
-constexpr int F2_PS = F2_BN + 4;                     // partial tile row pitch (floats)
 constexpr int F2_HP = R2_H + 8;                      // bf16 pitch of the resident attention.W slice / h rows
 constexpr int F2_UPR = R2_A / R2_CS;                 // 64 query units per rank
 constexpr int F2_GCP = 17;                           // pitch of the P-sum hand-over buffer (floats)
@@ -47,8 +47,7 @@ recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   const int B = p.B, T = p.T, K = p.K, S = p.S;
 
   uint8_t* ring = smem + F2_B_BYTES;
-  float* sPartial = reinterpret_cast<float*>(ring + F2_RING_BYTES);                       // [128][F2_PS]
-  __nv_bfloat16* sWatt = reinterpret_cast<__nv_bfloat16*>(sPartial + 128 * F2_PS);        // [UPR][HP]
+  __nv_bfloat16* sWatt = reinterpret_cast<__nv_bfloat16*>(ring + F2_RING_BYTES);          // [UPR][HP]
   __nv_bfloat16* sHb = sWatt + (size_t)UPR * HP;                                          // [4][HP] h rows of the cluster
   float* sQ = reinterpret_cast<float*>(sHb + (size_t)R2_CS * HP);                         // [A] wq of my row
   float* sWv = sQ + A;
@@ -61,10 +60,9 @@ recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   auto empty_bar = [&](int s) { return bar0 + 8u * (F2_STAGES + s); };
   const uint32_t tmem_full_bar = bar0 + 8u * (2 * F2_STAGES);
   const uint32_t w_bar = tmem_full_bar + 8u;
-  const uint32_t hb_full = w_bar + 8u;          // 4 arrivals: the owners of the cluster's rows published h_s here
-  const uint32_t q_full = hb_full + 8u;         // 4 arrivals: every rank delivered its slice of my row's query
-  const uint32_t part_full = q_full + 8u;       // 4 arrivals: the K-slice partials of the cluster are parked
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * F2_STAGES + 5);
+  const uint32_t hb_full = w_bar + 8u;          // 16 arrivals: 4 cell warps of each of the 4 row owners published h_s here
+  const uint32_t q_full = hb_full + 8u;         // 32 arrivals: 8 warps of every rank delivered their slice of my row's query
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * F2_STAGES + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_rank();
@@ -77,8 +75,11 @@ recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   const uint32_t ring_base = smem_base + F2_B_BYTES;
   const unsigned nctas = gridDim.x;
   const unsigned nlive = (unsigned)(B < (int)gridDim.x ? B : (int)gridDim.x);
-  unsigned* cntY = p.sync;
-  unsigned* cntX = p.sync + 16;
+  unsigned* cntY = p.sync;                        // Y[r] at cntY + 32 r: arrivals of the row owners of cluster rank r
+  unsigned* cntX = p.sync + 128;                  // X[r] at cntX + 32 r: arrivals of the GEMM groups of cluster rank r
+  // live rows per cluster rank (row b is owned by CTA b: rank b % 4), CTAs per rank
+  const unsigned nl0 = (unsigned)((nlive + 3) / 4), nl1 = (unsigned)((nlive + 2) / 4), nl2 = (unsigned)((nlive + 1) / 4),
+                 nl3 = (unsigned)(nlive / 4), ncr = nctas / R2_CS;
 
   // ---------------------------------------------------------------- one-time setup
   if (warp == 8 && lane == 0) {
@@ -90,9 +91,8 @@ recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(w_bar, 1);
-    mbar_init(hb_full, R2_CS);
-    mbar_init(q_full, R2_CS);
-    mbar_init(part_full, R2_CS);
+    mbar_init(hb_full, R2_CS * 4);
+    mbar_init(q_full, R2_CS * 8);
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -180,24 +180,31 @@ recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         const int r4 = lane >> 2, kq = (lane & 3) * 2;
         const __nv_bfloat16* arow = sHb + (size_t)(r4 & 3) * HP + kq;
         const __nv_bfloat16* wrow = sWatt + (size_t)(warp * 8 + r4) * HP + kq;
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
         const bool live = r4 < R2_CS;
-#pragma unroll 8
-        for (int k0 = 0; k0 < H; k0 += 16) {
-          const uint32_t a0 = live ? *reinterpret_cast<const uint32_t*>(arow + k0) : 0u;
-          const uint32_t a2 = live ? *reinterpret_cast<const uint32_t*>(arow + k0 + 8) : 0u;
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + k0);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + k0 + 8);
-          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                       : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
-                       : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
-        }
-        if (live) st_dsmem_f32x2(mapa(smem_u32(sQ + rank * UPR + warp * 8 + kq), (uint32_t)r4), c0, c1);
-        named_bar<1, 256>();
-        if (tid == 0) {
+        float acc4[4][4];                           // four independent accumulator chains over k
 #pragma unroll
-          for (int d = 0; d < R2_CS; ++d) mbar_arrive_remote(mapa(q_full, (uint32_t)d));
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc4[i][e] = 0.f;
+#pragma unroll
+        for (int k0 = 0; k0 < H; k0 += 64) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = k0 + 16 * i;
+            const uint32_t a0 = live ? *reinterpret_cast<const uint32_t*>(arow + k) : 0u;
+            const uint32_t a2 = live ? *reinterpret_cast<const uint32_t*>(arow + k + 8) : 0u;
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + k);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + k + 8);
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(acc4[i][0]), "+f"(acc4[i][1]), "+f"(acc4[i][2]), "+f"(acc4[i][3])
+                         : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+          }
         }
+        const float c0 = (acc4[0][0] + acc4[1][0]) + (acc4[2][0] + acc4[3][0]);
+        const float c1 = (acc4[0][1] + acc4[1][1]) + (acc4[2][1] + acc4[3][1]);
+        if (live) st_dsmem_f32x2(mapa(smem_u32(sQ + rank * UPR + warp * 8 + kq), (uint32_t)r4), c0, c1);
+        __syncwarp();
+        if (lane < R2_CS) mbar_arrive_remote(mapa(q_full, (uint32_t)lane));      // this warp's 8 units of all four rows
         mbar_wait_cl(q_full, (uint32_t)((s - 1) & 1));         // every rank's slice of my row's query has landed
       }
       F2_STAMP(2);
@@ -207,32 +214,49 @@ recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         float qb[AV], wv[AV];
 #pragma unroll
         for (int k = 0; k < AV; ++k) { qb[k] = sQ[lane + 32 * k] + sBias[lane + 32 * k]; wv[k] = sWv[lane + 32 * k]; }
+        float er[8];                                 // per-lane partial scores of frames warp + 8r (r < 6)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) er[r] = 0.f;
 #pragma unroll
         for (int r = 0; r < R2_R; ++r) {
-          const int t = warp + r * 8;
-          if (t < T) {
-            float e0 = 0.f, e1 = 0.f;
+          float e0 = 0.f, e1 = 0.f;
 #pragma unroll
-            for (int k = 0; k < AV; k += 2) {
-              e0 = fmaf(wv[k], tanh_fast(qb[k] + ur[r][k]), e0);
-              e1 = fmaf(wv[k + 1], tanh_fast(qb[k + 1] + ur[r][k + 1]), e1);
-            }
-            const float e = warp_sum(e0 + e1);
-            if (lane == 0) sE[t] = e;
+          for (int k = 0; k < AV; k += 2) {
+            e0 = fmaf(wv[k], tanh_fast(qb[k] + ur[r][k]), e0);
+            e1 = fmaf(wv[k + 1], tanh_fast(qb[k + 1] + ur[r][k + 1]), e1);
+          }
+          er[r] = e0 + e1;
+        }
+        // 8-value butterfly: lane l ends with the warp total of value l >> 2 (9 shuffles instead of 30)
+#pragma unroll
+        for (int w = 4; w >= 1; w >>= 1) {
+          const bool up = (lane & (4 * w)) != 0;
+#pragma unroll
+          for (int i = 0; i < w; ++i) {
+            const float keep = up ? er[w + i] : er[i], give = up ? er[i] : er[w + i];
+            er[i] = keep + __shfl_xor_sync(0xffffffffu, give, 4 * w);
           }
         }
+        er[0] += __shfl_xor_sync(0xffffffffu, er[0], 2);
+        er[0] += __shfl_xor_sync(0xffffffffu, er[0], 1);
+        const int tr = warp + 8 * (lane >> 2);
+        if ((lane & 3) == 0 && (lane >> 2) < R2_R && tr < T) sE[tr] = er[0];
       }
       named_bar<1, 256>();
-      if (has_row && warp == 0) {                 // softmax over T <= 48 frames
+      // softmax over T <= 48 frames, redundantly in every warp (no second barrier): lane l keeps alpha of frames l, l+32
+      float al_lo = 0.f, al_hi = 0.f;
+      if (has_row) {
         const float e0 = lane < T ? sE[lane] : -INFINITY, e1 = lane + 32 < T ? sE[lane + 32] : -INFINITY;
         const float mx = warp_max(fmaxf(e0, e1));
         const float p0 = lane < T ? __expf(e0 - mx) : 0.f, p1 = lane + 32 < T ? __expf(e1 - mx) : 0.f;
         const float inv = 1.f / warp_sum(p0 + p1);
-        float* al = p.alpha + grow * T;
-        if (lane < T) { sE[lane] = p0 * inv; al[lane] = p0 * inv; }
-        if (lane + 32 < T) { sE[lane + 32] = p1 * inv; al[lane + 32] = p1 * inv; }
+        al_lo = p0 * inv; al_hi = p1 * inv;
+        if (warp == 7) {
+          float* al = p.alpha + grow * T;
+          if (lane < T) al[lane] = al_lo;
+          if (lane + 32 < T) al[lane + 32] = al_hi;
+        }
       }
-      named_bar<1, 256>();
       F2_STAMP(3);
       // sum_t alpha_t P[b,t,:] straight out of TMEM: TMEM lane L owns gate columns [16L, 16L+16).  Warps w and w+4
       // share a lane quarter: even 4-frame chunks go to warps 0-3, odd ones to warps 4-7.
@@ -246,8 +270,10 @@ recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           if ((c & 1) == half && c * 4 < T) {
             uint32_t v[32];
             tmem_ld32(tmem_p + (uint32_t)(c * 32), v);
-            const float4 al4 = *reinterpret_cast<const float4*>(sE + c * 4);       // zero beyond T
-            const float al[4] = {al4.x, al4.y, al4.z, al4.w};
+            float al[4];                          // alpha of frames 4c .. 4c+3 (zero beyond T)
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+              al[f] = __shfl_sync(0xffffffffu, (c * 4 + f) < 32 ? al_lo : al_hi, (c * 4 + f) & 31);
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
 #pragma unroll
@@ -270,25 +296,34 @@ recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
       if (tid < 128) {
         // ============================================================ LSTM cell of my row: units 4*tid .. 4*tid+3
         if (s > 0) {
-          if (tid == 0) poll_counter(cntX, nctas * (unsigned)s);     // gh = h_s . W_hh^T is complete in global memory
+          if (tid == 0) poll_counters4(cntX, ncr * s, ncr * s, ncr * s, ncr * s);   // gh planes of h_s . W_hh^T are complete
           named_bar<2, 128>();
         }
         F2_STAMP(5);
+        float pre[16], hn[4];
+        uint32_t w0 = 0u, w1 = 0u;
+        const size_t nrow = (size_t)(s + 1) * B + brow;
         if (has_row) {
-          float pre[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) pre[i] = acc[i] + sGc[tid * F2_GCP + i];
 #pragma unroll
           for (int q = 0; q < 4; ++q) { pre[4 * q] += gx4[q].x; pre[4 * q + 1] += gx4[q].y; pre[4 * q + 2] += gx4[q].z; pre[4 * q + 3] += gx4[q].w; }
           if (s > 0) {
-            const float4* ghr = reinterpret_cast<const float4*>(p.gh + (size_t)brow * (4 * H)) + 4 * tid;
+            float4 g4[R2_CS][4];
+#pragma unroll
+            for (int r = 0; r < R2_CS; ++r) {
+              const float4* ghr = reinterpret_cast<const float4*>(p.gh + ((size_t)r * 128 + brow) * (4 * H)) + 4 * tid;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) g4[r][q] = __ldcg(ghr + q);
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 g4 = __ldcg(ghr + q);
-              pre[4 * q] += g4.x; pre[4 * q + 1] += g4.y; pre[4 * q + 2] += g4.z; pre[4 * q + 3] += g4.w;
+              float4 t4 = g4[0][q];
+#pragma unroll
+              for (int r = 1; r < R2_CS; ++r) { t4.x += g4[r][q].x; t4.y += g4[r][q].y; t4.z += g4[r][q].z; t4.w += g4[r][q].w; }
+              pre[4 * q] += t4.x; pre[4 * q + 1] += t4.y; pre[4 * q + 2] += t4.z; pre[4 * q + 3] += t4.w;
             }
           }
-          float hn[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float ig = sigmoid_ex2(pre[4 * u]), fg = sigmoid_ex2(pre[4 * u + 1]), gg = tanh_ex2(pre[4 * u + 2]),
@@ -297,38 +332,38 @@ recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
             cst[u] = fg * cst[u] + ig * gg;
             hn[u] = og * tanh_ex2(cst[u]);
           }
-          const size_t nrow = (size_t)(s + 1) * B + brow;
+          // publish h_{s+1} FIRST (the recurrent GEMM and the cluster's query projection wait for it) ...
+          __nv_bfloat162 h01 = __floats2bfloat162_rn(hn[0], hn[1]), h23 = __floats2bfloat162_rn(hn[2], hn[3]);
+          w0 = *reinterpret_cast<uint32_t*>(&h01); w1 = *reinterpret_cast<uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(p.xh + nrow * K + p.F + 4 * tid) = make_uint2(w0, w1);
+          const uint32_t hloc = smem_u32(sHb + (size_t)rank * HP + 4 * tid);
+#pragma unroll
+          for (int d = 0; d < R2_CS; ++d) st_dsmem_u32x2(mapa(hloc, (uint32_t)d), w0, w1);
+        }
+        __syncwarp();
+        if (lane < R2_CS) mbar_arrive_remote(mapa(hb_full, (uint32_t)lane));
+        named_bar<2, 128>();
+        if (tid == 0 && has_row) signal_counter(cntY + R2_CNT_STRIDE * rank);     // h_{s+1} of my row is in xh slot s+1
+        F2_STAMP(6);
+        // ... then everything that is only saved for the backward pass
+        if (has_row) {
           *reinterpret_cast<float4*>(p.c + nrow * H + 4 * tid) = make_float4(cst[0], cst[1], cst[2], cst[3]);
           if (p.out_hid) *reinterpret_cast<float4*>(p.out_hid + nrow * H + 4 * tid) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-          __nv_bfloat162 h01 = __floats2bfloat162_rn(hn[0], hn[1]), h23 = __floats2bfloat162_rn(hn[2], hn[3]);
-          const uint32_t w0 = *reinterpret_cast<uint32_t*>(&h01), w1 = *reinterpret_cast<uint32_t*>(&h23);
-          *reinterpret_cast<uint2*>(p.xh + nrow * K + p.F + 4 * tid) = make_uint2(w0, w1);
           if (p.act) {
             float4* ar = reinterpret_cast<float4*>(p.act + grow * (size_t)(4 * H)) + 4 * tid;
 #pragma unroll
             for (int q = 0; q < 4; ++q) ar[q] = make_float4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
           }
-          const uint32_t hloc = smem_u32(sHb + (size_t)rank * HP + 4 * tid);
-#pragma unroll
-          for (int d = 0; d < R2_CS; ++d) st_dsmem_u32x2(mapa(hloc, (uint32_t)d), w0, w1);
         }
-        named_bar<2, 128>();
-        if (tid == 0) {
-#pragma unroll
-          for (int d = 0; d < R2_CS; ++d) mbar_arrive_remote(mapa(hb_full, (uint32_t)d));
-          if (has_row) signal_counter(cntY);
-        }
-        F2_STAMP(6);
       }
     }
   } else {
     // ================================================================= recurrent GEMM group (warps 8-11)
-    const int ge = tid - 256;                     // 0..127
     uint32_t it_p = 0, it_c = 0;
     for (int s = 1; s < S; ++s) {
       if (warp == 8) {
         if (lane == 0) {
-          poll_counter(cntY, nlive * (unsigned)s);              // h_s of every row is in xh slot s
+          poll_counters4(cntY, nl0 * s, nl1 * s, nl2 * s, nl3 * s);      // h_s of every row is in xh slot s
           asm volatile("fence.proxy.async;" ::: "memory");
           for (int i = 0; i < F2_NKB; ++i, ++it_p) {
             const int stage = (int)(it_p % F2_STAGES);
@@ -360,55 +395,28 @@ recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         __syncwarp();
       }
       F2_STAMP_G(7);
-      // park this K-slice's partial tile [128 x 64]
+      // this K-slice's partial tile [128 x 64]: TMEM -> plane `rank` of gh (row = TMEM lane), no exchange
       mbar_wait(tmem_full_bar, (uint32_t)((s - 1) & 1));
       tc_fence_after();
       {
         const int prow = (warp & 3) * 32 + lane;
+        float4* dst = reinterpret_cast<float4*>(p.gh + ((size_t)rank * 128 + prow) * (4 * H) + n0);
 #pragma unroll
         for (int c = 0; c < F2_BN / 32; ++c) {
           uint32_t v[32];
           tmem_ld32(tmem_lane + (uint32_t)(c * 32), v);
-          float4* dst = reinterpret_cast<float4*>(sPartial + (size_t)prow * F2_PS + c * 32);
+          if (prow < B) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                      __uint_as_float(v[j + 3]));
+            for (int j = 0; j < 32; j += 4)
+              dst[c * 8 + (j >> 2)] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                  __uint_as_float(v[j + 3]));
+          }
         }
       }
       tc_fence_before();
-      named_bar<3, 128>();
-      if (ge == 0) {
-#pragma unroll
-        for (int d = 0; d < R2_CS; ++d) mbar_arrive_remote(mapa(part_full, (uint32_t)d));
-      }
-      mbar_wait_cl(part_full, (uint32_t)((s - 1) & 1));
       F2_STAMP_G(8);
-      {
-        // rank r finishes rows [32r, 32r+32): thread = (row, 16 columns); partials summed in rank order
-        const int rl = ge >> 2, cq = ge & 3;
-        const int row = rank * 32 + rl;
-        const uint32_t pbase = smem_u32(sPartial + (size_t)row * F2_PS + cq * 16);
-        float4 a4[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) a4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int sr = 0; sr < R2_CS; ++sr) {
-          const uint32_t src = mapa(pbase, (uint32_t)sr);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 t4 = ld_dsmem4(src + 16u * q);
-            a4[q].x += t4.x; a4[q].y += t4.y; a4[q].z += t4.z; a4[q].w += t4.w;
-          }
-        }
-        if (row < B) {
-          float4* out = reinterpret_cast<float4*>(p.gh + (size_t)row * (4 * H) + n0 + cq * 16);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) out[q] = a4[q];
-        }
-      }
       named_bar<3, 128>();
-      if (ge == 0) signal_counter(cntX);
+      if (tid == 256) signal_counter(cntX + R2_CNT_STRIDE * rank);
       F2_STAMP_G(9);
     }
   }
@@ -457,8 +465,8 @@ int r2_make_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box
 }
 
 static size_t recur2_fwd_smem() {
-  return 1024 + F2_B_BYTES + F2_RING_BYTES + sizeof(float) * 128 * F2_PS + (size_t)(F2_UPR + R2_CS) * F2_HP * 2 +
-         sizeof(float) * (3 * R2_A + 64 + 128 * F2_GCP) + 8 * (2 * F2_STAGES + 5) + 16;
+  return 1024 + F2_B_BYTES + F2_RING_BYTES + (size_t)(F2_UPR + R2_CS) * F2_HP * 2 +
+         sizeof(float) * (3 * R2_A + 64 + 128 * F2_GCP) + 8 * (2 * F2_STAGES + 4) + 16;
 }
 size_t recur2_bwd_smem();
 const void* recur2_bwd_kernel_ptr();
@@ -514,7 +522,7 @@ int recur2_fwd_launch(const Recur2FwdParams& p, const void* whh_um, int64_t ldw,
   // A operand: the h halves of the xh slots, [(S+1)*B rows, H cols], row pitch K
   MVC_TRY(r2_make_map(p.xh + p.F, (int64_t)(p.S + 1) * p.B, R2_H, p.K, 128, &mh));
   MVC_TRY(r2_make_map(whh_um, (int64_t)4 * R2_H, R2_H, ldw, F2_BN, &mw));
-  MVC_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned) * 32, st));
+  MVC_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned) * 256, st));
   const size_t smem = recur2_fwd_smem();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(R2_H / 16) * R2_CS);
