@@ -285,7 +285,7 @@ def config_block(workload, world, host_format):
     w = WORKLOADS[workload]
     B, T, L, V = SHAPES[w["shape"]]
     training = workload in TRAINING
-    es = 2 if host_format == "bf16" else 4
+    es = 2 if host_format in ("bf16", "shards") else 4
     in_bytes = B * T * 2176 * es + (B * L * 8 if training else 0)
     return {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world, "T": T, "L": L, "V": V,
             "parallelism": f"dp{world}" if training else f"batch-sharded x{world} (no comm)",
@@ -297,7 +297,7 @@ def config_block(workload, world, host_format):
 TRAINING = ("train", "train_dual", "recnet_global", "recnet_local")
 
 
-def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, world, lib, sampler=None):
+def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, world, lib, use_graph=True):
     """Device-resident value, end-to-end value, roofline of the dominant kernel for one workload -> dict."""
     import torch.distributed as dist
     from salstm import functional as Fn
@@ -309,19 +309,33 @@ def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, wor
     model = build_model(workload, dev, precision)
     training = workload in TRAINING
     host = make_batches(shape, N_ROT, seed0=1 + 100 * rank)
-    if host_format == "bf16":
+    feeder = None
+    if host_format == "shards":
+        # the product's own data path: features pre-packed as a bf16 shard file, fed through the pinned,
+        # double-buffered ShardFeeder; the shard is written before any timing starts
+        from salstm.shards import ShardFeeder, ShardReader, write_shard
+        import tempfile
+        root = "/dev/shm" if os.access("/dev/shm", os.W_OK) else None
+        tmpdir = tempfile.mkdtemp(prefix=f"mvc_bench_r{rank}_", dir=root)
+        path = os.path.join(tmpdir, f"{w['shape']}.shard")
+        write_shard(path, [a_ for b_ in host for a_ in b_[0]], [v_ for b_ in host for v_ in b_[1]],
+                    [c_ for b_ in host for c_ in b_[2].t()], T=T, L=L)
+        feeder = ShardFeeder(ShardReader(path, pin=True), B, dev, shuffle=False, with_captions=training, epochs=1 << 14)
+    if host_format in ("bf16", "shards"):
         host = [(a.bfloat16(), v.bfloat16(), c) for a, v, c in host]
-    pinned = [tuple(t.pin_memory() for t in b) for b in host]
+    pinned = [tuple(t.pin_memory() for t in b) for b in host] if feeder is None else None
     resident = [tuple(t.to(dev) for t in b) for b in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
     if not training:
         h2d_bytes -= host[0][2].numel() * host[0][2].element_size()
+    if feeder is not None:
+        h2d_bytes = feeder.h2d_bytes_per_batch
 
     if training:
         loss_fn = Lm.ModalityWiseReconstructionLossBuilder(rec_type=w["rec"], **LAMBDAS)
         opt = FlatClipAdam(model.parameters(), lr=1e-4, weight_decay=1e-5, clip_value=5.0, world_size=world)
 
-        def step(batch):
+        def step_eager(batch):
             audio, visual, caps = batch
             opt.zero_grad()
             out, ar, vr = model(audio, visual, caps)
@@ -331,6 +345,7 @@ def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, wor
                 opt.all_reduce_grads()
             opt.step()
             return terms[0]
+        step = step_eager
         d2h_bytes = 4
     elif workload == "greedy":
         def step(batch):
@@ -348,18 +363,35 @@ def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, wor
             dist.barrier()
         torch.cuda.synchronize()
 
+    # launches per step, counted on one eager step (a graph replay re-issues exactly these kernels)
+    step_eager_fn = step
+    step(resident[0]); step(resident[1])
+    torch.cuda.synchronize()
+    l0 = lib.mvc_launch_count()
+    step(resident[2])
+    launches_per_step = lib.mvc_launch_count() - l0
+    graphed = False
+    if training and use_graph:
+        # the whole optimiser step recorded once as a CUDA graph and replayed (salstm.trainer.GraphedTrainStep)
+        from salstm.trainer import GraphedTrainStep
+        try:
+            gstep = GraphedTrainStep(model, loss_fn, opt, resident[0])
+            step = lambda batch: gstep(batch[0], batch[1], batch[2])[0]
+            graphed = True
+        except Exception as e:                      # e.g. a collective that cannot be captured: keep the eager step
+            print(f"[bench] CUDA-graph capture unavailable ({type(e).__name__}: {e}); timing the eager step", file=sys.stderr)
+
     # ---- device-resident timing
     for i in range(warmup):
         step(resident[i % N_ROT])
     barrier()
-    l0 = lib.mvc_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         step(resident[i % N_ROT])
     e1.record()
     barrier()
-    launches = lib.mvc_launch_count() - l0
+    launches = launches_per_step * steps
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -371,7 +403,7 @@ def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, wor
     # Inputs of step i+1 are prefetched on a copy stream while step i computes (double buffering);
     # all copies are inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)] if feeder is None else None
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
     n_in = 3 if training else 2
@@ -393,18 +425,25 @@ def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, wor
     host_res = [torch.empty(res_shape, dtype=res_dtype).pin_memory() for _ in range(2)]
     res_done = [torch.cuda.Event(), torch.cuda.Event()]
 
+    feed_iter = iter(feeder) if feeder is not None else None
+
     def run_e2e(n):
         last = None
-        for s in range(2):
-            freed[s].record(torch.cuda.current_stream())
-        prefetch(0)
+        if feeder is None:
+            for s in range(2):
+                freed[s].record(torch.cuda.current_stream())
+            prefetch(0)
         for i in range(n):
             s = i % 2
-            if i + 1 < n:
-                prefetch(i + 1)
-            torch.cuda.current_stream().wait_event(ready[s])
-            r = step(slots[s])
-            freed[s].record(torch.cuda.current_stream())
+            if feeder is not None:
+                a_, v_, c_, _len = next(feed_iter)          # H2D of this batch was issued one step ahead by the feeder
+                r = step((a_, v_, c_))
+            else:
+                if i + 1 < n:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[s])
+                r = step(slots[s])
+                freed[s].record(torch.cuda.current_stream())
             host_res[s].copy_(r.detach().reshape(res_shape), non_blocking=True)      # D2H of this step's result
             res_done[s].record(torch.cuda.current_stream())
             if i >= 1:                                                              # consume step i-1's result
@@ -431,16 +470,21 @@ def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, wor
     # ---- roofline of the dominant kernel, timed in situ over K more steps
     pk = peaks()
     # every rank runs the extra steps (the train step contains the gradient all-reduce); rank 0 arms the timers
-    roof = roofline_pass(lib, workload, precision, steps, step, resident, shape, pk, arm=(rank == 0))
+    roof = roofline_pass(lib, workload, precision, steps, step_eager_fn, resident, shape, pk, arm=(rank == 0))
     cfg = config_block(workload, world, host_format)
+    cfg["step"] = ("one optimiser step recorded as a CUDA graph and replayed (salstm.trainer.GraphedTrainStep)" if graphed
+                   else "eager: one Python call per module, as src/train.py issues them")
     return {"metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": precision, "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / steps, "wall_ms_per_step": wall_ms / steps,
-                    "note": "pinned host inputs, double-buffered H2D on a copy stream; result of every step copied D2H "
-                            "asynchronously and consumed one step later"},
-            "gpu_launches": int(launches), "roofline": roof, "peaks": pk["src"]}
+                    "note": ("bf16 feature shard file, read once into page-locked memory -> salstm.shards.ShardFeeder (copy stream "
+                             "uploads each batch straight out of the shard, one batch ahead of the compute stream)"
+                             if feeder is not None else
+                             "pinned host inputs, double-buffered H2D on a copy stream") +
+                            "; result of every step copied D2H asynchronously and consumed one step later"},
+            "gpu_launches": int(launches), "cuda_graph": graphed, "roofline": roof, "peaks": pk["src"]}
 
 
 def main():
@@ -452,11 +496,14 @@ def main():
     ap.add_argument("--workload", default="train", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true",
+                    help="time the eager train step (what src/train.py issues) instead of the CUDA-graph replay")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the greedy-decode block the default (train) line carries as `secondary`")
-    ap.add_argument("--host-format", default="fp32", choices=["fp32", "bf16"],
-                    help="feature buffers handed to the model: fp32 as the reference's loader produces them (default), or "
-                         "pre-packed bf16 shards (SURVEY 8f-2; bf16 precision, workloads without reconstructor)")
+    ap.add_argument("--host-format", default=None, choices=["fp32", "bf16", "shards"],
+                    help="where the end-to-end leg's inputs come from: `shards` (default for bf16 workloads without a "
+                         "reconstructor) = a bf16 feature shard file fed by salstm.shards.ShardFeeder (SURVEY 8f-2); `fp32` = "
+                         "pinned fp32 tensors as the reference's loader produces them; `bf16` = pinned bf16 tensors")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -471,7 +518,8 @@ def main():
         print(json.dumps({"impl": "reference", "metric": w["metric"], "value": value, "unit": w["unit"],
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": config_block(args.workload, args.gpus, args.host_format),
+                          "data": "synthetic", "config": config_block(args.workload, args.gpus, args.host_format or
+                                                 ("shards" if (w["rec"] == "none" and args.precision == "bf16") else "fp32")),
                           "cpu_baseline": cb,
                           "e2e": {"value": value, "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -488,15 +536,19 @@ def main():
         G.build()
     from salstm import cabi
     lib = cabi.lib()
-    if args.host_format == "bf16" and (args.precision != "bf16" or w["rec"] != "none"):
-        sys.exit("--host-format bf16 needs --precision bf16 and a workload without reconstructor")
+    bf16_ok = args.precision == "bf16" and w["rec"] == "none"
+    if args.host_format is None:
+        args.host_format = "shards" if bf16_ok else "fp32"
+    if args.host_format in ("bf16", "shards") and not bf16_ok:
+        sys.exit("--host-format bf16/shards needs --precision bf16 and a workload without reconstructor")
 
     # clocks are sampled (nvidia-smi, 100 ms period) from before the warm-up until after the last timed
     # region, so the samples "under load" cover every timed loop of this process
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    line = measure_b200(args.workload, args.precision, args.host_format, args.steps, warmup, dev, rank, world, lib)
+    line = measure_b200(args.workload, args.precision, args.host_format, args.steps, warmup, dev, rank, world, lib,
+                        use_graph=not args.eager)
     secondary = None
     if args.workload == "train" and not args.no_secondary:
         # the second half of BASELINE.json's metric: greedy-decode captions/s (configs[2] per-GPU shape), same process

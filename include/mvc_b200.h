@@ -389,6 +389,14 @@ int mvc_clip_adam_step(float* param, const float* grad, float* exp_avg, float* e
                        float eps, float weight_decay, float clip_value, int step, float grad_scale,
                        void* stream);
 
+/* The same update with its two per-step scalars in DEVICE memory, so that the launch can be recorded in a CUDA graph
+ * and replayed: state_dev[0] = number of updates applied so far (a float; incremented by one before the update when
+ * tick != 0 -- pass tick only for the first range of a step), state_dev[1] = learning rate (the host rewrites it when
+ * an lr scheduler changes it; train.py:90-97). */
+int mvc_clip_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                           float* max_exp_avg_sq, int64_t n, float* state_dev, int tick, float beta1, float beta2,
+                           float eps, float weight_decay, float clip_value, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

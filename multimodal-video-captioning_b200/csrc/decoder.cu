@@ -70,28 +70,64 @@ static int get_loop_mode(const void* ws) {
   return it == g_loop_mode.end() ? -1 : it->second;
 }
 
-// A library-owned side stream per device (+ fork / join events): work that does not feed the recurrence (the weight
-// gradients of the vocabulary projection) runs there, on the SMs the persistent backward kernel leaves idle.
+// A library-owned side stream per (device, caller stream) with its own fork / join events: work that does not feed
+// the recurrence (weight packing, the weight gradients of the vocabulary projection, operand transposes) runs there,
+// next to the caller's stream.  Keyed by the caller's stream so that two user streams (or a CUDA-graph capture stream)
+// never share events; `SideGuard` makes every exit path -- including MVC_TRY / MVC_CUDA early returns between fork and
+// join -- order the caller's stream after whatever the side stream was given, so the torch-owned workspaces the side
+// stream writes cannot be recycled under it.
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
-static int get_side_stream(SideStream** out) {
+static int get_side_stream(cudaStream_t caller, SideStream** out) {
   static std::mutex mu;
-  static SideStream pool[64];
+  static std::unordered_map<uint64_t, SideStream*> pool;
   int dev = 0;
   MVC_CUDA(cudaGetDevice(&dev));
-  MVC_CHECK(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  const uint64_t key = (reinterpret_cast<uint64_t>(caller) << 8) ^ (uint64_t)(dev & 0xff);
   std::lock_guard<std::mutex> lk(mu);
-  SideStream& s = pool[dev];
-  if (!s.stream) {
-    MVC_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    MVC_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
-    MVC_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  auto it = pool.find(key);
+  if (it == pool.end()) {
+    SideStream* s = new SideStream();
+    MVC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    MVC_CUDA(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
+    MVC_CUDA(cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming));
+    it = pool.emplace(key, s).first;
   }
-  *out = &s;
+  *out = it->second;
   return 0;
 }
+struct SideGuard {
+  cudaStream_t caller;
+  SideStream* side = nullptr;
+  bool open = false;                                   // forked and not yet joined
+  explicit SideGuard(cudaStream_t c) : caller(c) {}
+  int fork() {                                         // side stream continues after everything enqueued on `caller`
+    if (!side) MVC_TRY(get_side_stream(caller, &side));
+    MVC_CUDA(cudaEventRecord(side->fork, caller));
+    MVC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    open = true;
+    return 0;
+  }
+  int mark() {                                         // "everything given to the side stream so far"
+    MVC_CUDA(cudaEventRecord(side->join, side->stream));
+    return 0;
+  }
+  int join() {                                         // caller waits for the last mark()
+    if (open) {
+      MVC_CUDA(cudaStreamWaitEvent(caller, side->join, 0));
+      open = false;
+    }
+    return 0;
+  }
+  ~SideGuard() {
+    if (open) {                                        // error path: never leave the side stream running un-joined
+      cudaEventRecord(side->join, side->stream);
+      cudaStreamWaitEvent(caller, side->join, 0);
+    }
+  }
+};
 
 // tile-interleaved gate order (fused gate-GEMM + cell epilogue): bf16 path with H a multiple of 32
 static inline int dec_perm(const MvcDecoderDims* d) { return d->precision == MVC_BF16 && d->H % 32 == 0; }
@@ -246,11 +282,9 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
   const int permH = perm == 2 ? -H : (perm ? H : 0);
   MVC_CHECK(Fa + Fv == F, "decoder: Fa (%d) + Fv (%d) != in_feature_size (%d)", Fa, Fv, F);
   // weight packing / casting on the side stream, concurrent with the feature cast and the U.k GEMM
-  SideStream* side = nullptr;
-  MVC_TRY(get_side_stream(&side));
-  MVC_CUDA(cudaEventRecord(side->fork, st));
-  MVC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-  cudaStream_t ss = side->stream;
+  SideGuard sg(st);
+  MVC_TRY(sg.fork());
+  cudaStream_t ss = sg.side->stream;
   MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, permH, ss));
   MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, bf, perm, ss));
   if (bf) {
@@ -261,7 +295,7 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
       MVC_CUDA(cudaMemsetAsync((char*)w.outw + (size_t)V * H * 2, 0, (size_t)(tc_aux_row0(V) - V) * H * 2, ss));
     if (need_embtab) MVC_TRY(launch_cast_pad_bf16(p->embedding, V, E, E, Ep, w.embb, 0, ss));
   }
-  MVC_CUDA(cudaEventRecord(side->join, ss));
+  MVC_TRY(sg.mark());
   if (mvc_get_input_format() == MVC_INPUT_BF16) {
     // pre-packed bf16 feature shards: half the H2D bytes upstream, no cast pass here
     MVC_CHECK(bf, "decoder: bf16 input features need precision = MVC_BF16");
@@ -272,7 +306,7 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
   if (bf) MVC_TRY(mvc_cast_bf16(p->att_U, w.U, (int64_t)A * F, st));
   // uk = feats . U^T      (temporal_attention.py:21, hoisted)
   MVC_TRY(gemm_nt(d->precision, B * T, A, F, w.feats, F, bf ? w.U : (const void*)p->att_U, F, 0.f, w.uk, A, nullptr, st));
-  MVC_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  MVC_TRY(sg.join());
   if (need_embtab) {
     // embtab[v,:] = embedding[v] . W_ih[:, :E]^T + b_ih + b_hh
     if (bf) MVC_TRY(gemm_nt(MVC_BF16, V, 4 * H, Ep, w.embb, Ep, w.wie, Ep, 0.f, w.embtab, 4 * H, w.bsum, st));
@@ -560,7 +594,7 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   const bool use_r2 = loop_mode == DEC_LOOP_RECUR2;
 
   // ---- vocabulary projection backward (all steps at once)
-  SideStream* side = nullptr;
+  SideGuard sg(st);
   bool forked = false;
   if (dlogp) {
     const float* lp = out_logp + (int64_t)B * V;
@@ -573,11 +607,9 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_TRY(mvc_gemm_bf16(SB, H, V, q.dlogits_b, Vp, q.outwT, Vp, 0.f, q.dhall, H, nullptr, nullptr, 0, st));
       // dW_out = dlogits^T . hall ; db_out = colsum(dlogits) (fp32).  Nothing in the recurrence needs them: fork them
       // onto the side stream, where they overlap the persistent backward kernel (joined before returning).
-      MVC_TRY(get_side_stream(&side));
-      MVC_CUDA(cudaEventRecord(side->fork, st));
-      MVC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      MVC_TRY(sg.fork());
       forked = true;
-      cudaStream_t ss = side->stream;
+      cudaStream_t ss = sg.side->stream;
       MVC_TRY(mvc_transpose_to_bf16(q.dlogits_b, 1, SB, V, Vp, q.dlogitsT, SBp, ss));
       MVC_TRY(mvc_transpose_to_bf16(hall, 1, SB, H, ldx, q.hallT, SBp, ss));
       MVC_TRY(mvc_gemm_bf16(V, H, SB, q.dlogitsT, SBp, q.hallT, SBp, 0.f, g->out_w, H, nullptr, nullptr, 0, ss));
@@ -590,7 +622,7 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
       MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, ss));
       MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, ss));
-      MVC_CUDA(cudaEventRecord(side->join, ss));
+      MVC_TRY(sg.mark());
     } else {
       MVC_TRY(mvc_log_softmax_bwd(lp, dl, SB, V, q.dlogits, nullptr, st));
       MVC_TRY(mvc_gemm_f32(SB, H, V, 1.f, q.dlogits, V, 1, p->out_w, 1, H, 0.f, q.dhall, H, nullptr, st));
@@ -685,11 +717,12 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, E, 0, st));
     MVC_TRY(mvc_gemm_f32(4 * H, E, SB, 1.f, q.dG, 1, 4 * H, (const float*)w.xemb, 1, E, 0.f, g->w_ih, E + F, nullptr, st));
     MVC_TRY(mvc_gemm_f32(SB, E, 4 * H, 1.f, q.dG, 4 * H, 1, p->w_ih, 1, E + F, 0.f, q.dxemb, E, nullptr, st));
+    MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, st));
   } else {
     // transposed bf16 operands (tcgen05 GEMM takes K-contiguous A[M,K], B[N,K])
     const bool pre_t = forked;                 // xhT / featsT / xembT / wieT were produced on the side stream
     if (forked) {
-      MVC_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+      MVC_TRY(sg.join());
       forked = false;
     }
     if (!pre_t) {
@@ -698,16 +731,19 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     }
     const char* hprevT = cptr(q.xhT, (int64_t)F * SBp, 2);
     // the attention-parameter gradients (small GEMMs) run on the side stream next to the LSTM weight gradients
-    if (!side) MVC_TRY(get_side_stream(&side));
-    MVC_CUDA(cudaEventRecord(side->fork, st));
-    MVC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    MVC_TRY(sg.fork());
     {
-      cudaStream_t ss = side->stream;
+      cudaStream_t ss = sg.side->stream;
+      if (pre_t) {
+        // the embedding gradient (dxemb = dG . W_ie, scattered into the table) needs neither dG^T nor the main stream
+        MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, q.wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, ss));
+        MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, ss));
+      }
       MVC_TRY(mvc_transpose_to_bf16(q.dwq_b, 1, SB, A, A, q.dwqT, SBp, ss));
       MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * T, A, A, q.dukT, BTp, ss));
       MVC_TRY(mvc_gemm_bf16(A, H, SB, q.dwqT, SBp, hprevT, SBp, 0.f, g->att_W, H, nullptr, nullptr, 0, ss));
       MVC_TRY(mvc_gemm_bf16(A, F, B * T, q.dukT, BTp, q.featsT, BTp, 0.f, g->att_U, F, nullptr, nullptr, 0, ss));
-      MVC_CUDA(cudaEventRecord(side->join, ss));
+      MVC_TRY(sg.mark());
       forked = true;
     }
     MVC_TRY(launch_transpose_bf16(q.dG_b, 1, SB, 4 * H, 4 * H, q.dGT, SBp, permH, st));   // natural gate rows
@@ -718,11 +754,13 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, st));
     }
     MVC_TRY(mvc_gemm_bf16(4 * H, E, SB, q.dGT, SBp, q.xembT, SBp, 0.f, g->w_ih, E + F, nullptr, nullptr, 0, st));
-    if (!pre_t) MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
-    MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, q.wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, st));
+    if (!pre_t) {
+      MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
+      MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, q.wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, st));
+      MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, st));
+    }
   }
-  MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, st));
-  if (forked) MVC_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  if (forked) MVC_TRY(sg.join());
   return 0;
 }
 

@@ -414,6 +414,30 @@ __global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict_
   }
 }
 
+// Same update with the step count and the learning rate read from DEVICE memory, so that the launch can sit inside a
+// CUDA graph: state[0] = step count (float, incremented by adam_tick_kernel before this kernel), state[1] = lr.
+__global__ void clip_adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                     float* __restrict__ v, float* __restrict__ vmax, int64_t n,
+                                     const float* __restrict__ state, float b1, float b2, float eps, float wd, float clip,
+                                     float grad_scale) {
+  const float step = state[0], lr = state[1];
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+    const float pi = p[i];
+    gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float vm = fmaxf(vmax[i], vi);
+    m[i] = mi; v[i] = vi; vmax[i] = vm;
+    const float denom = sqrtf(vm) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+__global__ void adam_tick_kernel(float* __restrict__ state) { state[0] += 1.f; }
+
 static inline int grid_for(int64_t n, int block = 256) {
   int64_t g = cdiv(n, block);
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -676,6 +700,23 @@ extern "C" int mvc_clip_adam_step(float* param, const float* grad, float* exp_av
   clip_adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n,
                                                                lr, beta1, beta2, eps, weight_decay, clip_value, bc1,
                                                                bc2_sqrt, grad_scale);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_clip_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                      float* max_exp_avg_sq, int64_t n, float* state_dev, int tick, float beta1, float beta2,
+                                      float eps, float weight_decay, float clip_value, float grad_scale, void* stream) {
+  if (n == 0) return 0;
+  MVC_CHECK(state_dev, "mvc_clip_adam_step_dev: null state");
+  if (tick) {
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state_dev);
+    MVC_LAUNCH_CHECK();
+  }
+  ProfScope prof(PK_ADAM, 0, 0, 0, (cudaStream_t)stream);
+  clip_adam_dev_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n,
+                                                                   state_dev, beta1, beta2, eps, weight_decay, clip_value,
+                                                                   grad_scale);
   MVC_LAUNCH_CHECK();
   return 0;
 }

@@ -28,6 +28,7 @@
 //     X = "the recurrent GEMM of step s is in global memory", polled by the row owners.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -94,6 +95,22 @@ int r2_ctx_rows(const void* feats_bf16, const float* alpha, int B, int T, int F,
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+// Spin-wait bound (SM clock cycles; ~4 s at 1.9 GHz by default).  The kernels synchronise 128 co-resident CTAs by
+// spinning, so they need the GPU to themselves: under a profiler that serialises / replays kernels, MPS or
+// time-slicing, raise it with MVC_B200_SPIN_TIMEOUT_S=<seconds> (read once per process by the launchers) or take
+// the launch chain with MVC_B200_PERSISTENT=0.  One copy per translation unit; set by r2_apply_spin_limit().
+static __constant__ long long c_r2_spin_limit = 8000000000LL;
+static inline int r2_apply_spin_limit() {
+  static int done = 0;
+  if (done) return 0;
+  done = 1;
+  const char* e = getenv("MVC_B200_SPIN_TIMEOUT_S");
+  if (e && atof(e) > 0.0) {
+    const long long cycles = (long long)(atof(e) * 2.0e9);
+    MVC_CUDA(cudaMemcpyToSymbol(c_r2_spin_limit, &cycles, sizeof(cycles)));
+  }
+  return 0;
+}
 namespace r2 {
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -148,7 +165,7 @@ __device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_cl(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_cl(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {
+    if (clock64() - t0 > c_r2_spin_limit) {
       printf("mvc recur2: cluster mbarrier wait timed out (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
       __trap();
     }
@@ -172,7 +189,7 @@ __device__ __forceinline__ void poll_counters4(const unsigned* counters, unsigne
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(counters + 2 * R2_CNT_STRIDE) : "memory");
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v3) : "l"(counters + 3 * R2_CNT_STRIDE) : "memory");
     if (v0 >= t0 && v1 >= t1 && v2 >= t2 && v3 >= t3) return;
-    if (clock64() - c0 > 8000000000LL) {
+    if (clock64() - c0 > c_r2_spin_limit) {
       printf("mvc recur2: progress-counter wait timed out (block %d thread %d: %u %u %u %u of %u %u %u %u)\n", blockIdx.x,
              threadIdx.x, v0, v1, v2, v3, t0, t1, t2, t3);
       __trap();

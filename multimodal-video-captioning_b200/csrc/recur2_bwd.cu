@@ -517,6 +517,7 @@ static long long* g_recur2_bwd_prof = nullptr;
 void r2_set_bwd_prof(long long* p) { g_recur2_bwd_prof = p; }
 
 int recur2_bwd_launch(const Recur2BwdParams& p, const void* whhT_um, cudaStream_t st) {
+  MVC_TRY(r2_apply_spin_limit());
   MVC_CHECK(recur2_supported(p.B, p.T, p.F, R2_H, R2_A), "persistent backward recurrence: unsupported dims");
   CUtensorMap mg, mw;
   MVC_TRY(r2_make_map(p.dG_b, (int64_t)p.S * p.B, 4 * (int64_t)R2_H, 4 * (int64_t)R2_H, 128, &mg));

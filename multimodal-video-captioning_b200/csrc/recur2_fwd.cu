@@ -517,6 +517,7 @@ static long long* g_recur2_prof = nullptr;
 void r2_set_fwd_prof(long long* p) { g_recur2_prof = p; }
 
 int recur2_fwd_launch(const Recur2FwdParams& p, const void* whh_um, int64_t ldw, cudaStream_t st) {
+  MVC_TRY(r2_apply_spin_limit());
   MVC_CHECK(recur2_supported(p.B, p.T, p.F, R2_H, R2_A), "persistent recurrence: unsupported dims");
   CUtensorMap mh, mw;
   // A operand: the h halves of the xh slots, [(S+1)*B rows, H cols], row pitch K

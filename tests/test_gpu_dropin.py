@@ -376,3 +376,49 @@ def test_reference_trainer_runs_unchanged_over_the_b200_modules(dev, tmp_path, r
         ids = O.av_dual_greedy_ids({k: v.detach().cpu() for k, v in model.state_dict().items()}, batches[0][0],
                                    batches[0][1], 30)
     assert [gen[f"vid{i}"][0] for i in range(4)] == [vocab.decode_indexes(r[1:]) for r in ids.tolist()]
+
+
+def test_graphed_train_step_equals_eager_steps(dev):
+    """salstm.trainer.GraphedTrainStep (one optimiser step as a CUDA-graph replay, device-side step count / lr) gives
+    the parameters the eager loop gives, step after step, on the bf16 persistent-kernel path, including an lr change."""
+    from models import AVCaptioning
+    from salstm.trainer import FlatClipAdam, GraphedTrainStep
+    import losses as L
+    V, B, T, Lc = 97, 8, 6, 7
+    lam = dict(reg_lambda=0.0005, audio_recon_lambda=0.0, visual_recon_lambda=0.0)
+
+    def make():
+        torch.manual_seed(5)
+        m = AVCaptioning(Vocab(V), 1.0, "none", device=dev, precision="bf16").to(dev)
+        return m, FlatClipAdam(m.parameters(), lr=1e-3, weight_decay=1e-5, clip_value=5.0)
+
+    batches = []
+    for i in range(9):
+        a, v, c = O.synth_batch(B, T, Lc, V, seed=60 + i, min_frames=2, min_cap=3)
+        batches.append(((a / 255.0).to(dev), (v / 10.0).to(dev), c.to(dev)))
+    loss_fn = L.ModalityWiseReconstructionLossBuilder(rec_type="none", **lam)
+    ma, oa = make()
+    mb, ob = make()
+    gstep = GraphedTrainStep(ma, loss_fn, oa, batches[0], warmup=2)       # runs 2 eager warm-up steps on batches[0]
+    losses_a, losses_b = [], []
+    for _ in range(2):                                                    # the twin takes the same two warm-up steps
+        ob.zero_grad()
+        out, ar, vr = mb(*batches[0])
+        loss_fn(out, batches[0][2], batches[0][0], ar, batches[0][1], vr)[0].mean().backward()
+        ob.step()
+    for i, (a, v, c) in enumerate(batches[1:7]):
+        if i == 3:
+            oa.param_groups[0]["lr"] = 2.5e-4; ob.param_groups[0]["lr"] = 2.5e-4     # ReduceLROnPlateau-style change
+        losses_a.append(float(gstep(a, v, c)[0]))
+        ob.zero_grad()
+        out, ar, vr = mb(a, v, c)
+        t = loss_fn(out, c, a, ar, v, vr)
+        t[0].mean().backward()
+        ob.step()
+        losses_b.append(float(t[0]))
+    assert losses_a == pytest.approx(losses_b, rel=1e-6)
+    assert oa.step_count == ob.step_count == 8
+    for (k, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+        # same kernels in the same order; only the embedding scatter (atomicAdd order) and the bias-correction powf
+        # (device vs host libm) may differ in the last bits
+        torch.testing.assert_close(pa, pb, rtol=2e-5, atol=2e-6, msg=k)

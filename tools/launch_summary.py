@@ -1,23 +1,27 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time share per kernel."""
-import collections
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: total time per kernel name."""
 import csv
-import re
+import collections
 import sys
 
-rows = list(csv.reader(open(sys.argv[1])))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
-hdr, data = rows[hi], rows[hi + 1:]
-ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
-tot, cnt = collections.Counter(), collections.Counter()
-for r in data:
-    if len(r) <= vi:
+path = sys.argv[1]
+rows = []
+with open(path, newline="") as fh:
+    lines = [ln for ln in fh if ln.startswith('"')]
+rd = csv.reader(lines)
+hdr = next(rd)
+ki, mi, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+agg = collections.OrderedDict()
+for r in rd:
+    if r[mi] != "gpu__time_duration.sum":
         continue
-    name = re.sub(r'\(.*', '', r[ki])[:90]
-    v = float(r[vi].replace(',', ''))
-    v = v / 1000 if r[ui] == 'ns' else (v * 1000 if r[ui] == 'ms' else v)
-    tot[name] += v
-    cnt[name] += 1
-T = sum(tot.values())
-print(f"total {T:.1f} us over {sum(cnt.values())} launches")
-for n, v in tot.most_common(int(sys.argv[2]) if len(sys.argv) > 2 else 25):
-    print(f"{v:10.1f} us {100 * v / T:5.1f}%  n={cnt[n]:4d}  avg={v / cnt[n]:8.2f} us  {n}")
+    v = float(r[vi].replace(",", ""))
+    us = v / 1e3 if r[ui] in ("nsecond", "ns") else (v if r[ui] in ("usecond", "us") else v * 1e3)
+    name = r[ki]
+    a = agg.setdefault(name, [0.0, 0])
+    a[0] += us
+    a[1] += 1
+tot = sum(a[0] for a in agg.values())
+n = sum(a[1] for a in agg.values())
+print(f"total {tot:.1f} us over {n} launches")
+for name, (us, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+    print(f"{us:10.1f} us {100 * us / tot:5.1f}%  n={c:4d}  avg={us / c:8.2f} us  {name[:100]}")
