@@ -41,7 +41,9 @@ __global__ void __launch_bounds__(R2_THREADS, 1)
 recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_constant__ CUtensorMap map_wt,
                   const __grid_constant__ Recur2BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by OFFSET (not by integer round-trip): the pointer keeps its shared address space, so every
+  // access below compiles to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int H = R2_H, A = R2_A, AV = R2_AV, AP = B2_AP, UPR = B2_UPR;
   const int B = p.B, T = p.T, S = p.S;
 
@@ -232,11 +234,11 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
             dcr[u] = dct * fg;
           }
           // publish the bf16 row FIRST (A operand of the recurrent GEMM) and the fp32 copy for the attention backward
-          float4* dsm = reinterpret_cast<float4*>(sDg) + 4 * tid;
+          float4* dsm = reinterpret_cast<float4*>(sDg) + tid;        // [q][lane group]: conflict-free 16-byte accesses
           uint32_t pk[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            dsm[q] = make_float4(dg[4 * q], dg[4 * q + 1], dg[4 * q + 2], dg[4 * q + 3]);
+            dsm[q * 128] = make_float4(dg[4 * q], dg[4 * q + 1], dg[4 * q + 2], dg[4 * q + 3]);
             __nv_bfloat162 lo = __floats2bfloat162_rn(dg[4 * q], dg[4 * q + 1]), hi = __floats2bfloat162_rn(dg[4 * q + 2], dg[4 * q + 3]);
             pk[2 * q] = *reinterpret_cast<uint32_t*>(&lo);
             pk[2 * q + 1] = *reinterpret_cast<uint32_t*>(&hi);
@@ -259,7 +261,7 @@ recur2_bwd_kernel(const __grid_constant__ CUtensorMap map_dg, const __grid_const
         float dg[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 v4 = *(reinterpret_cast<const float4*>(sDg) + 4 * L + q);
+          const float4 v4 = *(reinterpret_cast<const float4*>(sDg) + q * 128 + L);
           dg[4 * q] = v4.x; dg[4 * q + 1] = v4.y; dg[4 * q + 2] = v4.z; dg[4 * q + 3] = v4.w;
         }
         float pt[32];                               // 24 live: chunk slot cs = i / 4 (chunk 2 cs + half), frame i % 4

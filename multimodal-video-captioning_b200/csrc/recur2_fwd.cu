@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(R2_THREADS, 1)
 recur2_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ Recur2FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by OFFSET (not by integer round-trip): the pointer keeps its shared address space, so every
+  // access below compiles to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int H = R2_H, A = R2_A, AV = R2_AV, HP = F2_HP, UPR = F2_UPR;
   const int B = p.B, T = p.T, K = p.K, S = p.S;
 
