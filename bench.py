@@ -297,7 +297,7 @@ def config_block(workload, world, host_format):
 TRAINING = ("train", "train_dual", "recnet_global", "recnet_local")
 
 
-def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, world, lib, use_graph=True):
+def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, world, lib, use_graph=True, force_nccl=False):
     """Device-resident value, end-to-end value, roofline of the dominant kernel for one workload -> dict."""
     import torch.distributed as dist
     from salstm import functional as Fn
@@ -333,7 +333,8 @@ def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, wor
 
     if training:
         loss_fn = Lm.ModalityWiseReconstructionLossBuilder(rec_type=w["rec"], **LAMBDAS)
-        opt = FlatClipAdam(model.parameters(), lr=1e-4, weight_decay=1e-5, clip_value=5.0, world_size=world)
+        opt = FlatClipAdam(model.parameters(), lr=1e-4, weight_decay=1e-5, clip_value=5.0, world_size=world,
+                           fused_comm=False if force_nccl else None)
 
         def step_eager(batch):
             audio, visual, caps = batch
@@ -474,6 +475,10 @@ def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, wor
     cfg = config_block(workload, world, host_format)
     cfg["step"] = ("one optimiser step recorded as a CUDA graph and replayed (salstm.trainer.GraphedTrainStep)" if graphed
                    else "eager: one Python call per module, as src/train.py issues them")
+    if training and world > 1:
+        cfg["grad_exchange"] = ("one kernel over NVSwitch multicast: in-switch reduce-scatter (multimem.ld_reduce) + sharded "
+                                "clip/Adam + multicast all-gather of the parameters (mvc_clip_adam_multimem)"
+                                if getattr(opt, "_mc", None) is not None else "NCCL all-reduce of the flat fp32 gradient buffer")
     return {"metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": precision, "data": "synthetic", "config": cfg,
@@ -498,6 +503,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true",
                     help="time the eager train step (what src/train.py issues) instead of the CUDA-graph replay")
+    ap.add_argument("--nccl", action="store_true",
+                    help="N > 1: exchange gradients with an NCCL all-reduce instead of the fused multicast kernel")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the greedy-decode block the default (train) line carries as `secondary`")
     ap.add_argument("--host-format", default=None, choices=["fp32", "bf16", "shards"],
@@ -548,7 +555,7 @@ def main():
     if rank == 0:
         sampler.start()
     line = measure_b200(args.workload, args.precision, args.host_format, args.steps, warmup, dev, rank, world, lib,
-                        use_graph=not args.eager)
+                        use_graph=not args.eager, force_nccl=args.nccl)
     secondary = None
     if args.workload == "train" and not args.no_secondary:
         # the second half of BASELINE.json's metric: greedy-decode captions/s (configs[2] per-GPU shape), same process

@@ -397,6 +397,19 @@ int mvc_clip_adam_step_dev(float* param, const float* grad, float* exp_avg, floa
                            float* max_exp_avg_sq, int64_t n, float* state_dev, int tick, float beta1, float beta2,
                            float eps, float weight_decay, float clip_value, float grad_scale, void* stream);
 
+/* Data-parallel trainer tail as ONE kernel over NVSwitch multicast (the per-step gradient all-reduce of
+ * train.py's data-parallel variant + train.py:207-210): param_mc / grad_mc are the MULTICAST addresses of the flat fp32
+ * parameter / gradient buffers, which every rank allocated symmetrically and bound to one multicast object (the host
+ * layer does this with torch.distributed._symmetric_memory); param_local and the optimiser state are this rank's own
+ * buffers.  The rank owns elements [lo, hi) (multiples of 4): multimem.ld_reduce sums the replicas' gradients in the
+ * switch, the clip + Adam(amsgrad) update is applied to the owned slice, multimem.st writes the new parameters into
+ * every replica.  grad_scale = 1/world.  The caller brackets the call with cross-rank barriers (all gradients written
+ * before / all slices stored after). */
+int mvc_clip_adam_multimem(const float* param_local, float* param_mc, const float* grad_mc, float* exp_avg,
+                           float* exp_avg_sq, float* max_exp_avg_sq, int64_t lo, int64_t hi, float* state_dev, int tick,
+                           float beta1, float beta2, float eps, float weight_decay, float clip_value, float grad_scale,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

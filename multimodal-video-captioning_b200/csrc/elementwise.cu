@@ -438,6 +438,61 @@ __global__ void clip_adam_dev_kernel(float* __restrict__ p, const float* __restr
 }
 __global__ void adam_tick_kernel(float* __restrict__ state) { state[0] += 1.f; }
 
+// ---- gradient exchange fused with the optimiser over NVSwitch multicast (NVLS), one kernel:
+//   reduce-scatter : this rank owns elements [lo, hi); multimem.ld_reduce.add on the MULTICAST address of the gradient
+//                    buffer makes the switch sum the eight replicas' gradients and deliver ONE value per element;
+//   update         : clip + Adam(amsgrad) on the owned slice only (1/world of the optimiser work and state traffic);
+//   all-gather     : multimem.st of the updated PARAMETERS to the multicast address of the parameter buffer: the
+//                    switch writes them into every replica.
+// Per GPU that is n*4 bytes out + n*4 bytes in over NVLink (~42 us for 9.4 M parameters at 900 GB/s per direction)
+// instead of an NCCL all-reduce (175 us measured, NVLS algorithm) followed by a full-size Adam pass (52 us).
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__global__ void clip_adam_multimem_kernel(const float* __restrict__ p_local, float* __restrict__ p_mc,
+                                          const float* __restrict__ g_mc, float* __restrict__ m, float* __restrict__ v,
+                                          float* __restrict__ vmax, int64_t lo, int64_t hi, const float* __restrict__ state,
+                                          float b1, float b2, float eps, float wd, float clip, float grad_scale) {
+  const float step = state[0], lr = state[1];
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  const float lr1 = lr / bc1;
+  const int64_t n4 = (hi - lo) >> 2;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n4; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = lo + 4 * j;
+    const float4 g4 = multimem_ld_reduce_add(g_mc + i);
+    const float4 p4 = *reinterpret_cast<const float4*>(p_local + i);
+    float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i),
+           x4 = *reinterpret_cast<const float4*>(vmax + i);
+    float gs[4] = {g4.x, g4.y, g4.z, g4.w}, ps[4] = {p4.x, p4.y, p4.z, p4.w}, ms[4] = {m4.x, m4.y, m4.z, m4.w},
+          vs[4] = {v4.x, v4.y, v4.z, v4.w}, xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float gi = gs[e] * grad_scale;
+      if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+      gi = fmaf(wd, ps[e], gi);
+      ms[e] = b1 * ms[e] + (1.f - b1) * gi;
+      vs[e] = b2 * vs[e] + (1.f - b2) * gi * gi;
+      xs[e] = fmaxf(xs[e], vs[e]);
+      ps[e] = ps[e] - lr1 * (ms[e] / (sqrtf(xs[e]) / bc2_sqrt + eps));
+    }
+    *reinterpret_cast<float4*>(m + i) = make_float4(ms[0], ms[1], ms[2], ms[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vs[0], vs[1], vs[2], vs[3]);
+    *reinterpret_cast<float4*>(vmax + i) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+    multimem_st(p_mc + i, make_float4(ps[0], ps[1], ps[2], ps[3]));
+  }
+  __threadfence_system();
+}
+
 static inline int grid_for(int64_t n, int block = 256) {
   int64_t g = cdiv(n, block);
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -717,6 +772,28 @@ extern "C" int mvc_clip_adam_step_dev(float* param, const float* grad, float* ex
   clip_adam_dev_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n,
                                                                    state_dev, beta1, beta2, eps, weight_decay, clip_value,
                                                                    grad_scale);
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mvc_clip_adam_multimem(const float* param_local, float* param_mc, const float* grad_mc, float* exp_avg,
+                                      float* exp_avg_sq, float* max_exp_avg_sq, int64_t lo, int64_t hi, float* state_dev,
+                                      int tick, float beta1, float beta2, float eps, float weight_decay, float clip_value,
+                                      float grad_scale, void* stream) {
+  MVC_CHECK(param_local && param_mc && grad_mc && exp_avg && exp_avg_sq && max_exp_avg_sq && state_dev,
+            "mvc_clip_adam_multimem: null argument");
+  MVC_CHECK(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, "mvc_clip_adam_multimem: [lo, hi) must be multiples of 4");
+  MVC_CHECK(((reinterpret_cast<uintptr_t>(param_mc) | reinterpret_cast<uintptr_t>(grad_mc) |
+              reinterpret_cast<uintptr_t>(param_local)) & 15u) == 0, "mvc_clip_adam_multimem: buffers must be 16-byte aligned");
+  if (tick) {
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state_dev);
+    MVC_LAUNCH_CHECK();
+  }
+  if (hi == lo) return 0;
+  ProfScope prof(PK_ADAM, 0, 0, 0, (cudaStream_t)stream);
+  clip_adam_multimem_kernel<<<grid_for((hi - lo) / 4), 256, 0, (cudaStream_t)stream>>>(
+      param_local, param_mc, grad_mc, exp_avg, exp_avg_sq, max_exp_avg_sq, lo, hi, state_dev, beta1, beta2, eps,
+      weight_decay, clip_value, grad_scale);
   MVC_LAUNCH_CHECK();
   return 0;
 }

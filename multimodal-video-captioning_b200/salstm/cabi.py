@@ -119,6 +119,7 @@ SIGNATURES = {
     "mvc_local_recon_loss": (i32, [vp, i64, vp, i64, i64, i32, vp, vp, i64, f32, vp, vp]),
     "mvc_loss_combine": (i32, [vp, f32, f32, f32, i32, i32, vp]),
     "mvc_scale_by_scalar": (i32, [vp, i64, vp, vp]),
+    "mvc_clip_adam_multimem": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, vp, i32, f32, f32, f32, f32, f32, f32, vp]),
     "mvc_clip_adam_step_dev": (i32, [vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, f32, f32, f32, f32, vp]),
     "mvc_clip_adam_step": (i32, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, i32, f32, vp]),
 }

@@ -24,9 +24,15 @@ import torch
 from . import functional as Fn
 
 
+def C_void(addr: int):
+    import ctypes
+    return ctypes.c_void_p(int(addr))
+
+
 class FlatClipAdam(torch.optim.Optimizer):
     def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5,
-                 clip_value: float = 5.0, process_group=None, world_size: Optional[int] = None, amsgrad: bool = True):
+                 clip_value: float = 5.0, process_group=None, world_size: Optional[int] = None, amsgrad: bool = True,
+                 fused_comm: Optional[bool] = None):
         if not amsgrad:
             raise NotImplementedError("FlatClipAdam implements the reference's Adam(amsgrad=True) (train.py:86-88)")
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip_value=clip_value)
@@ -45,6 +51,11 @@ class FlatClipAdam(torch.optim.Optimizer):
         self._arena = None
         self._pending = []          # async all-reduce work handles of this step (bucketed mode)
         self._dev_state = None      # [step count, lr] on the device: set by GraphedTrainStep (CUDA-graph replay)
+        # fused_comm: exchange gradients and update parameters in ONE kernel over NVSwitch multicast
+        # (mvc_clip_adam_multimem: in-switch reduce-scatter + sharded clip/Adam + multicast all-gather) instead of an NCCL
+        # all-reduce followed by a full-size update.  None = use it when world > 1 and the fabric supports multicast.
+        self.fused_comm = fused_comm
+        self._mc = None             # (symmetric-memory handle of flat_p, handle of flat_g, lo, hi) when active
 
     # convenience mirrors of the single param group (kept in sync with lr schedulers)
     @property
@@ -66,9 +77,8 @@ class FlatClipAdam(torch.optim.Optimizer):
             old = {id(p): (o, p.numel()) for p, o in zip(self._live, self._offsets)}
             old_m, old_v, old_vmax = self.m, self.v, self.vmax
         n = sum(p.numel() for p in live)
-        flat_p = torch.empty(n, device=dev, dtype=torch.float32)
-        flat_g = torch.empty(n, device=dev, dtype=torch.float32)
-        m, v, vmax = (torch.zeros(n, device=dev, dtype=torch.float32) for _ in range(3))
+        flat_p, flat_g = self._alloc_flat(n, dev)
+        m, v, vmax = (torch.zeros(flat_p.numel(), device=dev, dtype=torch.float32) for _ in range(3))
         off, offsets = 0, []
         for p in live:
             k = p.numel()
@@ -90,6 +100,35 @@ class FlatClipAdam(torch.optim.Optimizer):
             # backward kernels write gradients straight into these views (functional.GradArena)
             self._arena = Fn.GradArena(live, self._views)
             Fn.register_grad_arena(self._arena)
+
+    def _alloc_flat(self, n: int, dev):
+        """Flat parameter / gradient buffers.  Under data parallelism on an NVSwitch fabric they are allocated as
+        SYMMETRIC memory (same size on every rank) and bound to a multicast object, so that the fused exchange + update
+        kernel can address all replicas at once; otherwise plain device memory."""
+        self._mc = None
+        world = self.world or 1
+        want = self.fused_comm if self.fused_comm is not None else (world > 1)
+        if want and world > 1 and dev.type == "cuda":
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm_mem
+                group = self.group if self.group is not None else dist.group.WORLD
+                n_pad = (n + 4 * world - 1) // (4 * world) * (4 * world)          # every rank owns a float4-aligned slice
+                flat_p = symm_mem.empty(n_pad, dtype=torch.float32, device=dev)
+                flat_g = symm_mem.empty(n_pad, dtype=torch.float32, device=dev)
+                hp, hg = symm_mem.rendezvous(flat_p, group), symm_mem.rendezvous(flat_g, group)
+                if hp.multicast_ptr and hg.multicast_ptr:
+                    flat_p.zero_(); flat_g.zero_()
+                    per = n_pad // world
+                    rank = dist.get_rank(group)
+                    self._mc = (hp, hg, rank * per, (rank + 1) * per)
+                    return flat_p, flat_g
+                if self.fused_comm:
+                    raise RuntimeError("no multicast support on this fabric")
+            except Exception as e:
+                if self.fused_comm:
+                    raise RuntimeError(f"FlatClipAdam(fused_comm=True): symmetric-memory / multicast setup failed: {e}")
+        return (torch.empty(n, device=dev, dtype=torch.float32), torch.empty(n, device=dev, dtype=torch.float32))
 
     def zero_grad(self, set_to_none: bool = True):
         """Before the first step: plain ``grad = None``.  Afterwards gradients live in the flat buffer; on CUDA the
@@ -132,6 +171,8 @@ class FlatClipAdam(torch.optim.Optimizer):
         exchanged by the backward-pass hook (GradBuckets) are only waited for."""
         import torch.distributed as dist
         self._sync_views()
+        if self._mc is not None:
+            return                      # the exchange happens inside step() (mvc_clip_adam_multimem)
         if self._pending:
             for w in self._pending:
                 w.wait()
@@ -155,6 +196,11 @@ class FlatClipAdam(torch.optim.Optimizer):
         self.step_count += 1
         g = self.param_groups[0]
         scale = 1.0 / self.world if (self.world is not None and self.world > 1) else 1.0
+        if self._mc is not None:
+            self._fused_exchange_and_update(ranges, g, scale)
+            if self._arena is not None:
+                self._arena.new_step()
+            return loss
         for k, (lo, hi) in enumerate(ranges):
             if self._dev_state is not None:      # graph-capturable form: step count and lr live on the device
                 from . import cabi
@@ -169,6 +215,28 @@ class FlatClipAdam(torch.optim.Optimizer):
         if self._arena is not None:
             self._arena.new_step()
         return loss
+
+    def _fused_exchange_and_update(self, ranges, g, scale):
+        """barrier (every rank's gradients are complete) -> ONE kernel: in-switch sum of the replicas' gradients for the
+        slice this rank owns, clip + Adam on that slice, multicast store of the new parameters into every replica ->
+        barrier (every slice has landed everywhere)."""
+        from . import cabi
+        hp, hg, lo, hi = self._mc
+        n_live = sum(p.numel() for p in self._live)
+        if ranges != [(0, n_live)]:
+            raise RuntimeError("FlatClipAdam(fused_comm): every live parameter must receive a gradient each step")
+        if self._dev_state is None:
+            self._dev_state = torch.tensor([float(self.step_count - 1), float(g["lr"])], device=self.flat_p.device)
+            self._lr_on_dev = float(g["lr"])
+        elif getattr(self, "_lr_on_dev", None) != float(g["lr"]) and not torch.cuda.is_current_stream_capturing():
+            self._dev_state[1] = float(g["lr"])
+            self._lr_on_dev = float(g["lr"])
+        hg.barrier(channel=0)
+        cabi.check(cabi.lib().mvc_clip_adam_multimem(
+            cabi.ptr(self.flat_p), C_void(hp.multicast_ptr), C_void(hg.multicast_ptr), cabi.ptr(self.m), cabi.ptr(self.v),
+            cabi.ptr(self.vmax), lo, hi, cabi.ptr(self._dev_state), 1, g["betas"][0], g["betas"][1], g["eps"],
+            g["weight_decay"], g["clip_value"], scale, cabi.stream_ptr()), "mvc_clip_adam_multimem")
+        hp.barrier(channel=1)
 
     # ---- checkpointing: the flat moments, addressed by parameter order
     def state_dict(self):

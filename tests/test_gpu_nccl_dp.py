@@ -51,7 +51,8 @@ def _worker(rank, world, port, precision, q):
         lam = dict(reg_lambda=0.0005, audio_recon_lambda=0.00005, visual_recon_lambda=0.5)
         model = AVCaptioning(Vocab(), 1.0, "global", device=dev, precision=precision).to(dev)
         sd = model.state_dict(); sd.update({k: p[k].clone() for k in sd}); model.load_state_dict(sd)
-        opt = FlatClipAdam(model.parameters(), lr=1e-3, weight_decay=1e-5, clip_value=5.0, world_size=world)
+        opt = FlatClipAdam(model.parameters(), lr=1e-3, weight_decay=1e-5, clip_value=5.0, world_size=world,
+                           fused_comm=False)                 # the NCCL all-reduce path (the fused path is tested below)
         a, v, c = shard_batch(audio, visual, caps, rank, world)
         for it in range(2):                                  # second iteration exercises the gradient arena path
             opt.zero_grad()
@@ -87,7 +88,43 @@ def _worker(rank, world, port, precision, q):
         other = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(other, flat)
         same = all(torch.equal(other[0], o) for o in other)
-        q.put((rank, bad, same))
+        # ---- the fused exchange + update over NVSwitch multicast (mvc_clip_adam_multimem) must land on the same parameters
+        # as NCCL all-reduce + full-size update, step after step, and leave identical replicas
+        fused = "unsupported"
+        torch.manual_seed(1)
+        twins = []
+        for fc in (False, True):
+            m2 = AVCaptioning(Vocab(), 1.0, "global", device=dev, precision=precision).to(dev)
+            m2.load_state_dict({k: p[k].clone() for k in m2.state_dict()})
+            try:
+                o2 = FlatClipAdam(m2.parameters(), lr=1e-3, weight_decay=1e-5, clip_value=5.0, world_size=world, fused_comm=fc)
+                for it in range(3):
+                    o2.zero_grad()
+                    out, ar, vr = m2(a.to(dev), v.to(dev), c.to(dev))
+                    Lm.ModalityWiseReconstructionLoss(out, c.to(dev), a.to(dev), ar, v.to(dev), vr, rec_type="global",
+                                                      **lam)[0].mean().backward()
+                    o2.all_reduce_grads()
+                    o2.step()
+                twins.append((m2, o2))
+            except RuntimeError as e:
+                if "multicast" in str(e) or "symmetric" in str(e):
+                    break
+                raise
+        if len(twins) == 2:
+            (ma, oa), (mb, ob) = twins
+            assert ob._mc is not None
+            fused = "ok"
+            for (k, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+                if not torch.allclose(pa, pb, rtol=2e-5, atol=2e-6):
+                    fused = f"{k}: max diff {float((pa - pb).abs().max()):.3e}"
+                    break
+            n_live = sum(t.numel() for t in ob._live)
+            flat2 = ob.flat_p[:n_live].clone()
+            other2 = [torch.empty_like(flat2) for _ in range(world)]
+            dist.all_gather(other2, flat2)
+            if not all(torch.equal(other2[0], o) for o in other2):
+                fused = "replicas diverged under the fused exchange"
+        q.put((rank, bad, same, fused))
     finally:
         dist.destroy_process_group()
 
@@ -109,6 +146,8 @@ def test_nccl_dp_flat_gradient_is_mean_of_shard_gradients(precision):
         p.join(600)
         assert p.exitcode == 0
     res = sorted(q.get(timeout=5) for _ in range(world))
-    for rank, bad, same in res:
+    for rank, bad, same, fused in res:
         assert not bad, f"rank {rank}:\n" + "\n".join(bad)
         assert same, "replicas diverged after the optimiser step"
+        assert fused in ("ok", "unsupported"), f"rank {rank}: fused multicast exchange: {fused}"
+    print("fused multicast exchange:", res[0][3])
