@@ -597,15 +597,17 @@ def roofline_pass(lib, workload, precision, steps, step, resident, shape, pk, ar
         per_step = (per_f(2048) + per_f(128)) / 2 if WORKLOADS[workload].get("dual") else per_f(F)
         alg = per_step * S
         bound, peak, unit, scale = "tensor", pk["tensor"], "TFLOP/s", 1e12
-        name = (f"recur_fwd_kernel (persistent SA-LSTM recurrence, {S} steps/launch: attention + tcgen05 gate GEMM "
-                f"128x{4 * H}x{F + H} + LSTM cell), B={B}")
+        name = (f"recur2_fwd_kernel (persistent SA-LSTM recurrence, {S} steps/launch: attention + projected-key context sum "
+                f"out of TMEM + tcgen05 recurrent GEMM 128x{4 * H}x{H} + LSTM cell), B={B}")
         # DRAM bytes per launch of this kernel (dram__bytes_read.sum + dram__bytes_write.sum, one `ncu --set full`
-        # capture of this command at the C2 shape: profiles/ncu_final_kernels_r1.txt); None for other shapes
-        traffic = 66175232 + 6105088 if (B, T, L, V) == SHAPES["msvd"] and workload == "train" else None
+        # capture of this command at the C2 shape: profiles/ncu_recur2_kernels_r2.txt); None for other shapes
+        traffic = 55403776 + 5380096 if (B, T, L, V) == SHAPES["msvd"] and workload == "train" else None
         extra = {"traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes read+write)",
                  "algorithmic_flops_per_launch": alg, "peak_source": pk["src"] + " (bf16_tflops_sustained)",
-                 "note": "latency/sync-bound by construction: 2 grid barriers + one L2 round trip per phase per step "
-                         "(see profiles/recur_phases_r1.txt); tensor pipe is idle between steps"}
+                 "note": "algorithmic flops = SURVEY 8d accounting of the recurrence (gate contraction over F+H, query "
+                         "projection, scores, context sum); the kernel is latency bound (a 23-step dependency chain at M=128: "
+                         "two grid-scope signal hops + two cluster-scope hops per step, profiles/recur2_phases_r2.txt); the "
+                         "contraction over F itself runs once per sequence in the P = keys.Wc^T GEMM outside the kernel"}
     else:
         # launch-chain paths: soft-attention forward kernel, reads keys [B,T,F] + U.k [B,T,A] once per launch
         # (beam: the 5 beams of a video share ONE staged key block and U.k slab; only queries / outputs are per beam)

@@ -223,6 +223,34 @@ def build_caption_mask(outputs, captions=None):
     return Fn.caption_mask(outputs, captions).bool()
 
 
+def decode_batch(vocab, ids):
+    """[vocab.decode_indexes(row[1:]) for row in ids] (get_loader.py:79-89: words up to the first <EOS>, joined by
+    spaces) for a whole [B, L] id matrix at once: one table lookup over the matrix and one first-EOS search instead of a
+    Python loop with a dict lookup and an isinstance check per token.  Vocabularies without a dense
+    `itos` table fall back to the vocabulary's own method."""
+    import numpy as np
+    arr = np.asarray(ids, dtype=np.int64)
+    itos = getattr(vocab, "itos", None)
+    if arr.ndim != 2 or not isinstance(itos, dict) or len(itos) == 0 or arr.size == 0 or \
+            int(arr[:, 1:].max(initial=0)) >= len(itos) or int(arr[:, 1:].min(initial=0)) < 0:
+        return [vocab.decode_indexes(o[1:]) for o in (ids.tolist() if hasattr(ids, "tolist") else ids)]
+    table = getattr(vocab, "_mvc_itos_table", None)
+    if table is None or len(table) != len(itos):
+        try:
+            table = np.array([itos[i] for i in range(len(itos))], dtype=object)
+        except KeyError:
+            return [vocab.decode_indexes(o[1:]) for o in arr.tolist()]
+        try:
+            vocab._mvc_itos_table = table
+        except Exception:
+            pass
+    body = arr[:, 1:]
+    is_eos = body == 2
+    first = np.where(is_eos.any(1), is_eos.argmax(1), body.shape[1])
+    words = table[body]
+    return [" ".join(words[b, :first[b]]) for b in range(body.shape[0])]
+
+
 # --------------------------------------------------------------------------- wrappers (captioning.py)
 DECODER_CONFIG = {"rnn_type": "LSTM", "rnn_num_layers": 1, "rnn_bidirectional": False, "rnn_hidden_size": 512,
                   "rnn_dropout": 0.0, "in_feature_size": 2048 + 128, "embedding_size": 300, "attn_size": 256,
@@ -287,7 +315,7 @@ class AVCaptioning(nn.Module):
     def predict(self, audio_features, visual_features, max_caption_len=30, mode="direct", beam_alpha=0, beam_width=5):
         """-> list[str]; captioning.py:131-144."""
         ids = self.predict_ids(audio_features, visual_features, max_caption_len, mode, beam_alpha, beam_width)
-        return [self.vocab.decode_indexes(o[1:]) for o in ids]
+        return decode_batch(self.vocab, ids)
 
 
 class AVCaptioningDual(nn.Module):
@@ -345,7 +373,7 @@ class AVCaptioningDual(nn.Module):
 
     def predict(self, audio_features, visual_features, max_caption_len=30, mode="direct", beam_alpha=0, beam_width=5):
         ids = self.predict_ids(audio_features, visual_features, max_caption_len, mode, beam_alpha, beam_width)
-        return [self.vocab.decode_indexes(o[1:]) for o in ids]
+        return decode_batch(self.vocab, ids)
 
 
 # Pickle identity.  torch.save(model) (train.py:162-173) records each class as module path + name; the reference's

@@ -169,3 +169,34 @@ def test_launcher_puts_the_package_ahead_of_the_script_directory(tmp_path):
     assert out.returncode == 0, out.stderr
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")][0]
     assert line == f"RESULT reference {os.path.join(PKG, 'models')} {PKG} {{'CIDEr': 1.5}} ['--gpu', '0']"
+
+
+def test_vectorised_detokenisation_equals_decode_indexes():
+    """decode_batch(vocab, ids) == [vocab.decode_indexes(row[1:]) ...] (get_loader.py:79-89), including rows
+    without <EOS>, rows that start with <EOS>, and vocabularies without a dense table (fallback)."""
+    from salstm.modules import decode_batch
+
+    class V:
+        def __init__(self, n):
+            self.itos = {0: "<PAD>", 1: "<SOS>", 2: "<EOS>", 3: "<UNK>"}
+            self.itos.update({i: f"w{i}" for i in range(4, n)})
+
+        def decode_indexes(self, idx):
+            return O.decode_indexes(self.itos, idx)
+
+    g = torch.Generator().manual_seed(0)
+    v = V(40)
+    ids = torch.randint(0, 40, (64, 12), generator=g)
+    ids[0, 1:] = torch.randint(3, 40, (11,), generator=g)       # no EOS at all
+    ids[1, 1] = 2                                               # EOS first -> empty caption
+    want = [v.decode_indexes(r[1:]) for r in ids.tolist()]
+    assert decode_batch(v, ids.tolist()) == want and decode_batch(v, ids.numpy()) == want
+    assert want[1] == "" and "<EOS>" not in " ".join(want)
+
+    class Sparse(V):
+        def __init__(self):
+            super().__init__(40)
+            del self.itos[17]
+    s = Sparse()
+    ok = ids.clone(); ok[ok == 17] = 5
+    assert decode_batch(s, ok.tolist()) == [s.decode_indexes(r[1:]) for r in ok.tolist()]
