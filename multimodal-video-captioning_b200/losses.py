@@ -1,8 +1,9 @@
 """Drop-in for the hot-path half of the reference's `losses` module (src/losses.py:12-137):
 same function names and signatures, evaluated by the fused CUDA loss kernels of libmvc_b200
-(forward value and gradient).  NLPScore (string metrics over pycocoevalcap, losses.py:140-160) is not
-GPU work: the name is re-exported here so that `from losses import ..., NLPScore` (train.py:12) resolves,
-and forwards to the reference's own implementation found further down sys.path."""
+(forward value and gradient).  NLPScore (losses.py:140-160: BLEU / METEOR / ROUGE-L / CIDEr over pycocoevalcap) is
+provided too, so that `from losses import ..., NLPScore` (train.py:12) resolves: BLEU, ROUGE-L and CIDEr come from
+salstm/nlp_score.py (pinned against the reference's scorers); METEOR, a Java program, is delegated to the reference's
+scorer found further down sys.path when it and `java` exist."""
 import importlib.util
 import os
 import sys
@@ -60,9 +61,9 @@ def EntropyLoss(x, ignore_mask):
 _REF_LOSSES = None
 
 
-def _reference_losses():
+def _reference_losses(required: bool = False):
     """The reference's own losses.py: the next `losses.py` on sys.path after this one (the launcher and
-    INTEGRATION.md put the reference's src/ and repository root behind this package)."""
+    INTEGRATION.md put the reference's src/ and repository root behind this package); None when absent."""
     global _REF_LOSSES
     if _REF_LOSSES is None:
         here = os.path.dirname(os.path.abspath(__file__))
@@ -72,17 +73,20 @@ def _reference_losses():
                 root = os.path.dirname(os.path.dirname(os.path.abspath(cand)))       # <reference>/ holds pycocoevalcap/
                 if os.path.isdir(os.path.join(root, "pycocoevalcap")) and root not in sys.path:
                     sys.path.append(root)
-                spec = importlib.util.spec_from_file_location("_mvc_reference_losses", cand)
-                mod = importlib.util.module_from_spec(spec)
-                spec.loader.exec_module(mod)
-                _REF_LOSSES = mod
+                try:
+                    spec = importlib.util.spec_from_file_location("_mvc_reference_losses", cand)
+                    mod = importlib.util.module_from_spec(spec)
+                    spec.loader.exec_module(mod)
+                    _REF_LOSSES = mod
+                except Exception:
+                    _REF_LOSSES = None
                 break
-        else:
-            raise ImportError("NLPScore is the reference's pycocoevalcap wrapper (src/losses.py:140-160): put the "
-                              "reference's src/ directory on sys.path behind multimodal-video-captioning_b200/")
+        if _REF_LOSSES is None and required:
+            raise ImportError("the reference's src/losses.py is not on sys.path behind multimodal-video-captioning_b200/")
     return _REF_LOSSES
 
 
 def NLPScore(ref, hypo):
-    """losses.py:140-160 (BLEU / METEOR / ROUGE-L / CIDEr over pycocoevalcap): forwarded to the reference."""
-    return _reference_losses().NLPScore(ref, hypo)
+    """losses.py:140-160 -> {"Bleu_1".."Bleu_4", "METEOR", "ROUGE_L", "CIDEr"} for dicts {id: [sentence, ...]}."""
+    from salstm.nlp_score import nlp_score
+    return nlp_score(ref, hypo, _reference_losses())

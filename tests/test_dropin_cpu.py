@@ -63,25 +63,26 @@ def test_repo_pickle_roundtrip(tmp_path):
     assert type(pickle.loads(data)) is AVCaptioningDual
 
 
-def test_nlpscore_is_importable_and_forwards_to_the_reference(tmp_path, monkeypatch):
+def test_nlpscore_matches_the_reference_scorers():
+    """`from losses import ..., NLPScore` (train.py:12) resolves to this package, and BLEU-1..4 / ROUGE-L / CIDEr equal
+    what the reference's pycocoevalcap scorers return on the committed seeded sentence sets (tools/make_golden_r2.py)."""
+    import json
+    import math
     import losses as L
     assert os.path.dirname(L.__file__) == PKG
-    from losses import ModalityWiseReconstructionLossBuilder, NLPScore  # noqa: F401  (train.py:12)
-    ref_src = tmp_path / "ref" / "src"
-    ref_src.mkdir(parents=True)
-    (ref_src / "losses.py").write_text(textwrap.dedent("""
-        def NLPScore(ref, hypo):
-            return {"CIDEr": float(len(ref) + len(hypo))}
-    """))
-    monkeypatch.setattr(L, "_REF_LOSSES", None)
-    monkeypatch.syspath_prepend(str(ref_src))
-    sys.path.remove(str(ref_src)); sys.path.append(str(ref_src))          # behind the package, as the launcher does
-    assert L.NLPScore({"a": ["x"]}, {"a": ["y"], "b": ["z"]}) == {"CIDEr": 3.0}
-    monkeypatch.setattr(L, "_REF_LOSSES", None)
-    sys.path.remove(str(ref_src))
-    if not any(os.path.isfile(os.path.join(d or ".", "losses.py")) and os.path.abspath(d or ".") != PKG for d in sys.path):
-        with pytest.raises(ImportError, match="reference"):
-            L.NLPScore({}, {})
+    from losses import ModalityWiseReconstructionLossBuilder, NLPScore  # noqa: F401
+    cases = json.load(open(os.path.join(GOLDEN, "nlp_scores_small.json")))
+    assert len(cases) >= 5
+    for c in cases:
+        s = NLPScore(c["gts"], c["res"])
+        assert sorted(s) == ["Bleu_1", "Bleu_2", "Bleu_3", "Bleu_4", "CIDEr", "METEOR", "ROUGE_L"]
+        for k in range(4):
+            assert s[f"Bleu_{k + 1}"] == pytest.approx(c["Bleu"][k], abs=1e-12)
+        assert s["ROUGE_L"] == pytest.approx(c["ROUGE_L"], abs=1e-12)
+        assert s["CIDEr"] == pytest.approx(c["CIDEr"], abs=1e-12)
+        assert math.isnan(s["METEOR"]) or 0.0 <= s["METEOR"] <= 1.0      # Java scorer: delegated when available
+    with pytest.raises(AssertionError):
+        NLPScore({"a": ["x"]}, {"b": ["x"]})                              # same contract as the reference scorers
 
 
 def test_flat_clip_adam_is_a_torch_optimizer():
@@ -162,13 +163,18 @@ def test_launcher_puts_the_package_ahead_of_the_script_directory(tmp_path):
         from losses import ModalityWiseReconstructionLossBuilder, NLPScore
         from models import AVCaptioning, AVCaptioningDual
         import models, losses
-        print("RESULT", WHO, os.path.dirname(models.__file__), os.path.dirname(losses.__file__), NLPScore({}, {}), sys.argv[1:])
+        sc = NLPScore({"v": ["a b c"]}, {"v": ["a b c"]})
+        ref = losses._reference_losses()
+        print("RESULT", WHO, os.path.dirname(models.__file__), os.path.dirname(losses.__file__), round(sc["Bleu_1"], 6),
+              ref.NLPScore({}, {}), sys.argv[1:])
     """))
     out = subprocess.run([sys.executable, os.path.join(PKG, "salstm", "launch.py"), str(src / "train.py"), "--gpu", "0"],
                          capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
     assert out.returncode == 0, out.stderr
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")][0]
-    assert line == f"RESULT reference {os.path.join(PKG, 'models')} {PKG} {{'CIDEr': 1.5}} ['--gpu', '0']"
+    # models / losses from this package, get_loader from the script directory, and the reference's own losses.py (METEOR
+    # delegate) discoverable behind the package
+    assert line == f"RESULT reference {os.path.join(PKG, 'models')} {PKG} 1.0 {{'CIDEr': 1.5}} ['--gpu', '0']"
 
 
 def test_vectorised_detokenisation_equals_decode_indexes():

@@ -369,9 +369,11 @@ def test_reference_trainer_runs_unchanged_over_the_b200_modules(dev, tmp_path, r
     tr._save_checkpoint(1, model, {})                                                                          # :66-84
     assert sorted(torch.load(tmp_path / "ck" / "m.ckpt")["v_decoder"]) == sorted(model.v_decoder.state_dict())
     # Trainer.eval: predict() -> strings per video id
-    loader = [(["vid0", "vid1", "vid2", "vid3"], batches[0][0], batches[0][1], [["a b"]] * 4)]
-    scores, gt, gen = tr.eval(model, loader, "val", 1, mode="direct", get_scores=False)
-    assert scores is None and set(gen) == {"vid0", "vid1", "vid2", "vid3"} and all(isinstance(v[0], str) for v in gen.values())
+    loader = [(["vid0", "vid1", "vid2", "vid3"], batches[0][0], batches[0][1], [["w5 w6 w7", "w5 w9"]] * 4)]
+    scores, gt, gen = tr.eval(model, loader, "val", 1, mode="direct", get_scores=True)      # NLPScore: train.py:337-346
+    assert set(gen) == {"vid0", "vid1", "vid2", "vid3"} and all(isinstance(v[0], str) for v in gen.values())
+    assert {"Bleu_1", "Bleu_4", "ROUGE_L", "CIDEr", "METEOR"} <= set(scores) and 0.0 <= scores["Bleu_1"] <= 1.0
+    assert "val/score/direct/CIDEr" in {t for t, _, _ in tr.summary_writer.scalars}
     with torch.no_grad():
         ids = O.av_dual_greedy_ids({k: v.detach().cpu() for k, v in model.state_dict().items()}, batches[0][0],
                                    batches[0][1], 30)

@@ -150,7 +150,45 @@ def gen_total_loss():
     save("total_loss_small", **d)
 
 
+def gen_nlp_scores():
+    """Seeded sentence sets scored by the reference's own pycocoevalcap scorers (Bleu / Rouge / Cider, the three that
+    need no Java) -> tests/golden/nlp_scores_small.json, the pin of salstm/nlp_score.py."""
+    import contextlib
+    import io
+    import json
+    import random
+    from pycocoevalcap.bleu.bleu import Bleu
+    from pycocoevalcap.cider.cider import Cider
+    from pycocoevalcap.rouge.rouge import Rouge
+    rng = random.Random(0)
+    words = [f"w{i}" for i in range(30)]
+
+    def sent(lo, hi):
+        return " ".join(rng.choice(words) for _ in range(rng.randint(lo, hi)))
+    cases = []
+    for _ in range(4):
+        gts, res = {}, {}
+        for v in range(rng.randint(3, 12)):
+            refs = [sent(3, 12) for _ in range(rng.randint(1, 5))]
+            base = refs[0].split()
+            hyp = " ".join(w if rng.random() < 0.7 else rng.choice(words) for w in base[:rng.randint(1, len(base))])
+            gts[f"vid{v}"] = refs
+            res[f"vid{v}"] = [hyp]
+        cases.append((gts, res))
+    cases.append(({"a": ["w1 w2 w3"]}, {"a": ["w9"]}))
+    out = []
+    for gts, res in cases:
+        with contextlib.redirect_stdout(io.StringIO()):
+            rb, _ = Bleu(4).compute_score(gts, res)
+            rr, _ = Rouge().compute_score(gts, res)
+            rc, _ = Cider().compute_score(gts, res)
+        out.append({"gts": gts, "res": res, "Bleu": list(rb), "ROUGE_L": float(rr), "CIDEr": float(rc)})
+    json.dump(out, open(os.path.join(OUT, "nlp_scores_small.json"), "w"))
+    print("nlp_scores_small.json:", len(out), "cases")
+
+
 if __name__ == "__main__":
+    gen_nlp_scores()
     gen_pickles()
     gen_word_step()
     gen_total_loss()
