@@ -725,6 +725,42 @@ def test_bf16_dual_persistent_kernels_vs_fp64_oracle(dev, B, T):
     assert not bad, "\n".join(bad)
 
 
+@pytest.mark.parametrize("B,T,Lc", [(1, 1, 2), (3, 48, 3), (128, 2, 4), (2, 47, 5)])
+def test_bf16_persistent_kernels_edge_shapes(dev, B, T, Lc):
+    """Edges of the projected-keys persistent kernels: a single row / frame / loop step (no recurrent GEMM at all when
+    L = 2), the maximum frame count (T = 48: every TMEM chunk in use), a full batch with two frames."""
+    from models import AVCaptioning
+    import losses as L
+    V = 61
+    p = _wrapper_params("joint", V, "none", 123)
+    p["decoder.out.weight"] /= 6.0
+    audio, visual, caps = O.synth_batch(B, T, Lc, V, seed=40 + T, min_frames=1, min_cap=2)
+    audio, visual = audio / 255.0, visual / 10.0
+    model = AVCaptioning(Vocab(V), 1.0, "none", device=dev, precision="bf16").to(dev)
+    _load(model, p)
+    out, _, _ = model(audio.to(dev), visual.to(dev), caps.to(dev))
+    terms = L.ModalityWiseReconstructionLoss(out, caps.to(dev), reg_lambda=0.0005)
+    terms[0].backward()
+    pd = {k: v.double().requires_grad_() for k, v in p.items()}
+    o_out, _, _ = O.av_forward(pd, audio.double(), visual.double(), caps, 1.0, "none", hoist=True)
+    o_terms = O.modality_wise_loss(o_out, caps, reg_lambda=0.0005)
+    o_terms[0].backward()
+    close(out, o_out, atol=5e-2, rtol=5e-2)
+    close(terms[0], o_terms[0], rtol=2e-2, atol=1e-3)
+    bad = []
+    for k, v in model.named_parameters():
+        ref = pd[k].grad
+        n1, n2 = float(v.grad.norm()), float(ref.norm())
+        if n2 < 1e-9:                               # e.g. dW_hh with a single step: h_0 = 0
+            if n1 > 1e-6:
+                bad.append(f"{k}: expected a zero gradient, norm {n1:.3e}")
+            continue
+        c = cos(v.grad, ref)
+        if c < 0.998 or abs(n1 - n2) > 5e-2 * n2 + 1e-7:
+            bad.append(f"{k}: cosine {c:.5f}, norm {n1:.4e} vs {n2:.4e}")
+    assert not bad, "\n".join(bad)
+
+
 # --------------------------------------------------------------------------- full-size properties (BASELINE configs)
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_config2_shape_properties(dev, precision):
