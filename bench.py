@@ -472,6 +472,24 @@ def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, wor
     pk = peaks()
     # every rank runs the extra steps (the train step contains the gradient all-reduce); rank 0 arms the timers
     roof = roofline_pass(lib, workload, precision, steps, step_eager_fn, resident, shape, pk, arm=(rank == 0))
+    agreement = None
+    if not training and precision == "bf16" and rank == 0:
+        # how many captions of the bf16 tensor-core path equal the fp32 exact path's (ids up to and including the first
+        # <EOS>), on the first input batch; reported, not required -- the fp32 path is the one whose ids are
+        # identical to the reference's
+        with torch.no_grad():
+            ids_b = step_eager_fn(resident[0]).cpu()
+            model.set_precision("fp32")
+            ids_f = step_eager_fn(tuple(t.float() if t.is_floating_point() else t for t in resident[0])).cpu()
+            model.set_precision("bf16")
+
+        def prefix(row):
+            row = row.tolist()
+            body = row[1:]
+            return row[:body.index(2) + 2] if 2 in body else row
+        same = sum(prefix(a_) == prefix(b_) for a_, b_ in zip(ids_b, ids_f))
+        agreement = {"identical_captions": same, "of": int(ids_b.shape[0]), "rate": same / float(ids_b.shape[0]),
+                     "note": "bf16 path vs fp32 exact path on the same batch, default-init weights (near-uniform logits)"}
     cfg = config_block(workload, world, host_format)
     cfg["step"] = ("one optimiser step recorded as a CUDA graph and replayed (salstm.trainer.GraphedTrainStep)" if graphed
                    else "eager: one Python call per module, as src/train.py issues them")
@@ -489,7 +507,8 @@ def measure_b200(workload, precision, host_format, steps, warmup, dev, rank, wor
                              if feeder is not None else
                              "pinned host inputs, double-buffered H2D on a copy stream") +
                             "; result of every step copied D2H asynchronously and consumed one step later"},
-            "gpu_launches": int(launches), "cuda_graph": graphed, "roofline": roof, "peaks": pk["src"]}
+            "gpu_launches": int(launches), "cuda_graph": graphed, "roofline": roof, "peaks": pk["src"],
+            "caption_agreement_vs_fp32": agreement}
 
 
 def main():
@@ -561,7 +580,7 @@ def main():
         # the second half of BASELINE.json's metric: greedy-decode captions/s (configs[2] per-GPU shape), same process
         sec = measure_b200("greedy", args.precision, args.host_format, max(5, args.steps // 2), 3, dev, rank, world, lib)
         secondary = {k: sec[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "config", "e2e",
-                                         "gpu_launches", "roofline")}
+                                         "gpu_launches", "roofline", "caption_agreement_vs_fp32")}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:

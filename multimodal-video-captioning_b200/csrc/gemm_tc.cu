@@ -125,10 +125,7 @@ __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
 
 // 16-bit copy of an output value: bf16, or fp16 with saturation (TcEpilogue::cb_f16)
 __device__ __forceinline__ __nv_bfloat16 to_b16(float r, int f16) {
-  if (f16) {
-    const __half h = __float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f));
-    return *reinterpret_cast<const __nv_bfloat16*>(&h);
-  }
+  if (f16) return __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f))));
   return __float2bfloat16(r);
 }
 
@@ -483,8 +480,9 @@ constexpr int PG_STAGES = 4;
 constexpr int PG_A_BYTES = TC_BM * TC_BK * 2;            // 16 KB
 constexpr int PG_B_BYTES = PG_BN * TC_BK * 2;            // 32 KB
 constexpr int PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;  // 48 KB
-constexpr int PG_EPI_OFF = PG_STAGES * PG_STAGE_BYTES;   // 4 warps x [32][33] floats staging
-constexpr int PG_EPI_BYTES = 4 * 32 * 33 * 4 + 4 * PG_BN * 4;   // per-warp transpose staging + per-warp bias tile
+constexpr int PG_EPI_OFF = PG_STAGES * PG_STAGE_BYTES;   // 4 warps x [32][36] floats staging
+constexpr int PG_STG = 32 * 36;                           // floats per warp: pitch 36 = 16-byte aligned rows (float4 accesses)
+constexpr int PG_EPI_BYTES = 4 * PG_STG * 4 + 4 * PG_BN * 4;    // per-warp transpose staging + per-warp bias tile
 constexpr int PG_BAR_OFF = PG_EPI_OFF + PG_EPI_BYTES;
 constexpr int PG_SMEM = PG_BAR_OFF + (2 * PG_STAGES + 4) * 8 + 16 + 1024;
 
@@ -508,12 +506,31 @@ __device__ __forceinline__ void topk_insert_chunk(const float (&x)[32], float cm
   }
 }
 
-template <int MODE, int A_MN = 0, int B_MN = 0>
+// MC = 1: the CTAs run as CLUSTER PAIRS over two vertically adjacent 128-row tiles of the same 256-column block.  Both
+// need the same B tile, so each CTA fetches only HALF of it (128 of the 256 rows) with a TMA multicast that lands in both
+// CTAs' shared memory: L2 reads per CTA and k-block drop from 48 KB to 32 KB (the 128x256-tile kernel is L2 -> SM
+// bandwidth bound: 43 GB/s per SM x 148 = 6.3 TB/s at 25-33 % tensor-pipe active).  A stage may be refilled only when
+// BOTH CTAs' MMAs have consumed it (the peer's multicast writes into my ring too): the MMA commit arrives on both CTAs'
+// empty barriers (multicast commit, count 2).
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+template <int MODE, int A_MN = 0, int B_MN = 0, int MC = 0>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M,
                             int N, int K, const __grid_constant__ TcEpilogue ep) {
+  static_assert(!MC || (!A_MN && !B_MN), "the multicast pair variant takes K-major operands");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by offset, not by integer round-trip: the pointer keeps its shared address space (LDS / STS, not generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_base + PG_BAR_OFF;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -525,14 +542,19 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (K + TC_BK - 1) / TC_BK;
   const int ntn = (N + PG_BN - 1) / PG_BN, ntm = (M + TC_BM - 1) / TC_BM;
-  const int ntiles = ntn * ntm;
+  // work items: tiles, or (MC) pairs of vertically adjacent tiles shared by the two CTAs of a cluster
+  int crank = 0;
+  if constexpr (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int ntiles = MC ? ntn * ((ntm + 1) / 2) : ntn * ntm;
+  const int tile0 = MC ? (int)blockIdx.x / 2 : (int)blockIdx.x, tile_step = MC ? (int)gridDim.x / 2 : (int)gridDim.x;
+  auto tile_m0 = [&](int tile) { return MC ? (2 * (tile / ntn) + crank) * TC_BM : (tile / ntn) * TC_BM; };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < PG_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
@@ -548,6 +570,10 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (MC) {                               // the peer's barriers are initialised before any multicast / commit
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();
 
@@ -555,8 +581,8 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     if (lane == 0) {
       pdl_wait();
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * PG_BN;
+      for (int tile = tile0; tile < ntiles; tile += tile_step) {
+        const int m0 = tile_m0(tile), n0 = (tile % ntn) * PG_BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int stage = (int)(it % PG_STAGES);
           const uint32_t par = (it / PG_STAGES) & 1u;
@@ -573,6 +599,9 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
 #pragma unroll
             for (int i = 0; i < PG_BN / 64; ++i)
               tma_load_2d(a_dst + PG_A_BYTES + i * 8192, &map_b, full_bar(stage), n0 + i * 64, kb * TC_BK);
+          } else if constexpr (MC) {              // my half of the shared B tile, delivered to both CTAs of the pair
+            tma_load_2d_mc(a_dst + PG_A_BYTES + crank * (PG_B_BYTES / 2), &map_b, full_bar(stage), kb * TC_BK,
+                           n0 + crank * (PG_BN / 2), (uint16_t)0x3);
           } else {
             tma_load_2d(a_dst + PG_A_BYTES, &map_b, full_bar(stage), kb * TC_BK, n0);
           }
@@ -585,7 +614,7 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       constexpr uint32_t idesc = make_idesc_bf16_major(TC_BM, PG_BN, A_MN, B_MN);
       uint32_t it = 0;
       int ti = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      for (int tile = tile0; tile < ntiles; tile += tile_step, ++ti) {
         const int buf = ti & 1;
         mbar_wait(tempty_bar(buf), (((uint32_t)ti >> 1) & 1u) ^ 1u);     // epilogue has drained this buffer
         tc_fence_after();
@@ -603,7 +632,8 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_bf16(tacc, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+          if constexpr (MC) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);
+          else umma_commit(empty_bar(stage));
         }
         umma_commit(tfull_bar(buf));
       }
@@ -611,13 +641,13 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     __syncwarp();
   } else {
     const int q = warp & 3;                       // TMEM lane quarter of this warp
-    float* stg = reinterpret_cast<float*>(smem + PG_EPI_OFF) + (warp - 2) * (32 * 33);
-    float* sbias = reinterpret_cast<float*>(smem + PG_EPI_OFF + 4 * 32 * 33 * 4) + (warp - 2) * PG_BN;   // bias of this tile
+    float* stg = reinterpret_cast<float*>(smem + PG_EPI_OFF) + (warp - 2) * PG_STG;
+    float* sbias = reinterpret_cast<float*>(smem + PG_EPI_OFF + 4 * PG_STG * 4) + (warp - 2) * PG_BN;   // bias of this tile
     pdl_wait();
     int ti = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+    for (int tile = tile0; tile < ntiles; tile += tile_step, ++ti) {
       const int buf = ti & 1;
-      const int m0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * PG_BN;
+      const int m0 = tile_m0(tile), n0 = (tile % ntn) * PG_BN;
       // this tile's bias values -> the warp's private smem copy (broadcast reads below instead of 256 LDGs per thread)
 #pragma unroll
       const int nmain = (MODE != TC_MODE_PLAIN && ep.aux_C) ? ep.n_main : N;   // columns that carry a bias / reduction
@@ -744,28 +774,90 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           lsm = lsm * __expf(lmx - nmx) + part;
           lmx = nmx;
         }
+        // The warp's 32x32 chunk goes row-major through shared memory (thread = accumulator row writes 8 float4; pitch 36
+        // keeps both sides conflict-free) and leaves as float4 per lane: 8 lanes cover the 32 columns of one row, so one
+        // store instruction writes four 128-byte row segments -- 8 store instructions per chunk instead of 32, all
+        // branches hoisted.  (The previous loop, one 4-byte store per lane and row with the null / beta checks inside, ran
+        // at ~190 cycles per row on the single epilogue warp of each scheduler: 26 us per 128x256 tile, three times the
+        // 9 us mainloop -- every big GEMM was epilogue bound, tools/gemm_probe.py.)
+        {
+          float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 8; ++j)
+            srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3]));
+        }
         __syncwarp();
-        const int gn = gn0 + lane;
-        const float bv = sbias[c * 32 + lane];
         const int64_t gm0 = (int64_t)m0 + q * 32;
-        const int nrows = (int)((M - gm0) < 32 ? (M - gm0) : 32);
-        if (gn < N && nrows > 0) {
-          float* dst = ep.C ? ep.C + gm0 * ep.ldc + gn : nullptr;
-          __nv_bfloat16* dstb = ep.Cb ? ep.Cb + gm0 * ep.ldcb + gn : nullptr;
-          const float beta = ep.beta;
-#pragma unroll 4
-          for (int rr = 0; rr < nrows; ++rr) {
-            float r = stg[rr * 33 + lane] + bv;
-            if (dst) {
-              if (beta != 0.f) r += beta * (*dst);
-              *dst = r;
-              dst += ep.ldc;
+        const int cg = lane & 7, rsub = lane >> 3;
+        const int gn = gn0 + cg * 4;
+        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c * 32 + cg * 4);
+        float* Cp = ep.C;
+        __nv_bfloat16* Cbp = ep.Cb;
+        const int64_t ldc = ep.ldc, ldcb = ep.ldcb;
+        const float beta = ep.beta;
+        const int f16 = ep.cb_f16;
+        const bool c_vec = Cp && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp) & 15u) == 0 && gn + 3 < N;
+        const bool cb_vec = Cbp && (ldcb & 3) == 0 && (reinterpret_cast<uintptr_t>(Cbp) & 7u) == 0 && gn + 3 < N;
+        float4 r4[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float4 t4 = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * 36 + cg * 4);
+          r4[it] = make_float4(t4.x + b4.x, t4.y + b4.y, t4.z + b4.z, t4.w + b4.w);
+        }
+        if (gn < N) {
+          if (Cp) {
+            if (c_vec) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int64_t gm = gm0 + it * 4 + rsub;
+                if (gm < M) {
+                  float4* dst = reinterpret_cast<float4*>(Cp + gm * ldc + gn);
+                  if (beta != 0.f) {
+                    const float4 o4 = *dst;
+                    r4[it].x += beta * o4.x; r4[it].y += beta * o4.y; r4[it].z += beta * o4.z; r4[it].w += beta * o4.w;
+                  }
+                  *dst = r4[it];
+                }
+              }
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int64_t gm = gm0 + it * 4 + rsub;
+                if (gm < M) {
+                  float* dst = Cp + gm * ldc + gn;
+                  float rr[4] = {r4[it].x, r4[it].y, r4[it].z, r4[it].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (gn + e < N) {
+                      if (beta != 0.f) rr[e] += beta * dst[e];
+                      dst[e] = rr[e];
+                    }
+                  r4[it] = make_float4(rr[0], rr[1], rr[2], rr[3]);
+                }
+              }
             }
-            if (dstb) {
-              *dstb = to_b16(r, ep.cb_f16);
-              dstb += ep.ldcb;
+          }
+          if (Cbp) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int64_t gm = gm0 + it * 4 + rsub;
+              if (gm < M) {
+                __nv_bfloat16* dstb = Cbp + gm * ldcb + gn;
+                if (cb_vec) {
+                  const __nv_bfloat16 h0 = to_b16(r4[it].x, f16), h1 = to_b16(r4[it].y, f16), h2 = to_b16(r4[it].z, f16),
+                                      h3 = to_b16(r4[it].w, f16);
+                  uint2 pk;
+                  pk.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                  pk.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+                  *reinterpret_cast<uint2*>(dstb) = pk;
+                } else {
+                  const float rr[4] = {r4[it].x, r4[it].y, r4[it].z, r4[it].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (gn + e < N) dstb[e] = to_b16(rr[e], f16);
+                }
+              }
             }
           }
         }
@@ -788,6 +880,10 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) {                               // the peer's last commits / multicasts target my shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
@@ -934,9 +1030,56 @@ static int max_active_clusters(int cs) {
   return n;
 }
 
+// multicast-pair variant (plain epilogue, K-major operands): 74 clusters of 2 CTAs
+static bool mc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // opt-in: measured on B200 at the C2 shapes the pair variant is NOT faster (P GEMM 94 vs 91 us, dW_c 49 vs 42 us):
+    // L2 throughput sits at 17 % of peak in the 1-CTA kernel, so halving the L2 reads of B buys nothing
+    const char* e = getenv("MVC_B200_GEMM_MULTICAST");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+static int launch_tc_persist_mc(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, TcEpilogue ep,
+                                bool pdl, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  MVC_TRY(get_tensor_map(A, M, K, lda, TC_BM, &ma));
+  MVC_TRY(get_tensor_map(B, N, K, ldb, PG_BN / 2, &mb));           // each CTA of a pair fetches half of the B tile
+  auto kern = gemm_bf16_tc_persist_kernel<TC_MODE_PLAIN, 0, 0, 1>;
+  static bool configured = false;
+  if (!configured) {
+    MVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+    configured = true;
+  }
+  const int64_t pairs = cdiv(cdiv(M, TC_BM), 2) * cdiv(N, PG_BN);
+  const int64_t max_clusters = kNumSMs / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * (pairs < max_clusters ? pairs : max_clusters)));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = PG_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 2 : 1;
+  ProfScope prof(PK_GEMM_TC, M, N, K, st);
+  MVC_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, ep));
+  MVC_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int MODE, int A_MN = 0, int B_MN = 0>
 static int launch_tc_persist(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, TcEpilogue ep,
                              bool pdl, cudaStream_t st) {
+  if constexpr (MODE == TC_MODE_PLAIN && !A_MN && !B_MN) {
+    // two or more tile rows and enough tiles to fill the machine in pairs: share every B tile between two CTAs
+    if (mc_enabled() && cdiv(M, TC_BM) >= 2 && cdiv(M, TC_BM) * cdiv(N, PG_BN) >= 64)
+      return launch_tc_persist_mc(M, N, K, A, lda, B, ldb, ep, pdl, st);
+  }
   CUtensorMap ma, mb;
   // K-major operand [rows = M|N, cols = K], box {64 k, rows}; MN-major operand stored [K, M|N], box {64 mn, 64 k}
   if (A_MN) MVC_TRY(get_tensor_map(A, K, M, lda, 64, &ma));
