@@ -1166,7 +1166,12 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
     MVC_CHECK(ep.topk_val && ep.topk_idx && ep.lse_max && ep.lse_sum, "tcgen05 GEMM top-k epilogue: null partial buffers");
     return launch_tc_persist<TC_MODE_TOPK>(M, N, K, A, lda, B, ldb, ep, pdl, st);
   }
-  if (mt * cdiv(N, PG_BN) >= kNumSMs / 2 && K >= 2 * TC_BK)
+  static int persist_min_tiles = -1;
+  if (persist_min_tiles < 0) {
+    const char* e = getenv("MVC_B200_PERSIST_MIN_TILES");
+    persist_min_tiles = e ? atoi(e) : kNumSMs / 2;
+  }
+  if (mt * cdiv(N, PG_BN) >= persist_min_tiles && K >= 2 * TC_BK)
     return launch_tc_persist<TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, pdl, st);
   const int64_t t128 = mt * cdiv(N, 128), t64 = mt * cdiv(N, 64), t32 = mt * cdiv(N, 32);
   const int s128 = splits_for(t128, max_active_clusters<128, 6, TC_MODE_PLAIN>);
