@@ -552,8 +552,11 @@ static DecBwdWs dec_bwd_layout(const MvcDecoderDims* d, void* base) {
     w.dG_b = ar.take<char>(S * B * 4 * H * 2);
     w.wcatT = ar.take<char>((F + H) * 4 * H * 2);
     w.dGT = ar.take<char>(4 * H * SBp * 2);
-    w.xhT = ar.take<char>((F + H) * SBp * 2);
-    w.xembT = ar.take<char>(Ep * SBp * 2);
+    // [emb ; ctx ; h]^T in ONE buffer (rows E + F + H, +8 slack rows): the three LSTM weight gradients that share the
+    // operand dG^T become one GEMM.  The embedding block is transposed first (its Ep - E zero pad rows land on the first
+    // ctx rows), the [ctx ; h] block after it.
+    w.xembT = ar.take<char>((E + F + H + 8) * SBp * 2);
+    w.xhT = w.xembT ? (char*)w.xembT + (size_t)E * SBp * 2 : nullptr;
     w.wieT = ar.take<char>(Ep * 4 * H * 2);
     w.dukT = ar.take<char>(A * BTp * 2);
     w.featsT = ar.take<char>(F * BTp * 2);
@@ -617,10 +620,10 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       // operand transposes of the post-loop weight-gradient GEMMs that only need forward data
       // (recur2 forward never formed ctx: rebuild the ctx halves of the xh slots from the saved alpha first)
       if (use_r2) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, ss));
+      MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
+      MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, ss));        // before xhT: see dec_bwd_layout
       MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, ss));
       MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, ss));
-      MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
-      MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, ss));
       MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, ss));
       MVC_TRY(sg.mark());
     } else {
@@ -726,6 +729,8 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       forked = false;
     }
     if (!pre_t) {
+      MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, st));
+      MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, st));
       MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, st));
       MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
     }
@@ -747,13 +752,19 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       forked = true;
     }
     MVC_TRY(launch_transpose_bf16(q.dG_b, 1, SB, 4 * H, 4 * H, q.dGT, SBp, permH, st));   // natural gate rows
-    MVC_TRY(mvc_gemm_bf16(4 * H, F, SB, q.dGT, SBp, q.xhT, SBp, 0.f, g->w_ih + E, E + F, nullptr, nullptr, 0, st));
-    MVC_TRY(mvc_gemm_bf16(4 * H, H, SB, q.dGT, SBp, hprevT, SBp, 0.f, g->w_hh, H, nullptr, nullptr, 0, st));
-    if (!pre_t) {
-      MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, st));
-      MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, st));
+    if (E % 4 == 0 && (E + F) % 4 == 0 && cdiv(4 * H, 128) * cdiv(E + F + H, 256) >= kNumSMs / 2) {
+      // dW_ih = dG^T . [emb ; ctx] and dW_hh = dG^T . h_prev share the operand dG^T: ONE GEMM over [emb ; ctx ; h]^T whose
+      // epilogue writes columns [0, E+F) to dW_ih and [E+F, E+F+H) to dW_hh (was three launches: 37 + 25 + 29 us)
+      TcEpilogue ep{};
+      ep.mode = TC_MODE_PLAIN;
+      ep.C = g->w_ih; ep.ldc = E + F;
+      ep.C2 = g->w_hh; ep.ldc2 = H; ep.split_n = E + F;
+      MVC_TRY(tc_gemm(4 * H, E + F + H, SB, q.dGT, SBp, q.xembT, SBp, ep, 0, st));
+    } else {
+      MVC_TRY(mvc_gemm_bf16(4 * H, F, SB, q.dGT, SBp, q.xhT, SBp, 0.f, g->w_ih + E, E + F, nullptr, nullptr, 0, st));
+      MVC_TRY(mvc_gemm_bf16(4 * H, H, SB, q.dGT, SBp, hprevT, SBp, 0.f, g->w_hh, H, nullptr, nullptr, 0, st));
+      MVC_TRY(mvc_gemm_bf16(4 * H, E, SB, q.dGT, SBp, q.xembT, SBp, 0.f, g->w_ih, E + F, nullptr, nullptr, 0, st));
     }
-    MVC_TRY(mvc_gemm_bf16(4 * H, E, SB, q.dGT, SBp, q.xembT, SBp, 0.f, g->w_ih, E + F, nullptr, nullptr, 0, st));
     if (!pre_t) {
       MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
       MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, q.wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, st));

@@ -794,10 +794,16 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         const float4 b4 = *reinterpret_cast<const float4*>(sbias + c * 32 + cg * 4);
         float* Cp = ep.C;
         __nv_bfloat16* Cbp = ep.Cb;
-        const int64_t ldc = ep.ldc, ldcb = ep.ldcb;
+        int64_t ldc = ep.ldc;
+        const int64_t ldcb = ep.ldcb;
         const float beta = ep.beta;
         const int f16 = ep.cb_f16;
-        const bool c_vec = Cp && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp) & 15u) == 0 && gn + 3 < N;
+        int gnc = gn, lim = N;                      // column inside the fp32 destination / first column that is not mine
+        if (ep.C2) {                                // two destinations split at column split_n (a multiple of 4)
+          if (gn >= ep.split_n) { Cp = ep.C2; ldc = ep.ldc2; gnc = gn - ep.split_n; }
+          else lim = ep.split_n;
+        }
+        const bool c_vec = Cp && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp + gnc) & 15u) == 0 && gn + 3 < lim;
         const bool cb_vec = Cbp && (ldcb & 3) == 0 && (reinterpret_cast<uintptr_t>(Cbp) & 7u) == 0 && gn + 3 < N;
         float4 r4[8];
 #pragma unroll
@@ -812,7 +818,7 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
               for (int it = 0; it < 8; ++it) {
                 const int64_t gm = gm0 + it * 4 + rsub;
                 if (gm < M) {
-                  float4* dst = reinterpret_cast<float4*>(Cp + gm * ldc + gn);
+                  float4* dst = reinterpret_cast<float4*>(Cp + gm * ldc + gnc);
                   if (beta != 0.f) {
                     const float4 o4 = *dst;
                     r4[it].x += beta * o4.x; r4[it].y += beta * o4.y; r4[it].z += beta * o4.z; r4[it].w += beta * o4.w;
@@ -825,11 +831,11 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
               for (int it = 0; it < 8; ++it) {
                 const int64_t gm = gm0 + it * 4 + rsub;
                 if (gm < M) {
-                  float* dst = Cp + gm * ldc + gn;
+                  float* dst = Cp + gm * ldc + gnc;
                   float rr[4] = {r4[it].x, r4[it].y, r4[it].z, r4[it].w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e)
-                    if (gn + e < N) {
+                    if (gn + e < lim) {
                       if (beta != 0.f) rr[e] += beta * dst[e];
                       dst[e] = rr[e];
                     }
@@ -1165,6 +1171,12 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
   if (ep.mode == TC_MODE_TOPK) {
     MVC_CHECK(ep.topk_val && ep.topk_idx && ep.lse_max && ep.lse_sum, "tcgen05 GEMM top-k epilogue: null partial buffers");
     return launch_tc_persist<TC_MODE_TOPK>(M, N, K, A, lda, B, ldb, ep, pdl, st);
+  }
+  if (ep.C2) {
+    MVC_CHECK(ep.mode == TC_MODE_PLAIN && !(flags & (TC_FLAG_A_MN | TC_FLAG_B_MN)) && ep.split_n % 4 == 0 && ep.split_n > 0 &&
+                  ep.split_n < N && !ep.Cb,
+              "tcgen05 GEMM: the two-destination epilogue needs the plain mode, K-major operands and split_n %% 4 == 0");
+    return launch_tc_persist<TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, pdl, st);
   }
   static int persist_min_tiles = -1;
   if (persist_min_tiles < 0) {

@@ -23,6 +23,11 @@ struct TcEpilogue {
   const float* bias;          // also the (permuted) gate bias in cell mode, may be null
   __nv_bfloat16* Cb;
   int64_t ldcb;
+  // plain mode, persistent kernel: optional SECOND fp32 destination for the columns >= split_n (C2[m, n - split_n], ld ldc2;
+  // split_n a multiple of 4): one GEMM can feed two parameter-gradient tensors that share the A operand
+  float* C2;
+  int64_t ldc2;
+  int split_n;
   int cb_f16;                 // the 16-bit copy is IEEE fp16 (saturating) instead of bf16: 3 more mantissa bits for
                               // the projected keys of the persistent recurrence kernels (recur2.cuh)
   // fused row arg-max (mode == TC_MODE_ARGMAX): per (row, 256-column tile) partial maximum of acc + bias

@@ -70,6 +70,7 @@ classes = [
     ("gemm_tc gates greedy (B,4H,F+H)", (1, B, 2048, 2688)),
     ("gemm_tc uk", (1, B * T, 256, 2176)),
     ("gemm_tc P = keys.Wc^T (BT,4H,F)", (1, B * T, 2048, 2176)),
+    ("gemm_tn dW_ih|dW_hh merged (4H,E+F+H,SB)", (1, 2048, 300 + 2176 + 512, S * B)),
     ("gemm_tn dW_c (4H,F,SB)", (1, 2048, 2176, S * B)),
     ("gemm_tn dW_hh (4H,H,SB)", (1, 2048, 512, S * B)),
     ("gemm_tc gx (SB,4H,Ep)", (1, S * B, 2048, 304)),
