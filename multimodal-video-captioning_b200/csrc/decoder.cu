@@ -51,12 +51,18 @@ struct DecWs {
   unsigned* sync; // grid-barrier counters of the persistent recurrence kernels
   void* P;        // [B*T, 4H] fp16: keys . W_ih[:, E:]^T, unit-major gate columns (recur2 path)
   float* gh;      // [4, 128, 4H]  K-slice partials of h_s . W_hh^T of the current step (recur2 path)
+  // transposed weights of the backward pass, written by a training forward next to the weight casts (recur2 path)
+  void* outwT;    // [H, Vp]
+  void* attWT;    // [H, A]
+  void* whhT;     // [H, 4H]   unit-major gate columns
+  void* wieT;     // [Ep, 4H]
   size_t bytes;
 };
 
 // Which time-loop implementation a forward call ran, keyed by its workspace: the backward call must read the saved
 // activations in the layout that forward wrote (tile-interleaved vs unit-major gate columns, ctx present or not).
-enum { DEC_LOOP_CHAIN = 0, DEC_LOOP_RECUR1 = 1, DEC_LOOP_RECUR2 = 2 };
+enum { DEC_LOOP_CHAIN = 0, DEC_LOOP_RECUR1 = 1, DEC_LOOP_RECUR2 = 2, DEC_LOOP_MASK = 0xff,
+       DEC_FLAG_WT_READY = 0x100 };   // forward also wrote the transposed weights of the backward pass
 static std::mutex g_loop_mu;
 static std::unordered_map<const void*, int> g_loop_mode;
 static void set_loop_mode(const void* ws, int mode) {
@@ -79,6 +85,7 @@ static int get_loop_mode(const void* ws) {
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t aux[2] = {nullptr, nullptr};             // intermediate dependencies between the two streams
 };
 static int get_side_stream(cudaStream_t caller, SideStream** out) {
   static std::mutex mu;
@@ -93,6 +100,7 @@ static int get_side_stream(cudaStream_t caller, SideStream** out) {
     MVC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     MVC_CUDA(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
     MVC_CUDA(cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming));
+    for (auto& e : s->aux) MVC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     it = pool.emplace(key, s).first;
   }
   *out = it->second;
@@ -112,6 +120,16 @@ struct SideGuard {
   }
   int mark() {                                         // "everything given to the side stream so far"
     MVC_CUDA(cudaEventRecord(side->join, side->stream));
+    return 0;
+  }
+  int side_waits(int i) {                              // side stream waits for what `caller` holds now (forked already)
+    MVC_CUDA(cudaEventRecord(side->aux[i], caller));
+    MVC_CUDA(cudaStreamWaitEvent(side->stream, side->aux[i], 0));
+    return 0;
+  }
+  int caller_waits(int i) {                            // caller waits for what the side stream holds now
+    MVC_CUDA(cudaEventRecord(side->aux[i], side->stream));
+    MVC_CUDA(cudaStreamWaitEvent(caller, side->aux[i], 0));
     return 0;
   }
   int join() {                                         // caller waits for the last mark()
@@ -163,6 +181,10 @@ static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
   w.sync = ar.take<unsigned>(1024);   // recur1: [0,32); recur2 forward flags: [256,512); recur2 backward flags: [512,768)
   w.P = bf ? ar.take<char>(B * T * 4 * H * 2) : nullptr;
   w.gh = bf ? ar.take<float>(4 * 128 * 4 * H) : nullptr;
+  w.outwT = bf ? ar.take<char>(H * pad8((int)V) * 2) : nullptr;
+  w.attWT = bf ? ar.take<char>(H * A * 2) : nullptr;
+  w.whhT = bf ? ar.take<char>(H * 4 * H * 2) : nullptr;
+  w.wieT = bf ? ar.take<char>(Ep * 4 * H * 2) : nullptr;
   w.bytes = ar.off + 256;
   return w;
 }
@@ -182,6 +204,24 @@ __global__ void pack_wcat_kernel(const float* __restrict__ w_x, int64_t wx_ld, c
     if constexpr (sizeof(OutT) == 2) out[i] = __float2bfloat16(v);
     else out[i] = v;
   }
+}
+
+// bf16 variant with 16-byte loads: one block row per output row (no 64-bit division per element), 4 elements per thread
+__global__ void __launch_bounds__(256)
+pack_wcat_vec_kernel(const float* __restrict__ w_x, int64_t wx_ld, const float* __restrict__ w_hh, int F, int H,
+                     __nv_bfloat16* __restrict__ out, int perm) {
+  const int ro = blockIdx.y;
+  const int64_t r = perm == 2 ? gate_unperm(-H, ro) : (perm ? gate_unperm(H, ro) : ro);
+  const int K = F + H;
+  const int k = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (k >= K) return;
+  const float4 v = k < F ? *reinterpret_cast<const float4*>(w_x + r * wx_ld + k)
+                         : *reinterpret_cast<const float4*>(w_hh + r * H + (k - F));
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&lo);
+  o.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(out + (int64_t)ro * K + k) = o;
 }
 
 // out[r, 0:Cp] = bf16(src[r*lds + 0:C]) zero padded
@@ -239,6 +279,13 @@ __global__ void iota_i64_kernel(int64_t* __restrict__ p, int64_t n) {
 int launch_pack_wcat(const float* w_x, int64_t wx_ld, const float* w_hh, int F, int H, void* out, int out_bf16, int perm,
                      cudaStream_t st) {
   const int64_t n = (int64_t)4 * H * (F + H);
+  if (out_bf16 && F % 4 == 0 && H % 4 == 0 && wx_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(w_x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(w_hh) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+    pack_wcat_vec_kernel<<<dim3((unsigned)cdiv(F + H, 1024), (unsigned)(4 * H)), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H,
+                                                                                             (__nv_bfloat16*)out, perm);
+    MVC_LAUNCH_CHECK();
+    return 0;
+  }
   if (out_bf16) pack_wcat_kernel<__nv_bfloat16><<<gridn(n), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H, (__nv_bfloat16*)out, perm);
   else pack_wcat_kernel<float><<<gridn(n), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H, (float*)out, perm);
   MVC_LAUNCH_CHECK();
@@ -315,6 +362,67 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
   return 0;
 }
 
+// The whole prelude of a fully teacher-forced bf16 forward on the projected-keys path (recur2), scheduled over two
+// streams so that the serial chain in front of the persistent kernel is  features -> P GEMM -> U.k GEMM  only:
+//   side:   bias sum, [W_c | W_hh] pack (-> event 0), W_ie cast, <SOS> / caption tokens, embedding gather, gx GEMM,
+//           W / W_out casts, state clears, and (training) the transposed weights the backward pass will need
+//   caller: feature concat / cast, (wait event 0) P = keys . W_c^T, U cast, U.k GEMM, join
+// (the round-2 profile of the single-stream order: 139 us from step start to the persistent kernel, 80 us of it GEMMs)
+static int dec_prepare_r2(const MvcDecoderDims* d, const MvcDecoderParams* p, const float* audio, int Fa,
+                          const float* visual, int Fv, const int64_t* captions, float* out_logp, float* out_hid,
+                          int64_t* tokens_in, DecWs& w, bool train, cudaStream_t st) {
+  const int B = d->B, T = d->T, F = d->F, H = d->H, E = d->E, A = d->A, V = d->V, S = d->L - 1;
+  const int Ep = pad8(E);
+  const int64_t ldx = F + H;
+  MVC_CHECK(Fa + Fv == F, "decoder: Fa (%d) + Fv (%d) != in_feature_size (%d)", Fa, Fv, F);
+  SideGuard sg(st);
+  MVC_TRY(sg.fork());
+  cudaStream_t ss = sg.side->stream;
+  MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, -H, ss));
+  MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, 1, 2, ss));
+  MVC_CUDA(cudaEventRecord(sg.side->aux[0], ss));
+  MVC_TRY(launch_cast_pad_bf16(p->w_ih, 4 * H, E, E + F, Ep, w.wie, -H, ss));
+  // tokens_in[0] = <SOS>, tokens_in[s] = captions[s] (features_captioning.py:99, :121-125); hoisted embedding GEMM
+  MVC_TRY(launch_fill_i64(tokens_in, MVC_SOS, B, ss));
+  if (S > 1)
+    MVC_CUDA(cudaMemcpyAsync(tokens_in + B, captions + B, sizeof(int64_t) * (size_t)(S - 1) * B, cudaMemcpyDeviceToDevice, ss));
+  MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, (int64_t)S * B, w.xemb, Ep, 1, ss));
+  MVC_TRY(gemm_nt(MVC_BF16, S * B, 4 * H, Ep, w.xemb, Ep, w.wie, Ep, 0.f, w.gx, 4 * H, w.bsum, ss));
+  MVC_TRY(mvc_cast_bf16(p->att_W, w.W, (int64_t)A * H, ss));
+  MVC_TRY(mvc_cast_bf16(p->out_w, w.outw, (int64_t)V * H, ss));
+  if (tc_aux_row0(V) > V)
+    MVC_CUDA(cudaMemsetAsync((char*)w.outw + (size_t)V * H * 2, 0, (size_t)(tc_aux_row0(V) - V) * H * 2, ss));
+  MVC_CUDA(cudaMemsetAsync(out_logp, 0, sizeof(float) * (size_t)B * V, ss));      // sentence[0] = 0  (:96)
+  MVC_CUDA(cudaMemsetAsync(out_hid, 0, sizeof(float) * (size_t)B * H, ss));       // hidden_states[0] = 0 (:98)
+  MVC_CUDA(cudaMemsetAsync(w.c, 0, sizeof(float) * (size_t)B * H, ss));           // c_0 = 0 (:66-75)
+  MVC_CUDA(cudaMemsetAsync(w.xh, 0, (size_t)2 * B * ldx, ss));                    // h_0 = 0: clear slot 0
+  if (train) {
+    MVC_TRY(mvc_transpose_to_bf16(cptr(w.wcat, F, 2), 1, 4 * H, H, ldx, w.whhT, 4 * H, ss));
+    MVC_TRY(mvc_transpose_to_bf16(w.W, 1, A, H, H, w.attWT, A, ss));
+    MVC_TRY(mvc_transpose_to_bf16(w.outw, 1, V, H, H, w.outwT, pad8(V), ss));
+    MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, w.wieT, 4 * H, ss));
+  }
+  MVC_TRY(sg.mark());
+  if (mvc_get_input_format() == MVC_INPUT_BF16) MVC_TRY(mvc_concat_bf16(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, st));
+  else MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, 1, st));
+  MVC_CUDA(cudaStreamWaitEvent(st, sg.side->aux[0], 0));
+  {
+    // P = keys . W_ih[:, E:]^T  ([B*T, F] x [F, 4H], 16-bit out, unit-major gate columns): the context half of every
+    // step's gate pre-activation becomes sum_t alpha_t P[b,t,:], accumulated out of tensor memory by the row owner
+    // (stored as fp16, saturating: |P| beyond 65504 means fully saturated gates anyway, and the 11-bit mantissa keeps
+    // the rounding error of the pre-activation 4x below bf16's on unnormalised features)
+    TcEpilogue ep{};
+    ep.mode = TC_MODE_PLAIN;
+    ep.Cb = (__nv_bfloat16*)w.P; ep.ldcb = 4 * H; ep.cb_f16 = 1;
+    MVC_TRY(tc_gemm(B * T, 4 * H, F, w.feats, F, w.wcat, ldx, ep, 0, st));
+  }
+  MVC_TRY(mvc_cast_bf16(p->att_U, w.U, (int64_t)A * F, st));
+  // uk = feats . U^T      (temporal_attention.py:21, hoisted)
+  MVC_TRY(gemm_nt(MVC_BF16, B * T, A, F, w.feats, F, w.U, F, 0.f, w.uk, A, nullptr, st));
+  MVC_TRY(sg.join());
+  return 0;
+}
+
 static StepCfg dec_cfg(const MvcDecoderDims* d, const MvcDecoderParams* p, const DecWs& w, float* pre) {
   const bool bf = d->precision == MVC_BF16;
   StepCfg c{};
@@ -377,7 +485,6 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
                                    const float* visual, int Fv, const int64_t* captions, const uint8_t* tf_flags_host,
                                    float* out_logp, float* out_hid, int64_t* tokens_in, void* workspace,
                                    size_t workspace_bytes, int save_for_backward, void* stream) {
-  (void)save_for_backward;
   MVC_TRY(check_dims(d));
   MVC_CHECK(p && out_logp && out_hid && tokens_in && workspace, "mvc_decoder_forward: null argument");
   DecWs w = dec_layout(d, workspace);
@@ -399,15 +506,19 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
 
   // fully teacher-forced bf16 sequences take the projected-keys persistent kernels (recur2.cuh)
   const bool use_r2 = bf && all_tf && recur2_supported(B, T, F, H, A);
-  MVC_TRY(dec_prepare(d, p, audio, Fa, visual, Fv, w, !all_tf, st, use_r2));
-  MVC_CUDA(cudaMemsetAsync(out_logp, 0, sizeof(float) * (size_t)B * V, st));      // sentence[0] = 0  (:96)
-  MVC_CUDA(cudaMemsetAsync(out_hid, 0, sizeof(float) * (size_t)B * H, st));       // hidden_states[0] = 0 (:98)
-  MVC_CUDA(cudaMemsetAsync(w.c, 0, sizeof(float) * (size_t)B * H, st));           // c_0 = 0 (:66-75)
-  // h_0 = 0 in slot 0's h-part (strided): clear the whole slot 0
-  MVC_CUDA(cudaMemsetAsync(w.xh, 0, es * (size_t)B * ldx, st));
-  MVC_TRY(launch_fill_i64(tokens_in, MVC_SOS, B, st));                              // first input = <SOS> (:99)
+  if (use_r2) {
+    MVC_TRY(dec_prepare_r2(d, p, audio, Fa, visual, Fv, captions, out_logp, out_hid, tokens_in, w, save_for_backward != 0, st));
+  } else {
+    MVC_TRY(dec_prepare(d, p, audio, Fa, visual, Fv, w, !all_tf, st, false));
+    MVC_CUDA(cudaMemsetAsync(out_logp, 0, sizeof(float) * (size_t)B * V, st));      // sentence[0] = 0  (:96)
+    MVC_CUDA(cudaMemsetAsync(out_hid, 0, sizeof(float) * (size_t)B * H, st));       // hidden_states[0] = 0 (:98)
+    MVC_CUDA(cudaMemsetAsync(w.c, 0, sizeof(float) * (size_t)B * H, st));           // c_0 = 0 (:66-75)
+    // h_0 = 0 in slot 0's h-part (strided): clear the whole slot 0
+    MVC_CUDA(cudaMemsetAsync(w.xh, 0, es * (size_t)B * ldx, st));
+    MVC_TRY(launch_fill_i64(tokens_in, MVC_SOS, B, st));                              // first input = <SOS> (:99)
+  }
 
-  if (all_tf) {
+  if (all_tf && !use_r2) {
     // tokens_in[s] = captions[s] for s >= 1 ; hoisted embedding GEMM
     if (S > 1)
       MVC_CUDA(cudaMemcpyAsync(tokens_in + B, captions + B, sizeof(int64_t) * (size_t)(S - 1) * B,
@@ -419,18 +530,9 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
 
   const StepCfg cfg = dec_cfg(d, p, w, nullptr);
   const bool persistent = use_r2 || (cfg.perm && recur_fwd_supported(B, T, F, H, A));
-  set_loop_mode(workspace, use_r2 ? DEC_LOOP_RECUR2 : (persistent && all_tf ? DEC_LOOP_RECUR1 : DEC_LOOP_CHAIN));
+  set_loop_mode(workspace, use_r2 ? (DEC_LOOP_RECUR2 | (save_for_backward ? DEC_FLAG_WT_READY : 0))
+                                  : (persistent && all_tf ? DEC_LOOP_RECUR1 : DEC_LOOP_CHAIN));
   if (use_r2) {
-    // P = keys . W_ih[:, E:]^T  ([B*T, F] x [F, 4H], bf16 out, unit-major gate columns): the context half of every
-    // step's gate pre-activation becomes sum_t alpha_t P[b,t,:], accumulated out of tensor memory by the row owner
-    // (stored as fp16, saturating: |P| beyond 65504 means fully saturated gates anyway, and the 11-bit mantissa keeps
-    // the rounding error of the pre-activation 4x below bf16's on unnormalised features)
-    {
-      TcEpilogue ep{};
-      ep.mode = TC_MODE_PLAIN;
-      ep.Cb = (__nv_bfloat16*)w.P; ep.ldcb = 4 * H; ep.cb_f16 = 1;
-      MVC_TRY(tc_gemm(B * T, 4 * H, F, w.feats, F, w.wcat, ldx, ep, 0, st));
-    }
     Recur2FwdParams rp{};
     rp.B = B; rp.T = T; rp.F = F; rp.K = F + H; rp.S = S;
     rp.P = (const __nv_bfloat16*)w.P; rp.uk = w.uk; rp.attW = (const __nv_bfloat16*)w.W;
@@ -592,40 +694,59 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   // fp32 h_1..h_S (contiguous [S*B,H]) are not saved separately: they are the h-parts of xh slots 1..S.
   const char* hall = cptr(w.xh, (int64_t)B * ldx + F, es);    // rows = slots 1..S, ld = ldx
   const char* hprev = cptr(w.xh, F, es);                      // rows = slots 0..S-1
-  int loop_mode = get_loop_mode(fwd_workspace);
-  MVC_CHECK(loop_mode >= 0, "mvc_decoder_backward: fwd_workspace was not written by mvc_decoder_forward in this process");
+  const int loop_flags = get_loop_mode(fwd_workspace);
+  MVC_CHECK(loop_flags >= 0, "mvc_decoder_backward: fwd_workspace was not written by mvc_decoder_forward in this process");
+  const int loop_mode = loop_flags & DEC_LOOP_MASK;
   const bool use_r2 = loop_mode == DEC_LOOP_RECUR2;
+  // transposed weights: written by the training forward (recur2 path) or produced here
+  const bool wt_ready = bf && (loop_flags & DEC_FLAG_WT_READY);
+  const void* outwT = wt_ready ? w.outwT : q.outwT;
+  const void* attWT = wt_ready ? w.attWT : q.attWT;
+  const void* whhT = wt_ready ? w.whhT : q.whhT;
+  const void* wieT = wt_ready ? w.wieT : q.wieT;
 
   // ---- vocabulary projection backward (all steps at once)
+  // Two streams (round-2 timeline, tools/step_timeline.py): everything that needs forward data only -- state clears, the
+  // rebuilt ctx rows, the K-major operand copies of the post-loop weight-gradient GEMMs -- starts on the side stream at
+  // entry, next to log-softmax backward and dhall; dW_out / db_out follow there once dlogits exists, under the
+  // persistent backward kernel (which leaves 20 SMs idle).
   SideGuard sg(st);
   bool forked = false;
+  const bool early = bf && dlogp;          // the side stream carries the clears and the operand copies
+  if (early) {
+    MVC_TRY(sg.fork());
+    forked = true;
+    cudaStream_t ss = sg.side->stream;
+    MVC_CUDA(cudaMemsetAsync(q.dc, 0, sizeof(float) * (size_t)B * H, ss));
+    MVC_CUDA(cudaMemsetAsync(q.duk, 0, sizeof(float) * (size_t)B * T * A, ss));
+    MVC_CUDA(cudaMemsetAsync(q.dwpart, 0, sizeof(float) * (size_t)B * A, ss));
+    MVC_CUDA(cudaMemsetAsync(g->embedding, 0, sizeof(float) * (size_t)V * E, ss));
+    MVC_CUDA(cudaEventRecord(sg.side->aux[0], ss));       // "clears done": the time loop waits for this one only
+    // (recur2 forward never formed ctx: rebuild the ctx halves of the xh slots from the saved alpha first)
+    if (use_r2) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, ss));
+    MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
+    MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, ss));        // before xhT: see dec_bwd_layout
+    MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, ss));
+    MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, ss));
+    if (!wt_ready) MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, ss));
+  }
   if (dlogp) {
     const float* lp = out_logp + (int64_t)B * V;
     const float* dl = dlogp + (int64_t)B * V;
     if (bf) {
       MVC_CUDA(cudaMemsetAsync(q.dlogits_b, 0, (size_t)SB * Vp * 2, st));
       MVC_TRY(mvc_log_softmax_bwd(lp, dl, SB, V, q.dlogits, q.dlogits_b, st));
-      MVC_TRY(mvc_transpose_to_bf16(p->out_w, 0, V, H, H, q.outwT, Vp, st));
-      // dhall = dlogits . out_w
-      MVC_TRY(mvc_gemm_bf16(SB, H, V, q.dlogits_b, Vp, q.outwT, Vp, 0.f, q.dhall, H, nullptr, nullptr, 0, st));
-      // dW_out = dlogits^T . hall ; db_out = colsum(dlogits) (fp32).  Nothing in the recurrence needs them: fork them
-      // onto the side stream, where they overlap the persistent backward kernel (joined before returning).
-      MVC_TRY(sg.fork());
-      forked = true;
+      // dW_out = dlogits^T . hall ; db_out = colsum(dlogits) (fp32).  Nothing in the recurrence needs them.
+      MVC_TRY(sg.side_waits(1));
       cudaStream_t ss = sg.side->stream;
       MVC_TRY(mvc_transpose_to_bf16(q.dlogits_b, 1, SB, V, Vp, q.dlogitsT, SBp, ss));
       MVC_TRY(mvc_transpose_to_bf16(hall, 1, SB, H, ldx, q.hallT, SBp, ss));
       MVC_TRY(mvc_gemm_bf16(V, H, SB, q.dlogitsT, SBp, q.hallT, SBp, 0.f, g->out_w, H, nullptr, nullptr, 0, ss));
       MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, ss));
-      // operand transposes of the post-loop weight-gradient GEMMs that only need forward data
-      // (recur2 forward never formed ctx: rebuild the ctx halves of the xh slots from the saved alpha first)
-      if (use_r2) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, ss));
-      MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
-      MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, ss));        // before xhT: see dec_bwd_layout
-      MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, ss));
-      MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, ss));
-      MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, ss));
       MVC_TRY(sg.mark());
+      if (!wt_ready) MVC_TRY(mvc_transpose_to_bf16(p->out_w, 0, V, H, H, q.outwT, Vp, st));
+      // dhall = dlogits . out_w
+      MVC_TRY(mvc_gemm_bf16(SB, H, V, q.dlogits_b, Vp, outwT, Vp, 0.f, q.dhall, H, nullptr, nullptr, 0, st));
     } else {
       MVC_TRY(mvc_log_softmax_bwd(lp, dl, SB, V, q.dlogits, nullptr, st));
       MVC_TRY(mvc_gemm_f32(SB, H, V, 1.f, q.dlogits, V, 1, p->out_w, 1, H, 0.f, q.dhall, H, nullptr, st));
@@ -643,17 +764,22 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   }
 
   // ---- time loop
-  MVC_CUDA(cudaMemsetAsync(q.dc, 0, sizeof(float) * (size_t)B * H, st));
-  MVC_CUDA(cudaMemsetAsync(q.duk, 0, sizeof(float) * (size_t)B * T * A, st));
-  MVC_CUDA(cudaMemsetAsync(q.dwpart, 0, sizeof(float) * (size_t)B * A, st));
-  if (bf) {
+  if (early) {
+    MVC_CUDA(cudaStreamWaitEvent(st, sg.side->aux[0], 0));
+  } else {
+    MVC_CUDA(cudaMemsetAsync(q.dc, 0, sizeof(float) * (size_t)B * H, st));
+    MVC_CUDA(cudaMemsetAsync(q.duk, 0, sizeof(float) * (size_t)B * T * A, st));
+    MVC_CUDA(cudaMemsetAsync(q.dwpart, 0, sizeof(float) * (size_t)B * A, st));
+    MVC_CUDA(cudaMemsetAsync(g->embedding, 0, sizeof(float) * (size_t)V * E, st));
+  }
+  if (bf && !wt_ready) {
     if (use_r2) MVC_TRY(mvc_transpose_to_bf16(cptr(w.wcat, F, 2), 1, 4 * H, H, ldx, q.whhT, 4 * H, st));
     else MVC_TRY(mvc_transpose_to_bf16(w.wcat, 1, 4 * H, F + H, ldx, q.wcatT, 4 * H, st));
     MVC_TRY(mvc_transpose_to_bf16(w.W, 1, A, H, H, q.attWT, A, st));
   }
   StepCfg cfg = dec_cfg(d, p, w, nullptr);
   cfg.wcatT = q.wcatT;
-  cfg.attWT = q.attWT;
+  cfg.attWT = attWT;
   const int permH = use_r2 ? -H : (cfg.perm ? H : 0);
   const bool persistent_bwd = use_r2 || (bf && cfg.perm && recur_bwd_supported(B, T, F, H, A));
   if (use_r2) {
@@ -662,17 +788,17 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     rp.B = B; rp.T = T; rp.F = F; rp.K = F + H; rp.S = S;
     rp.P = (const __nv_bfloat16*)w.P; rp.uk = w.uk; rp.att_b = p->att_b; rp.att_w = p->att_w;
     rp.act = w.act; rp.c = w.c; rp.wq = w.wq; rp.alpha = w.alpha; rp.dh_ext = q.dhall;
-    rp.attWT = (const __nv_bfloat16*)q.attWT;
+    rp.attWT = (const __nv_bfloat16*)attWT;
     rp.dG = q.dG; rp.dG_b = (__nv_bfloat16*)q.dG_b; rp.dwq = q.dwq; rp.dwq_b = (__nv_bfloat16*)q.dwq_b;
     rp.duk = q.duk; rp.dwpart = q.dwpart; rp.ghb = q.ghb; rp.sync = w.sync + 512;
-    MVC_TRY(recur2_bwd_launch(rp, q.whhT, st));
+    MVC_TRY(recur2_bwd_launch(rp, whhT, st));
   } else if (persistent_bwd) {
     // the whole BPTT time loop in ONE persistent cluster-cooperative launch (recur_bwd.cu)
     RecurBwdParams rp{};
     rp.B = B; rp.T = T; rp.F = F; rp.H = H; rp.A = A; rp.K = F + H; rp.S = S;
     rp.feats = (const __nv_bfloat16*)w.feats; rp.uk = w.uk; rp.att_b = p->att_b; rp.att_w = p->att_w;
     rp.act = w.act; rp.c = w.c; rp.wq = w.wq; rp.alpha = w.alpha; rp.dh_ext = q.dhall;
-    rp.attWT = (const __nv_bfloat16*)q.attWT;
+    rp.attWT = (const __nv_bfloat16*)attWT;
     rp.dG = q.dG; rp.dG_b = (__nv_bfloat16*)q.dG_b; rp.dxh = q.dxh; rp.dwq = q.dwq; rp.dwq_b = (__nv_bfloat16*)q.dwq_b;
     rp.duk = q.duk; rp.dwpart = q.dwpart; rp.sync = w.sync + 16;
     MVC_TRY(recur_bwd_launch(rp, q.wcatT, st));
@@ -703,13 +829,16 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
 
   // ---- hoisted parameter gradients
   // attention: dW = dwq^T . h_prev ; db = colsum(dwq) ; dw = colsum(dwpart) ; dU = duk^T . feats
-  MVC_TRY(mvc_colsum(q.dwq, SB, A, A, g->att_b, st));
-  MVC_TRY(mvc_colsum(q.dwpart, B, A, A, g->att_w, st));
-  // LSTM biases
-  MVC_TRY(launch_colsum(q.dG, SB, 4 * H, 4 * H, g->b_ih, permH, st));
-  MVC_CUDA(cudaMemcpyAsync(g->b_hh, g->b_ih, sizeof(float) * 4 * (size_t)H, cudaMemcpyDeviceToDevice, st));
-  MVC_CUDA(cudaMemsetAsync(g->embedding, 0, sizeof(float) * (size_t)V * E, st));
+  auto bias_grads = [&]() -> int {
+    MVC_TRY(mvc_colsum(q.dwq, SB, A, A, g->att_b, st));
+    MVC_TRY(mvc_colsum(q.dwpart, B, A, A, g->att_w, st));
+    // LSTM biases
+    MVC_TRY(launch_colsum(q.dG, SB, 4 * H, 4 * H, g->b_ih, permH, st));
+    MVC_CUDA(cudaMemcpyAsync(g->b_hh, g->b_ih, sizeof(float) * 4 * (size_t)H, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  };
   if (!bf) {
+    MVC_TRY(bias_grads());
     const float* xh = (const float*)w.xh;
     MVC_TRY(mvc_gemm_f32(A, H, SB, 1.f, q.dwq, 1, A, (const float*)hprev, 1, ldx, 0.f, g->att_W, H, nullptr, st));
     MVC_TRY(mvc_gemm_f32(A, F, B * T, 1.f, q.duk, 1, A, (const float*)w.feats, 1, F, 0.f, g->att_U, F, nullptr, st));
@@ -733,17 +862,16 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, st));
       MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, st));
       MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
+      if (!wt_ready) MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
     }
     const char* hprevT = cptr(q.xhT, (int64_t)F * SBp, 2);
     // the attention-parameter gradients (small GEMMs) run on the side stream next to the LSTM weight gradients
     MVC_TRY(sg.fork());
     {
       cudaStream_t ss = sg.side->stream;
-      if (pre_t) {
-        // the embedding gradient (dxemb = dG . W_ie, scattered into the table) needs neither dG^T nor the main stream
-        MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, q.wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, ss));
-        MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, ss));
-      }
+      // the embedding gradient (dxemb = dG . W_ie, scattered into the table) needs neither dG^T nor the main stream
+      MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, ss));
+      MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, ss));
       MVC_TRY(mvc_transpose_to_bf16(q.dwq_b, 1, SB, A, A, q.dwqT, SBp, ss));
       MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * T, A, A, q.dukT, BTp, ss));
       MVC_TRY(mvc_gemm_bf16(A, H, SB, q.dwqT, SBp, hprevT, SBp, 0.f, g->att_W, H, nullptr, nullptr, 0, ss));
@@ -765,11 +893,8 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_TRY(mvc_gemm_bf16(4 * H, H, SB, q.dGT, SBp, hprevT, SBp, 0.f, g->w_hh, H, nullptr, nullptr, 0, st));
       MVC_TRY(mvc_gemm_bf16(4 * H, E, SB, q.dGT, SBp, q.xembT, SBp, 0.f, g->w_ih, E + F, nullptr, nullptr, 0, st));
     }
-    if (!pre_t) {
-      MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
-      MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, q.wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, st));
-      MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, st));
-    }
+    // bias gradients (column sums) behind the big GEMM on the caller's stream, next to the side stream's small GEMMs
+    MVC_TRY(bias_grads());
   }
   if (forked) MVC_TRY(sg.join());
   return 0;

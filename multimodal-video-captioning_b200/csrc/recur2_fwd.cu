@@ -547,48 +547,72 @@ int recur2_fwd_launch(const Recur2FwdParams& p, const void* whh_um, int64_t ldw,
 }
 
 // ------------------------------------------------------------------ ctx rows (backward only)
-// ctx[s,b,:] = sum_t alpha[s,b,t] feats[b,t,:] for all s: block = (feature chunk of 512, row b); alpha[.,b,.] staged in
-// shared memory, every thread owns 2 adjacent features and 8 steps at a time.
+// ctx[s,b,:] = sum_t alpha[s,b,t] feats[b,t,:] for all s: block = (chunk of 512 features, row b, chunk of 8 steps); the
+// 8 x T attention weights of the block sit in shared memory (zero padded to a multiple of 4 frames) and are read as
+// float4 (one LDS.128 per 16 FMAs); every thread owns 4 adjacent features (one 8-byte load per frame) and 8 steps.
+// (The first version -- 2 features per thread, scalar broadcast loads of alpha, all steps per block -- was LDS bound:
+// 62 us; this one is FMA bound.)
 constexpr int CR_S = 8;
-__global__ void __launch_bounds__(256)
+constexpr int CR_THREADS = 128;
+__global__ void __launch_bounds__(CR_THREADS)
 r2_ctx_rows_kernel(const __nv_bfloat16* __restrict__ feats, const float* __restrict__ alpha, int B, int T, int F, int S,
                    __nv_bfloat16* __restrict__ xh, int64_t ldx) {
-  extern __shared__ float sAl[];                  // [S][T]
-  const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < S * T; i += blockDim.x) {
-    const int s = i / T, t = i - s * T;
-    sAl[i] = alpha[((size_t)s * B + b) * T + t];
+  extern __shared__ float4 sAl4[];                // [CR_S][Tp / 4]
+  float* sAl = reinterpret_cast<float*>(sAl4);
+  const int b = blockIdx.y, s0 = blockIdx.z * CR_S;
+  const int Tp = (T + 3) & ~3, T4 = Tp >> 2;
+  for (int i = threadIdx.x; i < CR_S * Tp; i += CR_THREADS) {
+    const int si = i / Tp, t = i - si * Tp;
+    sAl[i] = (s0 + si < S && t < T) ? alpha[((size_t)(s0 + si) * B + b) * T + t] : 0.f;
   }
   __syncthreads();
-  const int f = (blockIdx.x * 256 + threadIdx.x) * 2;
+  const int f = (blockIdx.x * CR_THREADS + threadIdx.x) * 4;
   if (f >= F) return;
-  const __nv_bfloat162* kr = reinterpret_cast<const __nv_bfloat162*>(feats + (size_t)b * T * F + f);
-  for (int s0 = 0; s0 < S; s0 += CR_S) {
-    float ax[CR_S], ay[CR_S];
+  const uint2* kr = reinterpret_cast<const uint2*>(feats + (size_t)b * T * F + f);
+  const size_t rs = (size_t)F >> 2;               // frame pitch in uint2 units
+  float acc[CR_S][4];
 #pragma unroll
-    for (int i = 0; i < CR_S; ++i) { ax[i] = 0.f; ay[i] = 0.f; }
-    for (int t = 0; t < T; ++t) {
-      const float2 k2 = __bfloat1622float2(kr[(size_t)t * (F / 2)]);
+  for (int i = 0; i < CR_S; ++i)
 #pragma unroll
-      for (int i = 0; i < CR_S; ++i) {
-        const float a = (s0 + i < S) ? sAl[(s0 + i) * T + t] : 0.f;
-        ax[i] = fmaf(a, k2.x, ax[i]);
-        ay[i] = fmaf(a, k2.y, ay[i]);
-      }
+    for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+  for (int t4 = 0; t4 < T4; ++t4) {
+    float kf[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t4 * 4 + j;
+      const uint2 k = t < T ? kr[(size_t)t * rs] : make_uint2(0u, 0u);
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&k.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&k.y));
+      kf[j][0] = lo.x; kf[j][1] = lo.y; kf[j][2] = hi.x; kf[j][3] = hi.y;
     }
 #pragma unroll
-    for (int i = 0; i < CR_S; ++i)
-      if (s0 + i < S)
-        *reinterpret_cast<__nv_bfloat162*>(xh + ((size_t)(s0 + i) * B + b) * ldx + f) = __floats2bfloat162_rn(ax[i], ay[i]);
+    for (int i = 0; i < CR_S; ++i) {
+      const float4 a = sAl4[i * T4 + t4];
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][e] = fmaf(av[j], kf[j][e], acc[i][e]);
+    }
   }
+#pragma unroll
+  for (int i = 0; i < CR_S; ++i)
+    if (s0 + i < S) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(acc[i][0], acc[i][1]), hi = __floats2bfloat162_rn(acc[i][2], acc[i][3]);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(xh + ((size_t)(s0 + i) * B + b) * ldx + f) = o;
+    }
 }
 
 int r2_ctx_rows(const void* feats_bf16, const float* alpha, int B, int T, int F, int S, void* xh_bf16, int64_t ldx,
                 cudaStream_t st) {
-  MVC_CHECK(F % 2 == 0 && (size_t)S * T * sizeof(float) <= 48 * 1024, "r2_ctx_rows: unsupported dims S=%d T=%d F=%d", S, T, F);
-  dim3 grid((unsigned)cdiv(F, 512), (unsigned)B);
-  r2_ctx_rows_kernel<<<grid, 256, sizeof(float) * S * T, st>>>((const __nv_bfloat16*)feats_bf16, alpha, B, T, F, S,
-                                                              (__nv_bfloat16*)xh_bf16, ldx);
+  MVC_CHECK(F % 4 == 0 && ldx % 4 == 0 && T <= 1024, "r2_ctx_rows: unsupported dims S=%d T=%d F=%d", S, T, F);
+  dim3 grid((unsigned)cdiv(F, 4 * CR_THREADS), (unsigned)B, (unsigned)cdiv(S, CR_S));
+  const int Tp = (T + 3) & ~3;
+  r2_ctx_rows_kernel<<<grid, CR_THREADS, sizeof(float) * CR_S * Tp, st>>>((const __nv_bfloat16*)feats_bf16, alpha, B, T, F, S,
+                                                                         (__nv_bfloat16*)xh_bf16, ldx);
   MVC_LAUNCH_CHECK();
   return 0;
 }

@@ -153,6 +153,9 @@ class DecoderFn(torch.autograd.Function):
                                                cabi.ptr(ws), nbytes, 1, cabi.stream_ptr()), "mvc_decoder_forward")
         ctx.dims = dims
         ctx.save_for_backward(out, tokens, ws, *params)
+        # an output nothing consumed (the hidden states without a reconstructor) arrives as None in backward instead of a
+        # zero tensor that would be filled and added for nothing
+        ctx.set_materialize_grads(False)
         return out, hid.unsqueeze(1)
 
     @staticmethod

@@ -168,10 +168,13 @@ class ShardFeeder:
     A yielded batch lives in one of two device slots; it stays valid until the batch after next is requested (the
     feeder records, on the consumer's stream, when a slot may be overwritten).  ``rank`` / ``world`` give every
     data-parallel rank its contiguous share of each global batch.  ``with_captions=False`` feeds decoding.
+    ``device_slots`` = two (audio, visual, captions) tuples of device tensors to upload into instead of the feeder's own
+    (``GraphedTrainStep.input_slots``: the batch lands in the graph's static inputs, no device-to-device copy).
     """
 
     def __init__(self, reader: ShardReader, batch_size: int, device, shuffle: bool = False, seed: int = 0,
-                 drop_last: bool = True, rank: int = 0, world: int = 1, with_captions: bool = True, epochs: int = 1):
+                 drop_last: bool = True, rank: int = 0, world: int = 1, with_captions: bool = True, epochs: int = 1,
+                 device_slots=None):
         self.r, self.B, self.dev = reader, int(batch_size), torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("ShardFeeder feeds CUDA devices (the decoder has no CPU path)")
@@ -186,6 +189,17 @@ class ShardFeeder:
                        torch.empty(B, T, Fv, dtype=torch.bfloat16, device=self.dev),
                        torch.empty(L, B, dtype=torch.int64, device=self.dev),
                        torch.empty(B, dtype=torch.int32, device=self.dev)) for _ in range(2)]
+        if device_slots is not None:
+            if len(device_slots) < 2:
+                raise ValueError("ShardFeeder(device_slots=...): two slots are needed (double buffering)")
+            for k in range(2):
+                a, v, c = device_slots[k][:3]
+                want = self._devt[k]
+                for got, ref, name in ((a, want[0], "audio"), (v, want[1], "visual"), (c, want[2], "captions")):
+                    if got.shape != ref.shape or got.dtype != ref.dtype or got.device != ref.device or not got.is_contiguous():
+                        raise ValueError(f"ShardFeeder(device_slots=...): {name} slot must be a contiguous "
+                                         f"{tuple(ref.shape)} {ref.dtype} tensor on {ref.device}")
+                self._devt[k] = (a, v, c, want[3])
         self._direct = reader.pinned and shuffle in (False, "batches")
         self._src = reader.host_tensors() if self._direct else None
         self._copy = torch.cuda.Stream(device=self.dev)

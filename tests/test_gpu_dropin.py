@@ -424,3 +424,57 @@ def test_graphed_train_step_equals_eager_steps(dev):
         # same kernels in the same order; only the embedding scatter (atomicAdd order) and the bias-correction powf
         # (device vs host libm) may differ in the last bits
         torch.testing.assert_close(pa, pb, rtol=2e-5, atol=2e-6, msg=k)
+
+
+def test_graphed_train_step_input_slots_in_place(dev, tmp_path):
+    """GraphedTrainStep(slots=2): batches written straight into the graphs' static input tensors -- here by a ShardFeeder
+    with device_slots= -- take the copy-free replay and give the eager loop's parameters."""
+    from models import AVCaptioning
+    from salstm.trainer import FlatClipAdam, GraphedTrainStep
+    from salstm.shards import ShardFeeder, ShardReader, write_shard
+    import losses as L
+    V, B, T, Lc, N = 97, 8, 6, 7, 40
+    lam = dict(reg_lambda=0.0005, audio_recon_lambda=0.0, visual_recon_lambda=0.0)
+    a, v, c = O.synth_batch(N, T, Lc, V, seed=77, min_frames=2, min_cap=3)
+    a, v = a / 255.0, v / 10.0
+    path = str(tmp_path / "s.shard")
+    write_shard(path, list(a), list(v), list(c.t()), T=T, L=Lc)
+
+    def make():
+        torch.manual_seed(6)
+        m = AVCaptioning(Vocab(V), 1.0, "none", device=dev, precision="bf16").to(dev)
+        return m, FlatClipAdam(m.parameters(), lr=1e-3, weight_decay=1e-5, clip_value=5.0)
+
+    loss_fn = L.ModalityWiseReconstructionLossBuilder(rec_type="none", **lam)
+    first = (a[:B].bfloat16().to(dev), v[:B].bfloat16().to(dev), c[:, :B].contiguous().to(dev))
+    ma, oa = make()
+    mb, ob = make()
+    gstep = GraphedTrainStep(ma, loss_fn, oa, first, warmup=2, slots=2)
+    assert len(gstep.input_slots) == 2
+    for _ in range(2):
+        ob.zero_grad()
+        out, ar, vr = mb(*first)
+        loss_fn(out, first[2], first[0], ar, first[1], vr)[0].mean().backward()
+        ob.step()
+    feeder = ShardFeeder(ShardReader(path, pin=True), B, dev, shuffle=False, device_slots=gstep.input_slots)
+    la, lb, n = [], [], 0
+    for fa, fv, fc, _ in feeder:
+        k = n % 2
+        assert fa.data_ptr() == gstep.input_slots[k][0].data_ptr()          # uploaded in place
+        ref = tuple(t.clone() for t in (fa, fv, fc))
+        la.append(float(gstep(fa, fv, fc)[0]))
+        ob.zero_grad()
+        out, ar, vr = mb(*ref)
+        t = loss_fn(out, ref[2], ref[0], ar, ref[1], vr)
+        t[0].mean().backward()
+        ob.step()
+        lb.append(float(t[0]))
+        n += 1
+    assert n == N // B
+    assert la == pytest.approx(lb, rel=1e-6)
+    assert oa.step_count == ob.step_count == 2 + n
+    for (k, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+        torch.testing.assert_close(pa, pb, rtol=2e-5, atol=2e-6, msg=k)
+    with pytest.raises(ValueError):
+        f32 = (a[:B].to(dev), v[:B].to(dev), c[:, :B].contiguous().to(dev))
+        ShardFeeder(ShardReader(path, pin=True), B, dev, device_slots=[f32, f32])          # slots must be bf16 features

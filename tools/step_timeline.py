@@ -1,0 +1,72 @@
+"""Kernel timeline of ONE graphed C2 train step (torch.profiler / CUPTI activity records): start, duration and stream of
+every kernel relative to the first one, the idle gaps of the union, and which kernels run while nothing else does
+(= the critical path).  Numbers under a profiler are not bench values; the shares are what matter.
+
+    python tools/step_timeline.py [train|train_dual|recnet_global|recnet_local] > profiles/step_timeline_r2.txt
+"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "multimodal-video-captioning_b200"), ROOT]
+import torch
+from torch.profiler import profile, ProfilerActivity
+import bench as Bn
+from salstm.trainer import FlatClipAdam, GraphedTrainStep
+import losses as Lm
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "train"
+dev = torch.device("cuda:0")
+w = Bn.WORKLOADS[wl]
+shape = Bn.SHAPES[w["shape"]]
+model = Bn.build_model(wl, dev, "bf16")
+bs = [tuple(t.to(dev) for t in b) for b in Bn.make_batches(shape, 4)]
+loss_fn = Lm.ModalityWiseReconstructionLossBuilder(rec_type=w["rec"], **Bn.LAMBDAS)
+opt = FlatClipAdam(model.parameters(), lr=1e-4)
+step = GraphedTrainStep(model, loss_fn, opt, bs[0])
+for i in range(6):
+    step(*bs[i % 4][:3])
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for i in range(3):
+        step(*bs[i % 4][:3])
+        torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start]
+evs.sort(key=lambda e: e.time_range.start)
+# split into the three steps at the largest two gaps
+gaps = sorted(range(1, len(evs)), key=lambda i: evs[i].time_range.start - evs[i - 1].time_range.end, reverse=True)[:2]
+cut = sorted(gaps)
+steps = [evs[:cut[0]], evs[cut[0]:cut[1]], evs[cut[1]:]]
+ks = steps[-1]
+t0 = ks[0].time_range.start
+print("# %s: %d kernels / memsets in the last profiled step; columns: start us, duration us, stream, exclusive us, name" %
+      (wl, len(ks)))
+# exclusive time: part of a kernel's interval during which no other kernel is running
+pts = sorted(set([e.time_range.start for e in ks] + [e.time_range.end for e in ks]))
+excl = {id(e): 0.0 for e in ks}
+idle = 0.0
+for a, b in zip(pts[:-1], pts[1:]):
+    live = [e for e in ks if e.time_range.start <= a and e.time_range.end >= b]
+    if len(live) == 1:
+        excl[id(live[0])] += b - a
+    elif not live:
+        idle += b - a
+tot = ks[-1].time_range.end - t0
+for e in ks:
+    stream = getattr(e, "device_index", 0)
+    try:
+        stream = e.device_resource_id
+    except Exception:
+        pass
+    print("%9.1f %8.1f  s%-3s %8.1f  %s" % (e.time_range.start - t0, e.time_range.end - e.time_range.start, stream,
+                                            excl[id(e)], e.name[:110]))
+print("# span %.1f us; idle (no kernel running) %.1f us; sum of kernel durations %.1f us" %
+      (tot, idle, sum(e.time_range.end - e.time_range.start for e in ks)))
+agg = {}
+for e in ks:
+    n = e.name.split("(")[0][:70]
+    a = agg.setdefault(n, [0, 0.0, 0.0])
+    a[0] += 1
+    a[1] += e.time_range.end - e.time_range.start
+    a[2] += excl[id(e)]
+print("# by kernel: launches, total us, exclusive us (alone on the GPU)")
+for n, a in sorted(agg.items(), key=lambda kv: -kv[1][2]):
+    print("#  %3d %9.1f %9.1f  %s" % (a[0], a[1], a[2], n))
