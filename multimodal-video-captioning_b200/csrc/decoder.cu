@@ -56,6 +56,7 @@ struct DecWs {
   void* attWT;    // [H, A]
   void* whhT;     // [H, 4H]   unit-major gate columns
   void* wieT;     // [Ep, 4H]
+  void* featsT;   // [F, BTp]  keys, K-major operand of dU = duk^T . feats
   size_t bytes;
 };
 
@@ -185,6 +186,7 @@ static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
   w.attWT = bf ? ar.take<char>(H * A * 2) : nullptr;
   w.whhT = bf ? ar.take<char>(H * 4 * H * 2) : nullptr;
   w.wieT = bf ? ar.take<char>(Ep * 4 * H * 2) : nullptr;
+  w.featsT = bf ? ar.take<char>(F * pad8((int)(B * T)) * 2) : nullptr;
   w.bytes = ar.off + 256;
   return w;
 }
@@ -365,17 +367,18 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
 // The whole prelude of a fully teacher-forced bf16 forward on the projected-keys path (recur2), scheduled over two
 // streams so that the serial chain in front of the persistent kernel is  features -> P GEMM -> U.k GEMM  only:
 //   side:   bias sum, [W_c | W_hh] pack (-> event 0), W_ie cast, <SOS> / caption tokens, embedding gather, gx GEMM,
-//           W / W_out casts, state clears, and (training) the transposed weights the backward pass will need
-//   caller: feature concat / cast, (wait event 0) P = keys . W_c^T, U cast, U.k GEMM, join
+//           W cast, state clears (-> event 1: everything the persistent kernel reads); then, UNDER the persistent kernel
+//           (it leaves 20 SMs idle): W_out cast, output clears and (training) the transposed weights / keys the backward
+//           pass will need -- joined by the caller after the kernel (`dec_prepare_r2_finish`)
+//   caller: feature concat / cast, (wait event 0) P = keys . W_c^T, U cast, U.k GEMM, (wait event 1) kernel
 // (the round-2 profile of the single-stream order: 139 us from step start to the persistent kernel, 80 us of it GEMMs)
 static int dec_prepare_r2(const MvcDecoderDims* d, const MvcDecoderParams* p, const float* audio, int Fa,
                           const float* visual, int Fv, const int64_t* captions, float* out_logp, float* out_hid,
-                          int64_t* tokens_in, DecWs& w, bool train, cudaStream_t st) {
+                          int64_t* tokens_in, DecWs& w, bool train, SideGuard& sg, cudaStream_t st) {
   const int B = d->B, T = d->T, F = d->F, H = d->H, E = d->E, A = d->A, V = d->V, S = d->L - 1;
   const int Ep = pad8(E);
   const int64_t ldx = F + H;
   MVC_CHECK(Fa + Fv == F, "decoder: Fa (%d) + Fv (%d) != in_feature_size (%d)", Fa, Fv, F);
-  SideGuard sg(st);
   MVC_TRY(sg.fork());
   cudaStream_t ss = sg.side->stream;
   MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, -H, ss));
@@ -389,20 +392,10 @@ static int dec_prepare_r2(const MvcDecoderDims* d, const MvcDecoderParams* p, co
   MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, (int64_t)S * B, w.xemb, Ep, 1, ss));
   MVC_TRY(gemm_nt(MVC_BF16, S * B, 4 * H, Ep, w.xemb, Ep, w.wie, Ep, 0.f, w.gx, 4 * H, w.bsum, ss));
   MVC_TRY(mvc_cast_bf16(p->att_W, w.W, (int64_t)A * H, ss));
-  MVC_TRY(mvc_cast_bf16(p->out_w, w.outw, (int64_t)V * H, ss));
-  if (tc_aux_row0(V) > V)
-    MVC_CUDA(cudaMemsetAsync((char*)w.outw + (size_t)V * H * 2, 0, (size_t)(tc_aux_row0(V) - V) * H * 2, ss));
-  MVC_CUDA(cudaMemsetAsync(out_logp, 0, sizeof(float) * (size_t)B * V, ss));      // sentence[0] = 0  (:96)
   MVC_CUDA(cudaMemsetAsync(out_hid, 0, sizeof(float) * (size_t)B * H, ss));       // hidden_states[0] = 0 (:98)
   MVC_CUDA(cudaMemsetAsync(w.c, 0, sizeof(float) * (size_t)B * H, ss));           // c_0 = 0 (:66-75)
   MVC_CUDA(cudaMemsetAsync(w.xh, 0, (size_t)2 * B * ldx, ss));                    // h_0 = 0: clear slot 0
-  if (train) {
-    MVC_TRY(mvc_transpose_to_bf16(cptr(w.wcat, F, 2), 1, 4 * H, H, ldx, w.whhT, 4 * H, ss));
-    MVC_TRY(mvc_transpose_to_bf16(w.W, 1, A, H, H, w.attWT, A, ss));
-    MVC_TRY(mvc_transpose_to_bf16(w.outw, 1, V, H, H, w.outwT, pad8(V), ss));
-    MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, w.wieT, 4 * H, ss));
-  }
-  MVC_TRY(sg.mark());
+  MVC_CUDA(cudaEventRecord(sg.side->aux[1], ss));
   if (mvc_get_input_format() == MVC_INPUT_BF16) MVC_TRY(mvc_concat_bf16(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, st));
   else MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, 1, st));
   MVC_CUDA(cudaStreamWaitEvent(st, sg.side->aux[0], 0));
@@ -419,7 +412,22 @@ static int dec_prepare_r2(const MvcDecoderDims* d, const MvcDecoderParams* p, co
   MVC_TRY(mvc_cast_bf16(p->att_U, w.U, (int64_t)A * F, st));
   // uk = feats . U^T      (temporal_attention.py:21, hoisted)
   MVC_TRY(gemm_nt(MVC_BF16, B * T, A, F, w.feats, F, w.U, F, 0.f, w.uk, A, nullptr, st));
-  MVC_TRY(sg.join());
+  // what only the vocabulary projection / the backward pass need: behind the features (event 0 of the caller's stream),
+  // next to the persistent kernel
+  MVC_TRY(sg.side_waits(0));
+  MVC_TRY(mvc_cast_bf16(p->out_w, w.outw, (int64_t)V * H, ss));
+  if (tc_aux_row0(V) > V)
+    MVC_CUDA(cudaMemsetAsync((char*)w.outw + (size_t)V * H * 2, 0, (size_t)(tc_aux_row0(V) - V) * H * 2, ss));
+  MVC_CUDA(cudaMemsetAsync(out_logp, 0, sizeof(float) * (size_t)B * V, ss));      // sentence[0] = 0  (:96)
+  if (train) {
+    MVC_TRY(mvc_transpose_to_bf16(cptr(w.wcat, F, 2), 1, 4 * H, H, ldx, w.whhT, 4 * H, ss));
+    MVC_TRY(mvc_transpose_to_bf16(w.W, 1, A, H, H, w.attWT, A, ss));
+    MVC_TRY(mvc_transpose_to_bf16(w.outw, 1, V, H, H, w.outwT, pad8(V), ss));
+    MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, w.wieT, 4 * H, ss));
+    MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, w.featsT, pad8(B * T), ss));
+  }
+  MVC_TRY(sg.mark());
+  MVC_CUDA(cudaStreamWaitEvent(st, sg.side->aux[1], 0));
   return 0;
 }
 
@@ -506,8 +514,10 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
 
   // fully teacher-forced bf16 sequences take the projected-keys persistent kernels (recur2.cuh)
   const bool use_r2 = bf && all_tf && recur2_supported(B, T, F, H, A);
+  SideGuard sg_r2(st);
   if (use_r2) {
-    MVC_TRY(dec_prepare_r2(d, p, audio, Fa, visual, Fv, captions, out_logp, out_hid, tokens_in, w, save_for_backward != 0, st));
+    MVC_TRY(dec_prepare_r2(d, p, audio, Fa, visual, Fv, captions, out_logp, out_hid, tokens_in, w, save_for_backward != 0,
+                           sg_r2, st));
   } else {
     MVC_TRY(dec_prepare(d, p, audio, Fa, visual, Fv, w, !all_tf, st, false));
     MVC_CUDA(cudaMemsetAsync(out_logp, 0, sizeof(float) * (size_t)B * V, st));      // sentence[0] = 0  (:96)
@@ -540,6 +550,7 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
     rp.xh = (__nv_bfloat16*)w.xh; rp.c = w.c; rp.act = w.act; rp.alpha = w.alpha; rp.wq_out = w.wq;
     rp.out_hid = out_hid; rp.gh = w.gh; rp.sync = w.sync + 256;
     MVC_TRY(recur2_fwd_launch(rp, cptr(w.wcat, F, 2), ldx, st));
+    MVC_TRY(sg_r2.join());                        // W_out cast, clears, transposed weights: done under the kernel
   } else if (persistent && all_tf) {
     // the whole teacher-forced time loop in ONE persistent cluster-cooperative launch (recur_fwd.cu)
     RecurFwdParams rp{};
@@ -704,6 +715,7 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   const void* attWT = wt_ready ? w.attWT : q.attWT;
   const void* whhT = wt_ready ? w.whhT : q.whhT;
   const void* wieT = wt_ready ? w.wieT : q.wieT;
+  const void* featsT = wt_ready ? w.featsT : q.featsT;
 
   // ---- vocabulary projection backward (all steps at once)
   // Two streams (round-2 timeline, tools/step_timeline.py): everything that needs forward data only -- state clears, the
@@ -724,24 +736,32 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     MVC_CUDA(cudaEventRecord(sg.side->aux[0], ss));       // "clears done": the time loop waits for this one only
     // (recur2 forward never formed ctx: rebuild the ctx halves of the xh slots from the saved alpha first)
     if (use_r2) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, ss));
-    MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
+    // (a teacher-forced forward left the gathered embedding rows in xemb; the token-fed paths did not)
+    if (loop_mode == DEC_LOOP_CHAIN) MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
     MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, ss));        // before xhT: see dec_bwd_layout
     MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, ss));
-    MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, ss));
-    if (!wt_ready) MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, ss));
+    if (!wt_ready) {
+      MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, ss));
+      MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, ss));
+    }
   }
   if (dlogp) {
     const float* lp = out_logp + (int64_t)B * V;
     const float* dl = dlogp + (int64_t)B * V;
     if (bf) {
-      MVC_CUDA(cudaMemsetAsync(q.dlogits_b, 0, (size_t)SB * Vp * 2, st));
-      MVC_TRY(mvc_log_softmax_bwd(lp, dl, SB, V, q.dlogits, q.dlogits_b, st));
-      // dW_out = dlogits^T . hall ; db_out = colsum(dlogits) (fp32).  Nothing in the recurrence needs them.
+      MVC_TRY(mvc_log_softmax_bwd(lp, dl, SB, V, q.dlogits, q.dlogits_b, st));      // (zero-fills the Vp - V pad columns)
+      // dW_out = dlogits^T . hall ; db_out = colsum(dlogits) (fp32).  Nothing in the recurrence needs them: side stream,
+      // under the persistent backward kernel.  Both operands are consumed where they lie as MN-major tcgen05 operands
+      // (dlogits [SB, Vp] and the h halves of the xh slots [SB, F+H]): on the 20 SMs the persistent kernel leaves, the two
+      // transpose passes of the K-major form cost more than the GEMM.
       MVC_TRY(sg.side_waits(1));
       cudaStream_t ss = sg.side->stream;
-      MVC_TRY(mvc_transpose_to_bf16(q.dlogits_b, 1, SB, V, Vp, q.dlogitsT, SBp, ss));
-      MVC_TRY(mvc_transpose_to_bf16(hall, 1, SB, H, ldx, q.hallT, SBp, ss));
-      MVC_TRY(mvc_gemm_bf16(V, H, SB, q.dlogitsT, SBp, q.hallT, SBp, 0.f, g->out_w, H, nullptr, nullptr, 0, ss));
+      {
+        TcEpilogue ep{};
+        ep.mode = TC_MODE_PLAIN;
+        ep.C = g->out_w; ep.ldc = H;
+        MVC_TRY(tc_gemm(V, H, SB, q.dlogits_b, Vp, hall, ldx, ep, TC_FLAG_A_MN | TC_FLAG_B_MN, ss));
+      }
       MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, ss));
       MVC_TRY(sg.mark());
       if (!wt_ready) MVC_TRY(mvc_transpose_to_bf16(p->out_w, 0, V, H, H, q.outwT, Vp, st));
@@ -858,11 +878,13 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       forked = false;
     }
     if (!pre_t) {
-      MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, st));
+      if (loop_mode == DEC_LOOP_CHAIN) MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, st));
       MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, st));
       MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, st));
-      MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
-      if (!wt_ready) MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
+      if (!wt_ready) {
+        MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
+        MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
+      }
     }
     const char* hprevT = cptr(q.xhT, (int64_t)F * SBp, 2);
     // the attention-parameter gradients (small GEMMs) run on the side stream next to the LSTM weight gradients
@@ -875,7 +897,7 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_TRY(mvc_transpose_to_bf16(q.dwq_b, 1, SB, A, A, q.dwqT, SBp, ss));
       MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * T, A, A, q.dukT, BTp, ss));
       MVC_TRY(mvc_gemm_bf16(A, H, SB, q.dwqT, SBp, hprevT, SBp, 0.f, g->att_W, H, nullptr, nullptr, 0, ss));
-      MVC_TRY(mvc_gemm_bf16(A, F, B * T, q.dukT, BTp, q.featsT, BTp, 0.f, g->att_U, F, nullptr, nullptr, 0, ss));
+      MVC_TRY(mvc_gemm_bf16(A, F, B * T, q.dukT, BTp, featsT, BTp, 0.f, g->att_U, F, nullptr, nullptr, 0, ss));
       MVC_TRY(sg.mark());
       forked = true;
     }

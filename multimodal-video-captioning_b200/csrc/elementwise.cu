@@ -312,6 +312,8 @@ log_softmax_bwd_kernel(const float* __restrict__ logp, const float* __restrict__
         if (dl_bf16) dl_bf16[(int64_t)blockIdx.x * ldb + v] = __float2bfloat16(d);
       }
     }
+    // the pad columns [V, ldb) of the 16-bit copy (row pitch of the TMA operand) are zero-filled here, not by a memset
+    if (dl_bf16 && (int)threadIdx.x < (int)(ldb - V)) dl_bf16[(int64_t)blockIdx.x * ldb + V + threadIdx.x] = __float2bfloat16(0.f);
   } else {
     for (int v = threadIdx.x; v < V; v += blockDim.x) s += dlogp[off + v];
     s = block_sum(s, red);
@@ -320,6 +322,7 @@ log_softmax_bwd_kernel(const float* __restrict__ logp, const float* __restrict__
       if (dlogits) dlogits[off + v] = d;
       if (dl_bf16) dl_bf16[(int64_t)blockIdx.x * ldb + v] = __float2bfloat16(d);
     }
+    if (dl_bf16 && (int)threadIdx.x < (int)(ldb - V)) dl_bf16[(int64_t)blockIdx.x * ldb + V + threadIdx.x] = __float2bfloat16(0.f);
   }
 }
 

@@ -21,7 +21,11 @@ model = Bn.build_model(wl, dev, "bf16")
 bs = [tuple(t.to(dev) for t in b) for b in Bn.make_batches(shape, 4)]
 loss_fn = Lm.ModalityWiseReconstructionLossBuilder(rec_type=w["rec"], **Bn.LAMBDAS)
 opt = FlatClipAdam(model.parameters(), lr=1e-4)
-step = GraphedTrainStep(model, loss_fn, opt, bs[0])
+step = GraphedTrainStep(model, loss_fn, opt, bs[0], slots=4)
+for ins, src in zip(step.input_slots, bs):
+    for dst, t_ in zip(ins, src):
+        dst.copy_(t_)
+bs = step.input_slots                     # batches live in the graphs' own input tensors: no staging copy
 for i in range(6):
     step(*bs[i % 4][:3])
 torch.cuda.synchronize()
