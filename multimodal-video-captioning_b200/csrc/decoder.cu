@@ -395,6 +395,7 @@ static int dec_prepare_r2(const MvcDecoderDims* d, const MvcDecoderParams* p, co
   MVC_CUDA(cudaMemsetAsync(out_hid, 0, sizeof(float) * (size_t)B * H, ss));       // hidden_states[0] = 0 (:98)
   MVC_CUDA(cudaMemsetAsync(w.c, 0, sizeof(float) * (size_t)B * H, ss));           // c_0 = 0 (:66-75)
   MVC_CUDA(cudaMemsetAsync(w.xh, 0, (size_t)2 * B * ldx, ss));                    // h_0 = 0: clear slot 0
+  MVC_CUDA(cudaMemsetAsync(w.sync + 256, 0, sizeof(unsigned) * 256, ss));         // progress counters of the kernel
   MVC_CUDA(cudaEventRecord(sg.side->aux[1], ss));
   if (mvc_get_input_format() == MVC_INPUT_BF16) MVC_TRY(mvc_concat_bf16(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, st));
   else MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, 1, st));
@@ -549,7 +550,7 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
     rp.att_b = p->att_b; rp.att_w = p->att_w; rp.gx = w.gx;
     rp.xh = (__nv_bfloat16*)w.xh; rp.c = w.c; rp.act = w.act; rp.alpha = w.alpha; rp.wq_out = w.wq;
     rp.out_hid = out_hid; rp.gh = w.gh; rp.sync = w.sync + 256;
-    MVC_TRY(recur2_fwd_launch(rp, cptr(w.wcat, F, 2), ldx, st));
+    MVC_TRY(recur2_fwd_launch(rp, cptr(w.wcat, F, 2), ldx, st, /*sync_cleared=*/true));
     MVC_TRY(sg_r2.join());                        // W_out cast, clears, transposed weights: done under the kernel
   } else if (persistent && all_tf) {
     // the whole teacher-forced time loop in ONE persistent cluster-cooperative launch (recur_fwd.cu)
@@ -732,8 +733,9 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     MVC_CUDA(cudaMemsetAsync(q.dc, 0, sizeof(float) * (size_t)B * H, ss));
     MVC_CUDA(cudaMemsetAsync(q.duk, 0, sizeof(float) * (size_t)B * T * A, ss));
     MVC_CUDA(cudaMemsetAsync(q.dwpart, 0, sizeof(float) * (size_t)B * A, ss));
-    MVC_CUDA(cudaMemsetAsync(g->embedding, 0, sizeof(float) * (size_t)V * E, ss));
+    if (use_r2) MVC_CUDA(cudaMemsetAsync(w.sync + 512, 0, sizeof(unsigned) * 256, ss));
     MVC_CUDA(cudaEventRecord(sg.side->aux[0], ss));       // "clears done": the time loop waits for this one only
+    MVC_CUDA(cudaMemsetAsync(g->embedding, 0, sizeof(float) * (size_t)V * E, ss));
     // (recur2 forward never formed ctx: rebuild the ctx halves of the xh slots from the saved alpha first)
     if (use_r2) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, ss));
     // (a teacher-forced forward left the gathered embedding rows in xemb; the token-fed paths did not)
@@ -811,7 +813,7 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     rp.attWT = (const __nv_bfloat16*)attWT;
     rp.dG = q.dG; rp.dG_b = (__nv_bfloat16*)q.dG_b; rp.dwq = q.dwq; rp.dwq_b = (__nv_bfloat16*)q.dwq_b;
     rp.duk = q.duk; rp.dwpart = q.dwpart; rp.ghb = q.ghb; rp.sync = w.sync + 512;
-    MVC_TRY(recur2_bwd_launch(rp, whhT, st));
+    MVC_TRY(recur2_bwd_launch(rp, whhT, st, /*sync_cleared=*/early));
   } else if (persistent_bwd) {
     // the whole BPTT time loop in ONE persistent cluster-cooperative launch (recur_bwd.cu)
     RecurBwdParams rp{};
@@ -850,12 +852,9 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   // ---- hoisted parameter gradients
   // attention: dW = dwq^T . h_prev ; db = colsum(dwq) ; dw = colsum(dwpart) ; dU = duk^T . feats
   auto bias_grads = [&]() -> int {
-    MVC_TRY(mvc_colsum(q.dwq, SB, A, A, g->att_b, st));
-    MVC_TRY(mvc_colsum(q.dwpart, B, A, A, g->att_w, st));
-    // LSTM biases
-    MVC_TRY(launch_colsum(q.dG, SB, 4 * H, 4 * H, g->b_ih, permH, st));
-    MVC_CUDA(cudaMemcpyAsync(g->b_hh, g->b_ih, sizeof(float) * 4 * (size_t)H, cudaMemcpyDeviceToDevice, st));
-    return 0;
+    // LSTM biases (db_ih = db_hh = colsum dG), attention biases: one launch
+    return launch_colsum3(q.dG, SB, 4 * H, 4 * H, g->b_ih, g->b_hh, permH, q.dwq, SB, A, A, g->att_b, q.dwpart, B, A, A,
+                          g->att_w, st);
   };
   if (!bf) {
     MVC_TRY(bias_grads());

@@ -393,6 +393,53 @@ __global__ void colsum_stage2_kernel(const float* __restrict__ partial, int slic
   out[permH ? gate_unperm(permH, n) : n] = s;
 }
 
+// Up to three column sums in ONE launch (the bias gradients after the time loop: dG -> b_ih = b_hh, dwq -> att_b,
+// dwpart -> att_w): block = 32 columns x 32 row lanes, every thread sums rows y, y + 32, ... with 8 loads in flight, the
+// lanes are added in a fixed order through shared memory (deterministic).  Three two-stage launches + a copy cost 36 us of
+// serial small kernels behind the weight-gradient GEMM; this is one ~8 us launch.
+struct ColsumJob {
+  const float* x;
+  int64_t rows, ld;
+  int N, permH, blocks;
+  float* out;
+  float* out2;               // optional second copy of the result
+};
+struct ColsumJobs {
+  ColsumJob j[3];
+  int n;
+};
+__global__ void __launch_bounds__(1024)
+colsum_multi_kernel(const ColsumJobs jobs) {
+  __shared__ float red[32][33];
+  int blk = blockIdx.x, k = 0;
+  while (k + 1 < jobs.n && blk >= jobs.j[k].blocks) { blk -= jobs.j[k].blocks; ++k; }
+  const ColsumJob& jb = jobs.j[k];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blk * 32 + tx;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  if (col < jb.N) {
+    const float* p = jb.x + col;
+    int64_t r = ty;
+    for (; r + 7 * 32 < jb.rows; r += 8 * 32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += __ldcs(p + (r + i * 32) * jb.ld);
+    }
+    for (; r < jb.rows; r += 32) s[0] += __ldcs(p + r * jb.ld);
+  }
+  red[ty][tx] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  __syncthreads();
+  if (ty == 0 && col < jb.N) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 32; ++g) t += red[g][tx];
+    const int o = jb.permH ? gate_unperm(jb.permH, col) : col;
+    jb.out[o] = t;
+    if (jb.out2) jb.out2[o] = t;
+  }
+}
+
 __global__ void caption_mask_kernel(const int64_t* __restrict__ cap, int64_t n, uint8_t* __restrict__ mask) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) mask[i] = (cap[i] != MVC_PAD && cap[i] != MVC_EOS) ? 1 : 0;
@@ -627,6 +674,21 @@ static int colsum_scratch(cudaStream_t st, float** out, size_t* cap) {
   MVC_CUDA(cudaMalloc(&pbuf, kBytes));
   pool.emplace_back(key, pbuf);
   *out = pbuf; *cap = kBytes;
+  return 0;
+}
+
+int launch_colsum3(const float* x0, int64_t rows0, int N0, int64_t ld0, float* out0, float* out0b, int permH0,
+                   const float* x1, int64_t rows1, int N1, int64_t ld1, float* out1, const float* x2, int64_t rows2, int N2,
+                   int64_t ld2, float* out2, cudaStream_t st) {
+  ColsumJobs jobs{};
+  jobs.n = 3;
+  jobs.j[0] = ColsumJob{x0, rows0, ld0, N0, permH0, (int)cdiv(N0, 32), out0, out0b};
+  jobs.j[1] = ColsumJob{x1, rows1, ld1, N1, 0, (int)cdiv(N1, 32), out1, nullptr};
+  jobs.j[2] = ColsumJob{x2, rows2, ld2, N2, 0, (int)cdiv(N2, 32), out2, nullptr};
+  const int blocks = jobs.j[0].blocks + jobs.j[1].blocks + jobs.j[2].blocks;
+  if (blocks == 0) return 0;
+  colsum_multi_kernel<<<(unsigned)blocks, 1024, 0, st>>>(jobs);
+  MVC_LAUNCH_CHECK();
   return 0;
 }
 

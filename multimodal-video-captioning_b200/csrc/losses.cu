@@ -10,10 +10,11 @@
 
 namespace mvc {
 
-// result[0] = mean NLL over non-PAD targets, result[2] = count; zeroes result[1].
+// result[0] = mean NLL over non-PAD targets, result[2] = count; zeroes result[1] and the entropy accumulator.
 __global__ void nll_kernel(const float* __restrict__ logp, const int64_t* __restrict__ cap, int L, int B, int V,
-                           float* __restrict__ result) {
+                           float* __restrict__ result, double* __restrict__ ent_acc) {
   __shared__ float red[32];
+  if (threadIdx.x == 0) *ent_acc = 0.0;
   const int64_t n = (int64_t)(L - 1) * B;
   float s = 0.f, c = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -68,6 +69,7 @@ __global__ void entropy_kernel(const float* __restrict__ logp, const int64_t* __
         float g = es * p * (m * (lp + 1.f) - q);
         if (tok != MVC_PAD && tok == v) g -= ce_scale / cnt;
         dlogp[((int64_t)s * B + b) * V + v] = g;
+        if (s == 1) dlogp[(int64_t)b * V + v] = 0.f;                     // row 0 gets no gradient
       }
     }
   }
@@ -75,17 +77,20 @@ __global__ void entropy_kernel(const float* __restrict__ logp, const int64_t* __
   if (threadIdx.x == 0) atomicAdd(ent_acc, (double)e_sum);
 }
 
-// Same quantities for B <= 8 * ENT_RPT, ONE pass over the log-probs: block = 32 columns x 8 row groups, thread (x, y)
-// keeps rows y, y + 8, ... of its column in registers, the column-wise max / sum / weighted sums are combined across
-// the 8 row groups through shared memory.  (The 4-pass kernel above ran 16 warps per SM with 512 dependent-latency
+// Same quantities for B <= ENT_RG * ENT_RPT, ONE pass over the log-probs: block = 32 columns x ENT_RG row groups, thread
+// (x, y) keeps rows y, y + ENT_RG, ... of its column in registers, the column-wise max / sum / weighted sums are combined
+// across the row groups through shared memory.  (The 4-pass kernel above ran 16 warps per SM with 512 dependent-latency
 // loads per thread: 63 us for 2 x 37.7 MB; this one moves the same bytes in one read + one write.)
-constexpr int ENT_RPT = 16;
-__global__ void __launch_bounds__(256)
+// (16 row groups x 8 rows per thread: 512 threads per block at ~64 registers keep 32 warps per SM in flight; the first
+// shape -- 8 groups x 16 rows, 110 registers -- ran at 23 % occupancy and 36 us)
+constexpr int ENT_RPT = 8;
+constexpr int ENT_RG = 16;
+__global__ void __launch_bounds__(32 * ENT_RG)
 entropy_tile_kernel(const float* __restrict__ logp, const int64_t* __restrict__ cap, int L, int B, int V,
                     float* __restrict__ result, double* __restrict__ ent_acc, float* __restrict__ dlogp, float ce_scale,
                     float ent_scale) {
-  __shared__ float red[8][33];
-  __shared__ float red2[8][33];
+  __shared__ float red[ENT_RG][33];
+  __shared__ float red2[ENT_RG][33];
   __shared__ float bsum[32];
   const int s = blockIdx.y + 1;
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -98,7 +103,7 @@ entropy_tile_kernel(const float* __restrict__ logp, const int64_t* __restrict__ 
   float mx = -INFINITY;
 #pragma unroll
   for (int i = 0; i < ENT_RPT; ++i) {
-    const int b = ty + 8 * i;
+    const int b = ty + ENT_RG * i;
     const bool in = live && b < B;
     x[i] = in ? col[(int64_t)b * V] : -INFINITY;
     tok[i] = b < B ? (int)caps[b] : (int)MVC_PAD;
@@ -107,25 +112,25 @@ entropy_tile_kernel(const float* __restrict__ logp, const int64_t* __restrict__ 
   red[ty][tx] = mx;
   __syncthreads();
 #pragma unroll
-  for (int g = 0; g < 8; ++g) mx = fmaxf(mx, red[g][tx]);
+  for (int g = 0; g < ENT_RG; ++g) mx = fmaxf(mx, red[g][tx]);
   // one exponential per element: e = exp(x - max); p = e / z; log p = x - (max + log z)
   float z = 0.f;
 #pragma unroll
   for (int i = 0; i < ENT_RPT; ++i) {
-    pr[i] = (ty + 8 * i < B && live) ? expf(x[i] - mx) : 0.f;
+    pr[i] = (ty + ENT_RG * i < B && live) ? expf(x[i] - mx) : 0.f;
     z += pr[i];
   }
   red2[ty][tx] = z;
   __syncthreads();
   z = 0.f;
 #pragma unroll
-  for (int g = 0; g < 8; ++g) z += red2[g][tx];
+  for (int g = 0; g < ENT_RG; ++g) z += red2[g][tx];
   const float lse = live ? mx + logf(z) : 0.f;
   const float rz = live ? 1.f / z : 0.f;
   float e_sum = 0.f, q = 0.f;                     // q = sum_b m_b p_b (log p_b + 1)
 #pragma unroll
   for (int i = 0; i < ENT_RPT; ++i) {
-    const bool in = live && (ty + 8 * i < B);
+    const bool in = live && (ty + ENT_RG * i < B);
     const float lp = in ? x[i] - lse : 0.f;
     const float p = pr[i] * rz;
     x[i] = lp;
@@ -140,19 +145,20 @@ entropy_tile_kernel(const float* __restrict__ logp, const int64_t* __restrict__ 
   __syncthreads();
   q = 0.f;
 #pragma unroll
-  for (int g = 0; g < 8; ++g) q += red[g][tx];
+  for (int g = 0; g < ENT_RG; ++g) q += red[g][tx];
   if (dlogp && live) {
     const float cnt = result[2];
     const float es = -ent_scale / (float)B;
     const float ce = ce_scale / cnt;
 #pragma unroll
     for (int i = 0; i < ENT_RPT; ++i) {
-      const int b = ty + 8 * i;
+      const int b = ty + ENT_RG * i;
       if (b < B) {
         const float m = tok[i] != MVC_PAD ? 1.f : 0.f;
         float g = es * pr[i] * (m * (x[i] + 1.f) - q);
         if (tok[i] != MVC_PAD && tok[i] == v) g -= ce;
         dlogp[((int64_t)s * B + b) * V + v] = g;
+        if (s == 1) dlogp[(int64_t)b * V + v] = 0.f;                     // row 0 gets no gradient
       }
     }
   }
@@ -163,7 +169,7 @@ entropy_tile_kernel(const float* __restrict__ logp, const int64_t* __restrict__ 
   __syncthreads();
   if (tx == 0 && ty == 0) {
     float t = 0.f;
-    for (int g = 0; g < 8; ++g) t += bsum[g];
+    for (int g = 0; g < ENT_RG; ++g) t += bsum[g];
     atomicAdd(ent_acc, (double)t);
   }
 }
@@ -260,15 +266,15 @@ extern "C" int mvc_caption_loss(const float* logp, const int64_t* captions, int 
   MVC_CHECK(L >= 2 && B >= 1 && V >= 1, "mvc_caption_loss: bad dims L=%d B=%d V=%d", L, B, V);
   cudaStream_t st = (cudaStream_t)stream;
   double* acc = static_cast<double*>(workspace);
-  MVC_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
-  if (dlogp) MVC_CUDA(cudaMemsetAsync(dlogp, 0, sizeof(float) * (size_t)B * V, st));   // row 0 gets no gradient
-  nll_kernel<<<1, 1024, 0, st>>>(logp, captions, L, B, V, result);
+  // (no memset nodes on this chain: the NLL kernel clears the accumulator, the entropy kernels write the zero
+  // gradient of row 0 -- sentence[0] is a constant -- next to row 1)
+  nll_kernel<<<1, 1024, 0, st>>>(logp, captions, L, B, V, result, acc);
   MVC_LAUNCH_CHECK();
   dim3 grid((unsigned)cdiv(V, 128), (unsigned)(L - 1));
   ProfScope prof(PK_LOSS, L, B, V, st);
-  if (B <= 8 * ENT_RPT) {
+  if (B <= ENT_RG * ENT_RPT) {
     const dim3 tgrid((unsigned)cdiv(V, 32), (unsigned)(L - 1));
-    entropy_tile_kernel<<<tgrid, dim3(32, 8), 0, st>>>(logp, captions, L, B, V, result, acc, dlogp, ce_scale, ent_scale);
+    entropy_tile_kernel<<<tgrid, dim3(32, ENT_RG), 0, st>>>(logp, captions, L, B, V, result, acc, dlogp, ce_scale, ent_scale);
   } else {
     entropy_kernel<<<grid, 128, 0, st>>>(logp, captions, L, B, V, result, acc, dlogp, ce_scale, ent_scale);
   }

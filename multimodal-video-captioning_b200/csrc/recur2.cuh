@@ -87,8 +87,9 @@ struct Recur2BwdParams {
 };
 
 bool recur2_supported(int B, int T, int F, int H, int A);
-int recur2_fwd_launch(const Recur2FwdParams& p, const void* whh_um, int64_t ldw, cudaStream_t st);
-int recur2_bwd_launch(const Recur2BwdParams& p, const void* whhT_um, cudaStream_t st);
+// sync_cleared: the caller has zeroed the 256 progress-counter words already (off the critical chain)
+int recur2_fwd_launch(const Recur2FwdParams& p, const void* whh_um, int64_t ldw, cudaStream_t st, bool sync_cleared = false);
+int recur2_bwd_launch(const Recur2BwdParams& p, const void* whhT_um, cudaStream_t st, bool sync_cleared = false);
 // xh[(s*B + b), 0:F] = sum_t alpha[s,b,t] feats[b,t,:]  for s in [0,S): the context vectors the forward never formed
 int r2_ctx_rows(const void* feats_bf16, const float* alpha, int B, int T, int F, int S, void* xh_bf16, int64_t ldx,
                 cudaStream_t st);

@@ -518,13 +518,13 @@ const void* recur2_bwd_kernel_ptr() { return (const void*)recur2_bwd_kernel; }
 static long long* g_recur2_bwd_prof = nullptr;
 void r2_set_bwd_prof(long long* p) { g_recur2_bwd_prof = p; }
 
-int recur2_bwd_launch(const Recur2BwdParams& p, const void* whhT_um, cudaStream_t st) {
+int recur2_bwd_launch(const Recur2BwdParams& p, const void* whhT_um, cudaStream_t st, bool sync_cleared) {
   MVC_TRY(r2_apply_spin_limit());
   MVC_CHECK(recur2_supported(p.B, p.T, p.F, R2_H, R2_A), "persistent backward recurrence: unsupported dims");
   CUtensorMap mg, mw;
   MVC_TRY(r2_make_map(p.dG_b, (int64_t)p.S * p.B, 4 * (int64_t)R2_H, 4 * (int64_t)R2_H, 128, &mg));
   MVC_TRY(r2_make_map(whhT_um, R2_H, 4 * (int64_t)R2_H, 4 * (int64_t)R2_H, B2_BN, &mw));
-  MVC_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned) * 256, st));
+  if (!sync_cleared) MVC_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned) * 256, st));
   const size_t smem = recur2_bwd_smem();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(R2_H / 16) * R2_CS);

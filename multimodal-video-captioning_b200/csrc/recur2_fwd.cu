@@ -518,14 +518,14 @@ bool recur2_supported(int B, int T, int F, int H, int A) {
 static long long* g_recur2_prof = nullptr;
 void r2_set_fwd_prof(long long* p) { g_recur2_prof = p; }
 
-int recur2_fwd_launch(const Recur2FwdParams& p, const void* whh_um, int64_t ldw, cudaStream_t st) {
+int recur2_fwd_launch(const Recur2FwdParams& p, const void* whh_um, int64_t ldw, cudaStream_t st, bool sync_cleared) {
   MVC_TRY(r2_apply_spin_limit());
   MVC_CHECK(recur2_supported(p.B, p.T, p.F, R2_H, R2_A), "persistent recurrence: unsupported dims");
   CUtensorMap mh, mw;
   // A operand: the h halves of the xh slots, [(S+1)*B rows, H cols], row pitch K
   MVC_TRY(r2_make_map(p.xh + p.F, (int64_t)(p.S + 1) * p.B, R2_H, p.K, 128, &mh));
   MVC_TRY(r2_make_map(whh_um, (int64_t)4 * R2_H, R2_H, ldw, F2_BN, &mw));
-  MVC_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned) * 256, st));
+  if (!sync_cleared) MVC_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned) * 256, st));
   const size_t smem = recur2_fwd_smem();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(R2_H / 16) * R2_CS);

@@ -45,6 +45,10 @@ int launch_cell_bwd(int B, int H, const float* act, const float* c_prev, const f
                     int64_t dha_ld, const float* dh_b, int64_t dhb_ld, float* dc, float* dgates, void* dg_bf16, int perm,
                     cudaStream_t st);
 int launch_colsum(const float* x, int64_t rows, int N, int64_t ld, float* out, int permH, cudaStream_t st);
+// three column sums in one launch; job 0 may un-permute gate columns (permH) and write a second copy (out0b)
+int launch_colsum3(const float* x0, int64_t rows0, int N0, int64_t ld0, float* out0, float* out0b, int permH0,
+                   const float* x1, int64_t rows1, int N1, int64_t ld1, float* out1, const float* x2, int64_t rows2, int N2,
+                   int64_t ld2, float* out2, cudaStream_t st);
 bool pdl_enabled();
 
 struct AttnFwdArgs {

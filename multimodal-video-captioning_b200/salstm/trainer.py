@@ -306,7 +306,8 @@ class GraphedTrainStep:
             optimizer.zero_grad()
             out, ar, vr = model(*ins)
             terms = loss_fn(out, ins[2], ins[0], ar, ins[1], vr)
-            terms[0].mean().backward()
+            loss = terms[0]
+            (loss if loss.numel() == 1 else loss.mean()).backward()       # mean() of one element: two kernels for nothing
             if multi:
                 optimizer.all_reduce_grads()
             optimizer.step()
@@ -314,7 +315,9 @@ class GraphedTrainStep:
 
         # warm-up on the capture stream: lazy initialisations (side stream, scratch buffers, occupancy queries, the flat
         # parameter / gradient buffers and the gradient arena) must all have happened before the capture starts
-        stream = torch.cuda.Stream(device=dev)
+        # the capture stream outranks the library's side streams (priority 0): when both have blocks waiting -- operand
+        # preparation next to the launch of a persistent kernel -- the critical chain gets the SMs first
+        stream = torch.cuda.Stream(device=dev, priority=-1)
         stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream):
             for _ in range(max(2, warmup)):

@@ -36,8 +36,11 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start]
 evs.sort(key=lambda e: e.time_range.start)
 # split into the three steps at the largest two gaps
-gaps = sorted(range(1, len(evs)), key=lambda i: evs[i].time_range.start - evs[i - 1].time_range.end, reverse=True)[:2]
-cut = sorted(gaps)
+run_end, idle_before = evs[0].time_range.end, {}
+for i in range(1, len(evs)):
+    idle_before[i] = evs[i].time_range.start - run_end          # GPU idle before kernel i (all streams)
+    run_end = max(run_end, evs[i].time_range.end)
+cut = sorted(sorted(idle_before, key=idle_before.get, reverse=True)[:2])
 steps = [evs[:cut[0]], evs[cut[0]:cut[1]], evs[cut[1]:]]
 ks = steps[-1]
 t0 = ks[0].time_range.start
