@@ -57,6 +57,7 @@ struct DecWs {
   void* whhT;     // [H, 4H]   unit-major gate columns
   void* wieT;     // [Ep, 4H]
   void* featsT;   // [F, BTp]  keys, K-major operand of dU = duk^T . feats
+  void* xallT;    // [E + F + H (+8), SBp]  [emb ; ctx ; h_prev]^T, K-major operand of the merged LSTM weight-gradient GEMM
   size_t bytes;
 };
 
@@ -187,6 +188,7 @@ static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
   w.whhT = bf ? ar.take<char>(H * 4 * H * 2) : nullptr;
   w.wieT = bf ? ar.take<char>(Ep * 4 * H * 2) : nullptr;
   w.featsT = bf ? ar.take<char>(F * pad8((int)(B * T)) * 2) : nullptr;
+  w.xallT = bf ? ar.take<char>((E + F + H + 8) * pad8((int)(S * B)) * 2) : nullptr;
   w.bytes = ar.off + 256;
   return w;
 }
@@ -390,12 +392,13 @@ static int dec_prepare_r2(const MvcDecoderDims* d, const MvcDecoderParams* p, co
   if (S > 1)
     MVC_CUDA(cudaMemcpyAsync(tokens_in + B, captions + B, sizeof(int64_t) * (size_t)(S - 1) * B, cudaMemcpyDeviceToDevice, ss));
   MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, (int64_t)S * B, w.xemb, Ep, 1, ss));
-  MVC_TRY(gemm_nt(MVC_BF16, S * B, 4 * H, Ep, w.xemb, Ep, w.wie, Ep, 0.f, w.gx, 4 * H, w.bsum, ss));
   MVC_TRY(mvc_cast_bf16(p->att_W, w.W, (int64_t)A * H, ss));
   MVC_CUDA(cudaMemsetAsync(out_hid, 0, sizeof(float) * (size_t)B * H, ss));       // hidden_states[0] = 0 (:98)
   MVC_CUDA(cudaMemsetAsync(w.c, 0, sizeof(float) * (size_t)B * H, ss));           // c_0 = 0 (:66-75)
   MVC_CUDA(cudaMemsetAsync(w.xh, 0, (size_t)2 * B * ldx, ss));                    // h_0 = 0: clear slot 0
   MVC_CUDA(cudaMemsetAsync(w.sync + 256, 0, sizeof(unsigned) * 256, ss));         // progress counters of the kernel
+  // (last on this leg: the GEMM queues behind the caller's P GEMM for SMs)
+  MVC_TRY(gemm_nt(MVC_BF16, S * B, 4 * H, Ep, w.xemb, Ep, w.wie, Ep, 0.f, w.gx, 4 * H, w.bsum, ss));
   MVC_CUDA(cudaEventRecord(sg.side->aux[1], ss));
   if (mvc_get_input_format() == MVC_INPUT_BF16) MVC_TRY(mvc_concat_bf16(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, st));
   else MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, 1, st));
@@ -552,6 +555,20 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
     rp.out_hid = out_hid; rp.gh = w.gh; rp.sync = w.sync + 256;
     MVC_TRY(recur2_fwd_launch(rp, cptr(w.wcat, F, 2), ldx, st, /*sync_cleared=*/true));
     MVC_TRY(sg_r2.join());                        // W_out cast, clears, transposed weights: done under the kernel
+    if (save_for_backward) {
+      // Training: what the backward pass needs from the saved activations alone -- the ctx halves of the xh slots (this
+      // path never formed them: ctx_s = sum_t alpha_s,t keys_t) and [emb ; ctx ; h_prev]^T, the K-major operand of the
+      // merged LSTM weight-gradient GEMM -- is produced HERE, on the side stream, under the vocabulary projection (FMA /
+      // copy work next to a tensor-pipe kernel; 25 us hidden in a 58 us window).  Under the persistent backward kernel
+      // the same work had 20 SMs and delayed the kernel's own launch.
+      const int SB = S * B, SBp = pad8(SB);
+      MVC_TRY(sg_r2.fork());
+      cudaStream_t ss = sg_r2.side->stream;
+      MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, ss));
+      MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, w.xallT, SBp, ss));       // before the xh block: its Ep - E pad rows
+      MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, (char*)w.xallT + (size_t)E * SBp * 2, SBp, ss));
+      MVC_TRY(sg_r2.mark());
+    }
   } else if (persistent && all_tf) {
     // the whole teacher-forced time loop in ONE persistent cluster-cooperative launch (recur_fwd.cu)
     RecurFwdParams rp{};
@@ -605,6 +622,7 @@ extern "C" int mvc_decoder_forward(const MvcDecoderDims* d, const MvcDecoderPara
       MVC_TRY(mvc_log_softmax_rows(lp, (int64_t)S * B, V, nullptr, st));
     }
   }
+  MVC_TRY(sg_r2.join());
   return 0;
 }
 
@@ -717,6 +735,8 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   const void* whhT = wt_ready ? w.whhT : q.whhT;
   const void* wieT = wt_ready ? w.wieT : q.wieT;
   const void* featsT = wt_ready ? w.featsT : q.featsT;
+  const void* xallT = wt_ready ? w.xallT : q.xembT;           // [emb ; ctx ; h_prev]^T
+  const void* xhT = cptr(xallT, (int64_t)E * SBp, 2);
 
   // ---- vocabulary projection backward (all steps at once)
   // Two streams (round-2 timeline, tools/step_timeline.py): everything that needs forward data only -- state clears, the
@@ -736,13 +756,13 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     if (use_r2) MVC_CUDA(cudaMemsetAsync(w.sync + 512, 0, sizeof(unsigned) * 256, ss));
     MVC_CUDA(cudaEventRecord(sg.side->aux[0], ss));       // "clears done": the time loop waits for this one only
     MVC_CUDA(cudaMemsetAsync(g->embedding, 0, sizeof(float) * (size_t)V * E, ss));
-    // (recur2 forward never formed ctx: rebuild the ctx halves of the xh slots from the saved alpha first)
-    if (use_r2) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, ss));
-    // (a teacher-forced forward left the gathered embedding rows in xemb; the token-fed paths did not)
-    if (loop_mode == DEC_LOOP_CHAIN) MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
-    MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, ss));        // before xhT: see dec_bwd_layout
-    MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, ss));
     if (!wt_ready) {
+      // (a forward without save_for_backward, or one of the launch-chain / recur1 paths: operand copies made here)
+      if (use_r2) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, ss));
+      // (a teacher-forced forward left the gathered embedding rows in xemb; the token-fed paths did not)
+      if (loop_mode == DEC_LOOP_CHAIN) MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, ss));
+      MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, ss));        // before xhT: see dec_bwd_layout
+      MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, ss));
       MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, ss));
       MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, ss));
     }
@@ -756,19 +776,21 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       // under the persistent backward kernel.  Both operands are consumed where they lie as MN-major tcgen05 operands
       // (dlogits [SB, Vp] and the h halves of the xh slots [SB, F+H]): on the 20 SMs the persistent kernel leaves, the two
       // transpose passes of the K-major form cost more than the GEMM.
+      if (!wt_ready) MVC_TRY(mvc_transpose_to_bf16(p->out_w, 0, V, H, H, q.outwT, Vp, st));
+      // dhall = dlogits . out_w
+      MVC_TRY(mvc_gemm_bf16(SB, H, V, q.dlogits_b, Vp, outwT, Vp, 0.f, q.dhall, H, nullptr, nullptr, 0, st));
+      // (the side leg starts BEHIND dhall: its persistent GEMM must not hold SMs when the persistent backward kernel --
+      // a whole-SM cluster launch, next on the caller's stream -- wants 128 of them; the column sum goes first)
       MVC_TRY(sg.side_waits(1));
       cudaStream_t ss = sg.side->stream;
+      MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, ss));
       {
         TcEpilogue ep{};
         ep.mode = TC_MODE_PLAIN;
         ep.C = g->out_w; ep.ldc = H;
         MVC_TRY(tc_gemm(V, H, SB, q.dlogits_b, Vp, hall, ldx, ep, TC_FLAG_A_MN | TC_FLAG_B_MN, ss));
       }
-      MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, ss));
       MVC_TRY(sg.mark());
-      if (!wt_ready) MVC_TRY(mvc_transpose_to_bf16(p->out_w, 0, V, H, H, q.outwT, Vp, st));
-      // dhall = dlogits . out_w
-      MVC_TRY(mvc_gemm_bf16(SB, H, V, q.dlogits_b, Vp, outwT, Vp, 0.f, q.dhall, H, nullptr, nullptr, 0, st));
     } else {
       MVC_TRY(mvc_log_softmax_bwd(lp, dl, SB, V, q.dlogits, nullptr, st));
       MVC_TRY(mvc_gemm_f32(SB, H, V, 1.f, q.dlogits, V, 1, p->out_w, 1, H, 0.f, q.dhall, H, nullptr, st));
@@ -805,7 +827,7 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
   const int permH = use_r2 ? -H : (cfg.perm ? H : 0);
   const bool persistent_bwd = use_r2 || (bf && cfg.perm && recur_bwd_supported(B, T, F, H, A));
   if (use_r2) {
-    if (!dlogp) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, st));   // (otherwise done on the side stream)
+    if (!dlogp && !wt_ready) MVC_TRY(r2_ctx_rows(w.feats, w.alpha, B, T, F, S, w.xh, ldx, st));   // (else: forward / side stream)
     Recur2BwdParams rp{};
     rp.B = B; rp.T = T; rp.F = F; rp.K = F + H; rp.S = S;
     rp.P = (const __nv_bfloat16*)w.P; rp.uk = w.uk; rp.att_b = p->att_b; rp.att_w = p->att_w;
@@ -876,16 +898,14 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       MVC_TRY(sg.join());
       forked = false;
     }
-    if (!pre_t) {
+    if (!pre_t && !wt_ready) {
       if (loop_mode == DEC_LOOP_CHAIN) MVC_TRY(mvc_embedding_gather(p->embedding, E, tokens_in, SB, w.xemb, Ep, 1, st));
       MVC_TRY(mvc_transpose_to_bf16(w.xemb, 1, SB, Ep, Ep, q.xembT, SBp, st));
       MVC_TRY(mvc_transpose_to_bf16(w.xh, 1, SB, F + H, ldx, q.xhT, SBp, st));
-      if (!wt_ready) {
-        MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
-        MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
-      }
+      MVC_TRY(mvc_transpose_to_bf16(w.feats, 1, B * T, F, F, q.featsT, BTp, st));
+      MVC_TRY(mvc_transpose_to_bf16(w.wie, 1, 4 * H, Ep, Ep, q.wieT, 4 * H, st));
     }
-    const char* hprevT = cptr(q.xhT, (int64_t)F * SBp, 2);
+    const char* hprevT = cptr(xhT, (int64_t)F * SBp, 2);
     // the attention-parameter gradients (small GEMMs) run on the side stream next to the LSTM weight gradients
     MVC_TRY(sg.fork());
     {
@@ -908,11 +928,11 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       ep.mode = TC_MODE_PLAIN;
       ep.C = g->w_ih; ep.ldc = E + F;
       ep.C2 = g->w_hh; ep.ldc2 = H; ep.split_n = E + F;
-      MVC_TRY(tc_gemm(4 * H, E + F + H, SB, q.dGT, SBp, q.xembT, SBp, ep, 0, st));
+      MVC_TRY(tc_gemm(4 * H, E + F + H, SB, q.dGT, SBp, xallT, SBp, ep, 0, st));
     } else {
-      MVC_TRY(mvc_gemm_bf16(4 * H, F, SB, q.dGT, SBp, q.xhT, SBp, 0.f, g->w_ih + E, E + F, nullptr, nullptr, 0, st));
+      MVC_TRY(mvc_gemm_bf16(4 * H, F, SB, q.dGT, SBp, xhT, SBp, 0.f, g->w_ih + E, E + F, nullptr, nullptr, 0, st));
       MVC_TRY(mvc_gemm_bf16(4 * H, H, SB, q.dGT, SBp, hprevT, SBp, 0.f, g->w_hh, H, nullptr, nullptr, 0, st));
-      MVC_TRY(mvc_gemm_bf16(4 * H, E, SB, q.dGT, SBp, q.xembT, SBp, 0.f, g->w_ih, E + F, nullptr, nullptr, 0, st));
+      MVC_TRY(mvc_gemm_bf16(4 * H, E, SB, q.dGT, SBp, xallT, SBp, 0.f, g->w_ih, E + F, nullptr, nullptr, 0, st));
     }
     // bias gradients (column sums) behind the big GEMM on the caller's stream, next to the side stream's small GEMMs
     MVC_TRY(bias_grads());

@@ -81,10 +81,10 @@ __global__ void entropy_kernel(const float* __restrict__ logp, const int64_t* __
 // (x, y) keeps rows y, y + ENT_RG, ... of its column in registers, the column-wise max / sum / weighted sums are combined
 // across the row groups through shared memory.  (The 4-pass kernel above ran 16 warps per SM with 512 dependent-latency
 // loads per thread: 63 us for 2 x 37.7 MB; this one moves the same bytes in one read + one write.)
-// (16 row groups x 8 rows per thread: 512 threads per block at ~64 registers keep 32 warps per SM in flight; the first
-// shape -- 8 groups x 16 rows, 110 registers -- ran at 23 % occupancy and 36 us)
-constexpr int ENT_RPT = 8;
-constexpr int ENT_RG = 16;
+// (8 row groups x 16 rows per thread; 16 groups x 8 rows -- twice the occupancy, twice the shared-memory reads per
+// element -- measured 3 us slower: the kernel is issue bound, not latency bound)
+constexpr int ENT_RPT = 16;
+constexpr int ENT_RG = 8;
 __global__ void __launch_bounds__(32 * ENT_RG)
 entropy_tile_kernel(const float* __restrict__ logp, const int64_t* __restrict__ cap, int L, int B, int V,
                     float* __restrict__ result, double* __restrict__ ent_acc, float* __restrict__ dlogp, float ce_scale,

@@ -150,7 +150,8 @@ class DecoderFn(torch.autograd.Function):
         with _input_format(fmt):
             cabi.check(lib.mvc_decoder_forward(C.byref(d), C.byref(p), cabi.ptr(audio), Fa, cabi.ptr(visual), Fv,
                                                cabi.ptr(captions), fl, cabi.ptr(out), cabi.ptr(hid), cabi.ptr(tokens),
-                                               cabi.ptr(ws), nbytes, 1, cabi.stream_ptr()), "mvc_decoder_forward")
+                                               cabi.ptr(ws), nbytes, int(any(ctx.needs_input_grad)), cabi.stream_ptr()),
+                       "mvc_decoder_forward")      # (a backward pass will follow: forward also prepares its operands)
         ctx.dims = dims
         ctx.save_for_backward(out, tokens, ws, *params)
         # an output nothing consumed (the hidden states without a reconstructor) arrives as None in backward instead of a
