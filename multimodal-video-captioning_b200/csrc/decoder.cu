@@ -167,7 +167,7 @@ static DecWs dec_layout(const MvcDecoderDims* d, void* base) {
   w.act = ar.take<float>(S * B * 4 * H);
   w.c = ar.take<float>((S + 1) * B * H);
   w.xemb = ar.take<char>(S * B * Ep * es);
-  w.wcat = ar.take<char>(4 * H * (F + H) * es);
+  w.wcat = ar.take<char>((4 * H + (bf ? A : 0)) * (F + H) * es);   // bf16: + A rows [U | 0] (merged P / U.k GEMM, recur2)
   w.wie = bf ? ar.take<char>(4 * H * Ep * es) : nullptr;
   w.U = bf ? ar.take<char>(A * F * es) : nullptr;
   // bf16 vocabulary weights, followed (after padding to a multiple of 256 rows) by the attention query weights: one
@@ -383,9 +383,28 @@ static int dec_prepare_r2(const MvcDecoderDims* d, const MvcDecoderParams* p, co
   MVC_CHECK(Fa + Fv == F, "decoder: Fa (%d) + Fv (%d) != in_feature_size (%d)", Fa, Fv, F);
   MVC_TRY(sg.fork());
   cudaStream_t ss = sg.side->stream;
+  // (enqueue order = issue order of a captured graph's roots: the features leg first)
+  if (mvc_get_input_format() == MVC_INPUT_BF16) MVC_TRY(mvc_concat_bf16(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, st));
+  else MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, 1, st));
   MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, -H, ss));
   MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, 1, 2, ss));
+  // rows 4H .. 4H+A of the packed weights: [U | 0] -- the hoisted U.k projection rides in the P GEMM as one more N tile
+  // (352 -> 396 tiles of 128 x 256: three waves either way), instead of a 17 us GEMM of its own behind it
+  MVC_TRY(launch_cast_pad_bf16(p->att_U, A, F, F, (int)ldx, mptr(w.wcat, (int64_t)4 * H * ldx, 2), 0, ss));
   MVC_CUDA(cudaEventRecord(sg.side->aux[0], ss));
+  MVC_CUDA(cudaStreamWaitEvent(st, sg.side->aux[0], 0));
+  {
+    // P = keys . W_ih[:, E:]^T  ([B*T, F] x [F, 4H], 16-bit out, unit-major gate columns): the context half of every
+    // step's gate pre-activation becomes sum_t alpha_t P[b,t,:], accumulated out of tensor memory by the row owner
+    // (stored as fp16, saturating: |P| beyond 65504 means fully saturated gates anyway, and the 11-bit mantissa keeps
+    // the rounding error of the pre-activation 4x below bf16's on unnormalised features)
+    // columns [4H, 4H + A): uk = feats . U^T, fp32 (temporal_attention.py:21, hoisted)
+    TcEpilogue ep{};
+    ep.mode = TC_MODE_PLAIN;
+    ep.Cb = (__nv_bfloat16*)w.P; ep.ldcb = 4 * H; ep.cb_f16 = 1;
+    ep.C2 = w.uk; ep.ldc2 = A; ep.split_n = 4 * H;
+    MVC_TRY(tc_gemm(B * T, 4 * H + A, F, w.feats, F, w.wcat, ldx, ep, 0, st));
+  }
   MVC_TRY(launch_cast_pad_bf16(p->w_ih, 4 * H, E, E + F, Ep, w.wie, -H, ss));
   // tokens_in[0] = <SOS>, tokens_in[s] = captions[s] (features_captioning.py:99, :121-125); hoisted embedding GEMM
   MVC_TRY(launch_fill_i64(tokens_in, MVC_SOS, B, ss));
@@ -400,22 +419,6 @@ static int dec_prepare_r2(const MvcDecoderDims* d, const MvcDecoderParams* p, co
   // (last on this leg: the GEMM queues behind the caller's P GEMM for SMs)
   MVC_TRY(gemm_nt(MVC_BF16, S * B, 4 * H, Ep, w.xemb, Ep, w.wie, Ep, 0.f, w.gx, 4 * H, w.bsum, ss));
   MVC_CUDA(cudaEventRecord(sg.side->aux[1], ss));
-  if (mvc_get_input_format() == MVC_INPUT_BF16) MVC_TRY(mvc_concat_bf16(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, st));
-  else MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, 1, st));
-  MVC_CUDA(cudaStreamWaitEvent(st, sg.side->aux[0], 0));
-  {
-    // P = keys . W_ih[:, E:]^T  ([B*T, F] x [F, 4H], 16-bit out, unit-major gate columns): the context half of every
-    // step's gate pre-activation becomes sum_t alpha_t P[b,t,:], accumulated out of tensor memory by the row owner
-    // (stored as fp16, saturating: |P| beyond 65504 means fully saturated gates anyway, and the 11-bit mantissa keeps
-    // the rounding error of the pre-activation 4x below bf16's on unnormalised features)
-    TcEpilogue ep{};
-    ep.mode = TC_MODE_PLAIN;
-    ep.Cb = (__nv_bfloat16*)w.P; ep.ldcb = 4 * H; ep.cb_f16 = 1;
-    MVC_TRY(tc_gemm(B * T, 4 * H, F, w.feats, F, w.wcat, ldx, ep, 0, st));
-  }
-  MVC_TRY(mvc_cast_bf16(p->att_U, w.U, (int64_t)A * F, st));
-  // uk = feats . U^T      (temporal_attention.py:21, hoisted)
-  MVC_TRY(gemm_nt(MVC_BF16, B * T, A, F, w.feats, F, w.U, F, 0.f, w.uk, A, nullptr, st));
   // what only the vocabulary projection / the backward pass need: behind the features (event 0 of the caller's stream),
   // next to the persistent kernel
   MVC_TRY(sg.side_waits(0));

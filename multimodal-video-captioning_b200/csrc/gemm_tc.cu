@@ -800,7 +800,7 @@ gemm_bf16_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         const int f16 = ep.cb_f16;
         int gnc = gn, lim = N;                      // column inside the fp32 destination / first column that is not mine
         if (ep.C2) {                                // two destinations split at column split_n (a multiple of 4)
-          if (gn >= ep.split_n) { Cp = ep.C2; ldc = ep.ldc2; gnc = gn - ep.split_n; }
+          if (gn >= ep.split_n) { Cp = ep.C2; ldc = ep.ldc2; gnc = gn - ep.split_n; Cbp = nullptr; }   // 16-bit copy: first part only
           else lim = ep.split_n;
         }
         const bool c_vec = Cp && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp + gnc) & 15u) == 0 && gn + 3 < lim;
@@ -1174,7 +1174,7 @@ int tc_gemm(int M, int N, int K, const void* A, int64_t lda, const void* B, int6
   }
   if (ep.C2) {
     MVC_CHECK(ep.mode == TC_MODE_PLAIN && !(flags & (TC_FLAG_A_MN | TC_FLAG_B_MN)) && ep.split_n % 4 == 0 && ep.split_n > 0 &&
-                  ep.split_n < N && !ep.Cb,
+                  ep.split_n < N && (ep.C || ep.Cb) && (!ep.Cb || ep.ldcb >= ep.split_n),
               "tcgen05 GEMM: the two-destination epilogue needs the plain mode, K-major operands and split_n %% 4 == 0");
     return launch_tc_persist<TC_MODE_PLAIN>(M, N, K, A, lda, B, ldb, ep, pdl, st);
   }

@@ -24,7 +24,8 @@ struct TcEpilogue {
   __nv_bfloat16* Cb;
   int64_t ldcb;
   // plain mode, persistent kernel: optional SECOND fp32 destination for the columns >= split_n (C2[m, n - split_n], ld ldc2;
-  // split_n a multiple of 4): one GEMM can feed two parameter-gradient tensors that share the A operand
+  // split_n a multiple of 4): one GEMM can feed two tensors that share the A operand.  C / Cb (either may be null) then
+  // receive the columns < split_n only.
   float* C2;
   int64_t ldc2;
   int split_n;
