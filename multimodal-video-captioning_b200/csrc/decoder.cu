@@ -85,8 +85,8 @@ static int get_loop_mode(const void* ws) {
 // join -- order the caller's stream after whatever the side stream was given, so the torch-owned workspaces the side
 // stream writes cannot be recycled under it.
 struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;    // stream2: a second leg for three-way splits
+  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
   cudaEvent_t aux[2] = {nullptr, nullptr};             // intermediate dependencies between the two streams
 };
 static int get_side_stream(cudaStream_t caller, SideStream** out) {
@@ -100,6 +100,8 @@ static int get_side_stream(cudaStream_t caller, SideStream** out) {
   if (it == pool.end()) {
     SideStream* s = new SideStream();
     MVC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    MVC_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    MVC_CUDA(cudaEventCreateWithFlags(&s->join2, cudaEventDisableTiming));
     MVC_CUDA(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
     MVC_CUDA(cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming));
     for (auto& e : s->aux) MVC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -112,7 +114,17 @@ struct SideGuard {
   cudaStream_t caller;
   SideStream* side = nullptr;
   bool open = false;                                   // forked and not yet joined
+  bool open2 = false;                                  // second leg forked and not yet joined
   explicit SideGuard(cudaStream_t c) : caller(c) {}
+  int fork2() {                                        // right after fork(): the second leg starts at the same point
+    MVC_CUDA(cudaStreamWaitEvent(side->stream2, side->fork, 0));
+    open2 = true;
+    return 0;
+  }
+  int mark2() {
+    MVC_CUDA(cudaEventRecord(side->join2, side->stream2));
+    return 0;
+  }
   int fork() {                                         // side stream continues after everything enqueued on `caller`
     if (!side) MVC_TRY(get_side_stream(caller, &side));
     MVC_CUDA(cudaEventRecord(side->fork, caller));
@@ -139,12 +151,20 @@ struct SideGuard {
       MVC_CUDA(cudaStreamWaitEvent(caller, side->join, 0));
       open = false;
     }
+    if (open2) {
+      MVC_CUDA(cudaStreamWaitEvent(caller, side->join2, 0));
+      open2 = false;
+    }
     return 0;
   }
   ~SideGuard() {
     if (open) {                                        // error path: never leave the side stream running un-joined
       cudaEventRecord(side->join, side->stream);
       cudaStreamWaitEvent(caller, side->join, 0);
+    }
+    if (open2) {
+      cudaEventRecord(side->join2, side->stream2);
+      cudaStreamWaitEvent(caller, side->join2, 0);
     }
   }
 };
@@ -910,16 +930,20 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
     }
     const char* hprevT = cptr(xhT, (int64_t)F * SBp, 2);
     // the attention-parameter gradients (small GEMMs) run on the side stream next to the LSTM weight gradients
+    // three legs: the LSTM weight gradients + bias sums (caller), embedding + dW_att (side), dU (second side leg) -- the
+    // small GEMMs are serial k-block chains on few tiles (15-30 us each), six of them in a row were the tail's critical path
     MVC_TRY(sg.fork());
+    MVC_TRY(sg.fork2());
     {
-      cudaStream_t ss = sg.side->stream;
+      cudaStream_t ss = sg.side->stream, s2 = sg.side->stream2;
+      MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * T, A, A, q.dukT, BTp, s2));
+      MVC_TRY(mvc_gemm_bf16(A, F, B * T, q.dukT, BTp, featsT, BTp, 0.f, g->att_U, F, nullptr, nullptr, 0, s2));
+      MVC_TRY(sg.mark2());
       // the embedding gradient (dxemb = dG . W_ie, scattered into the table) needs neither dG^T nor the main stream
       MVC_TRY(mvc_gemm_bf16(SB, E, 4 * H, q.dG_b, 4 * H, wieT, 4 * H, 0.f, q.dxemb, E, nullptr, nullptr, 0, ss));
       MVC_TRY(mvc_embedding_scatter_add(q.dxemb, E, E, tokens_in, SB, g->embedding, ss));
       MVC_TRY(mvc_transpose_to_bf16(q.dwq_b, 1, SB, A, A, q.dwqT, SBp, ss));
-      MVC_TRY(mvc_transpose_to_bf16(q.duk, 0, B * T, A, A, q.dukT, BTp, ss));
       MVC_TRY(mvc_gemm_bf16(A, H, SB, q.dwqT, SBp, hprevT, SBp, 0.f, g->att_W, H, nullptr, nullptr, 0, ss));
-      MVC_TRY(mvc_gemm_bf16(A, F, B * T, q.dukT, BTp, featsT, BTp, 0.f, g->att_U, F, nullptr, nullptr, 0, ss));
       MVC_TRY(sg.mark());
       forked = true;
     }

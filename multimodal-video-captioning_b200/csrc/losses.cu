@@ -92,32 +92,31 @@ entropy_tile_kernel(const float* __restrict__ logp, const int64_t* __restrict__ 
   __shared__ float red[ENT_RG][33];
   __shared__ float red2[ENT_RG][33];
   __shared__ float bsum[32];
+  __shared__ int stok[ENT_RG * ENT_RPT];          // target token of every row of this step (PAD beyond B)
   const int s = blockIdx.y + 1;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int v = blockIdx.x * 32 + tx;
   const bool live = v < V;
-  const float* col = logp + (int64_t)s * B * V + v;
-  const int64_t* caps = cap + (int64_t)s * B;
+  for (int i = ty * 32 + tx; i < ENT_RG * ENT_RPT; i += 32 * ENT_RG) stok[i] = i < B ? (int)cap[(int64_t)s * B + i] : (int)MVC_PAD;
+  // rows ty, ty + ENT_RG, ...: one base pointer, compile-time multiples of the row-group pitch
+  const size_t pitch = (size_t)ENT_RG * V;
+  const float* xp = logp + ((size_t)s * B + ty) * V + v;
   float x[ENT_RPT], pr[ENT_RPT];
-  int tok[ENT_RPT];
   float mx = -INFINITY;
 #pragma unroll
   for (int i = 0; i < ENT_RPT; ++i) {
-    const int b = ty + ENT_RG * i;
-    const bool in = live && b < B;
-    x[i] = in ? col[(int64_t)b * V] : -INFINITY;
-    tok[i] = b < B ? (int)caps[b] : (int)MVC_PAD;
+    x[i] = (live && ty + ENT_RG * i < B) ? xp[i * pitch] : -INFINITY;
     mx = fmaxf(mx, x[i]);
   }
   red[ty][tx] = mx;
-  __syncthreads();
+  __syncthreads();                                // (also publishes stok)
 #pragma unroll
   for (int g = 0; g < ENT_RG; ++g) mx = fmaxf(mx, red[g][tx]);
   // one exponential per element: e = exp(x - max); p = e / z; log p = x - (max + log z)
   float z = 0.f;
 #pragma unroll
   for (int i = 0; i < ENT_RPT; ++i) {
-    pr[i] = (ty + ENT_RG * i < B && live) ? expf(x[i] - mx) : 0.f;
+    pr[i] = live ? __expf(x[i] - mx) : 0.f;       // rows beyond B hold -inf: exp -> 0
     z += pr[i];
   }
   red2[ty][tx] = z;
@@ -128,6 +127,7 @@ entropy_tile_kernel(const float* __restrict__ logp, const int64_t* __restrict__ 
   const float lse = live ? mx + logf(z) : 0.f;
   const float rz = live ? 1.f / z : 0.f;
   float e_sum = 0.f, q = 0.f;                     // q = sum_b m_b p_b (log p_b + 1)
+  unsigned keep = 0;                              // bit i: row i of this thread is a non-PAD target row
 #pragma unroll
   for (int i = 0; i < ENT_RPT; ++i) {
     const bool in = live && (ty + ENT_RG * i < B);
@@ -135,7 +135,8 @@ entropy_tile_kernel(const float* __restrict__ logp, const int64_t* __restrict__ 
     const float p = pr[i] * rz;
     x[i] = lp;
     pr[i] = p;
-    if (in && tok[i] != MVC_PAD) {
+    if (in && stok[ty + ENT_RG * i] != MVC_PAD) {
+      keep |= 1u << i;
       e_sum += p * lp;
       q += p * (lp + 1.f);
     }
@@ -150,15 +151,16 @@ entropy_tile_kernel(const float* __restrict__ logp, const int64_t* __restrict__ 
     const float cnt = result[2];
     const float es = -ent_scale / (float)B;
     const float ce = ce_scale / cnt;
+    float* gp = dlogp + ((size_t)s * B + ty) * V + v;
+    float* g0 = dlogp + (size_t)ty * V + v;       // row 0 of the gradient (no gradient: sentence[0] is a constant)
 #pragma unroll
     for (int i = 0; i < ENT_RPT; ++i) {
-      const int b = ty + ENT_RG * i;
-      if (b < B) {
-        const float m = tok[i] != MVC_PAD ? 1.f : 0.f;
-        float g = es * pr[i] * (m * (x[i] + 1.f) - q);
-        if (tok[i] != MVC_PAD && tok[i] == v) g -= ce;
-        dlogp[((int64_t)s * B + b) * V + v] = g;
-        if (s == 1) dlogp[(int64_t)b * V + v] = 0.f;                     // row 0 gets no gradient
+      if (ty + ENT_RG * i < B) {
+        const bool k = (keep >> i) & 1u;
+        float g = es * pr[i] * ((k ? x[i] + 1.f : 0.f) - q);
+        if (k && stok[ty + ENT_RG * i] == v) g -= ce;
+        gp[i * pitch] = g;
+        if (s == 1) g0[i * pitch] = 0.f;
       }
     }
   }
