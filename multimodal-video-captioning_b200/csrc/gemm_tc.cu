@@ -1099,8 +1099,20 @@ static int launch_tc_persist(int M, int N, int K, const void* A, int64_t lda, co
     configured = true;
   }
   const int64_t tiles = cdiv(M, TC_BM) * cdiv(N, PG_BN);
+  // Optional balanced grid (MVC_B200_GEMM_BALANCED=1): the kernel takes ceil(tiles / SMs) rounds whatever the grid; the
+  // SMALLEST grid with that many rounds gives every CTA the same number of tiles and leaves the other SMs to the
+  // neighbouring streams (192 tiles: 96 CTAs x 2 instead of 148 CTAs of which 44 run two).  Same stand-alone duration;
+  // inside the train step it measured 1.7 % SLOWER (137.1 k vs 139.5 k samples/s): the neighbours are cluster launches
+  // that do better on the SMs the one-tile CTAs free half-way than on scattered idle SMs.  Off by default.
+  static int balanced = -1;
+  if (balanced < 0) {
+    const char* e = getenv("MVC_B200_GEMM_BALANCED");
+    balanced = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int64_t rounds = cdiv(tiles, kNumSMs);
+  const int64_t grid = balanced ? cdiv(tiles, rounds) : (tiles < kNumSMs ? tiles : kNumSMs);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
+  cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = PG_SMEM;
   cfg.stream = st;
