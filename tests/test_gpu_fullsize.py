@@ -163,3 +163,41 @@ def test_c3_fp32_greedy_ids_identical_to_oracle(dev):
     rate = float((ids_b == ref).all(1).float().mean())
     print(f"bf16 greedy captions identical to fp32 oracle: {rate:.3f}")
     assert rate > 0.5
+
+
+def test_c2_backward_without_forward_side_preparation(dev, monkeypatch):
+    """A training forward (save_for_backward = 1, recur2 path) prepares the backward pass's operands itself: transposed
+    weights / keys under the persistent kernel, ctx rows and [emb ; ctx ; h]^T under the vocabulary projection.  A forward
+    called with save_for_backward = 0 leaves all of that to mvc_decoder_backward: both orders must give the same
+    gradients (same kernels on the same data; only the embedding scatter's atomic order may differ)."""
+    from models import AVCaptioning
+    from salstm import cabi
+    import losses as Lm
+    B, T, L, V = 128, 44, 24, 3201
+    audio, visual, caps = O.synth_batch(B, T, L, V, seed=3)
+    audio, visual, caps = (audio / 255.0).to(dev), (visual / 10.0).to(dev), caps.to(dev)
+
+    def run():
+        torch.manual_seed(11)
+        model = AVCaptioning(Vocab(V), 1.0, "none", device=dev, precision="bf16").to(dev)
+        out, _, _ = model(audio, visual, caps)
+        Lm.ModalityWiseReconstructionLoss(out, caps, **LAM)[0].mean().backward()
+        return out.detach().clone(), {k: v.grad.clone() for k, v in model.named_parameters()}
+
+    out_a, g_a = run()
+    lib = cabi.lib()
+    orig = lib.mvc_decoder_forward
+    seen = []
+
+    def no_prep(*args):
+        args = list(args)
+        seen.append(args[13])
+        args[13] = 0                                   # save_for_backward
+        return orig(*args)
+
+    monkeypatch.setattr(lib, "mvc_decoder_forward", no_prep)
+    out_b, g_b = run()
+    assert seen == [1]                                 # the autograd path asks for the preparation
+    assert torch.equal(out_a, out_b)
+    for k in g_a:
+        torch.testing.assert_close(g_b[k], g_a[k], rtol=1e-5, atol=1e-7, msg=k)
