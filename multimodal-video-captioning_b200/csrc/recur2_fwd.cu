@@ -606,8 +606,120 @@ r2_ctx_rows_kernel(const __nv_bfloat16* __restrict__ feats, const float* __restr
     }
 }
 
+// Tensor-core form of the same contraction (T <= 64): per row b it is the small GEMM ctx[S, F] = alpha_b[S, T] . keys_b[T, F].
+// block = (256 features, row b, 32 steps), 4 warps x 64 features; alpha is split into two bf16 terms (hi + lo: the fp32
+// weight to 2^-17) held as mma.sync A fragments in registers for the whole block, the key tile is staged once in shared
+// memory ([t][f], 16-byte copies) and read as B fragments by ldmatrix.trans; fp32 accumulation, bf16 result.  The key
+// tile is read once (not once per 8-step chunk) and the FMA pipe is left alone: 33 -> ~10 us, and it no longer slows the
+// vocabulary projection it runs next to.
+constexpr int CM_F = 256, CM_KP = CM_F + 8, CM_AP = 72;
+__global__ void __launch_bounds__(128)
+r2_ctx_rows_mma_kernel(const __nv_bfloat16* __restrict__ feats, const float* __restrict__ alpha, int B, int T, int F, int S,
+                       __nv_bfloat16* __restrict__ xh, int64_t ldx) {
+  __shared__ __align__(16) __nv_bfloat16 sK[64 * CM_KP];
+  __shared__ __align__(16) __nv_bfloat16 sAh[32 * CM_AP];
+  __shared__ __align__(16) __nv_bfloat16 sAl[32 * CM_AP];
+  const int b = blockIdx.y, f0 = blockIdx.x * CM_F, s0 = blockIdx.z * 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int Tk = (T + 15) & ~15;
+  const int nf = F - f0 < CM_F ? F - f0 : CM_F;              // live features of this block (a multiple of 8)
+  for (int i = tid; i < 32 * 64; i += 128) {
+    const int m = i >> 6, t = i & 63;
+    const float a = (s0 + m < S && t < T) ? alpha[((size_t)(s0 + m) * B + b) * T + t] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16(a);
+    sAh[m * CM_AP + t] = hi;
+    sAl[m * CM_AP + t] = __float2bfloat16(a - __bfloat162float(hi));
+  }
+  for (int i = tid; i < Tk * (CM_F / 8); i += 128) {
+    const int t = i >> 5, c = i & 31;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (t < T && c * 8 < nf) v = *reinterpret_cast<const uint4*>(feats + ((size_t)b * T + t) * F + f0 + c * 8);
+    *reinterpret_cast<uint4*>(sK + t * CM_KP + c * 8) = v;
+  }
+  __syncthreads();
+  uint32_t ah[2][4][4], al[2][4][4];                         // [m tile][k step][fragment register]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int o = (mt * 16 + g) * CM_AP + ks * 16 + 2 * q;
+      ah[mt][ks][0] = *reinterpret_cast<const uint32_t*>(sAh + o);
+      ah[mt][ks][1] = *reinterpret_cast<const uint32_t*>(sAh + o + 8 * CM_AP);
+      ah[mt][ks][2] = *reinterpret_cast<const uint32_t*>(sAh + o + 8);
+      ah[mt][ks][3] = *reinterpret_cast<const uint32_t*>(sAh + o + 8 * CM_AP + 8);
+      al[mt][ks][0] = *reinterpret_cast<const uint32_t*>(sAl + o);
+      al[mt][ks][1] = *reinterpret_cast<const uint32_t*>(sAl + o + 8 * CM_AP);
+      al[mt][ks][2] = *reinterpret_cast<const uint32_t*>(sAl + o + 8);
+      al[mt][ks][3] = *reinterpret_cast<const uint32_t*>(sAl + o + 8 * CM_AP + 8);
+    }
+  const int mi = lane >> 3, mr = lane & 7;                   // ldmatrix: lanes 8i..8i+7 address the rows of matrix i
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const int nb = warp * 64 + it * 16;                      // 16 features = two n tiles
+    if (nb >= nf) break;
+    float acc[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      if (ks * 16 < Tk) {
+        // matrices: (k 0-7, n 0-7), (k 8-15, n 0-7), (k 0-7, n 8-15), (k 8-15, n 8-15), transposed on the way in
+        const uint32_t addr = smem_u32(sK + (ks * 16 + (mi & 1) * 8 + mr) * CM_KP + nb + (mi >> 1) * 8);
+        uint32_t bq[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(bq[0]), "=r"(bq[1]), "=r"(bq[2]), "=r"(bq[3]) : "r"(addr));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+                         : "r"(ah[mt][ks][0]), "r"(ah[mt][ks][1]), "r"(ah[mt][ks][2]), "r"(ah[mt][ks][3]),
+                           "r"(bq[2 * nt]), "r"(bq[2 * nt + 1]));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+                         : "r"(al[mt][ks][0]), "r"(al[mt][ks][1]), "r"(al[mt][ks][2]), "r"(al[mt][ks][3]),
+                           "r"(bq[2 * nt]), "r"(bq[2 * nt + 1]));
+          }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int fl = nb + nt * 8 + 2 * q;                  // feature inside the block
+        if (fl < nf) {
+          const int sa = s0 + mt * 16 + g, sb = sa + 8;
+          if (sa < S)
+            *reinterpret_cast<__nv_bfloat162*>(xh + ((size_t)sa * B + b) * ldx + f0 + fl) =
+                __floats2bfloat162_rn(acc[mt][nt][0], acc[mt][nt][1]);
+          if (sb < S)
+            *reinterpret_cast<__nv_bfloat162*>(xh + ((size_t)sb * B + b) * ldx + f0 + fl) =
+                __floats2bfloat162_rn(acc[mt][nt][2], acc[mt][nt][3]);
+        }
+      }
+  }
+}
+
 int r2_ctx_rows(const void* feats_bf16, const float* alpha, int B, int T, int F, int S, void* xh_bf16, int64_t ldx,
                 cudaStream_t st) {
+  static int use_mma = -1;
+  if (use_mma < 0) {
+    const char* e = getenv("MVC_B200_CTX_MMA");
+    use_mma = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_mma && T <= 64 && F % 8 == 0 && ldx % 2 == 0 && (reinterpret_cast<uintptr_t>(feats_bf16) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(xh_bf16) & 3) == 0) {
+    dim3 grid((unsigned)cdiv(F, CM_F), (unsigned)B, (unsigned)cdiv(S, 32));
+    r2_ctx_rows_mma_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)feats_bf16, alpha, B, T, F, S,
+                                                 (__nv_bfloat16*)xh_bf16, ldx);
+    MVC_LAUNCH_CHECK();
+    return 0;
+  }
   MVC_CHECK(F % 4 == 0 && ldx % 4 == 0 && T <= 1024, "r2_ctx_rows: unsupported dims S=%d T=%d F=%d", S, T, F);
   dim3 grid((unsigned)cdiv(F, 4 * CR_THREADS), (unsigned)B, (unsigned)cdiv(S, CR_S));
   const int Tp = (T + 3) & ~3;
