@@ -48,6 +48,16 @@ struct VecOf<__nv_bfloat16> {
   }
 };
 
+// eight fp16 values (the projected keys of the decode loops)
+__device__ __forceinline__ void unpack_f16x8(const uint4& r, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+
 // dynamic smem layout (floats): sQ[A] (wq+bias), sW[A], sE[T], sRed[32], sPart[G*chunk]
 template <typename KT, bool FAST, bool VEC>
 __global__ void __launch_bounds__(256)
@@ -437,7 +447,7 @@ attn_fwd_staged_kernel(const AttnFwdArgs a, int chunk) {
 // the context sum, the stores and the query / score / soft-max phases of block i + 1.  (A fresh CTA per block
 // serialises load -> compute: 4.7 us per block of which 3.6 us is the block's share of HBM time.)
 // Requires: one query per key block, bf16 keys with k_st == F (contiguous block), F / 8 <= NT.
-template <bool FAST, int AV, int NT>
+template <bool FAST, int AV, int NT, bool F16 = false>
 __global__ void __launch_bounds__(NT, 1)
 attn_fwd_stream_kernel(const AttnFwdArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -576,7 +586,8 @@ attn_fwd_stream_kernel(const AttnFwdArgs a) {
       for (int t = 0; t < Th; ++t) {
         const uint4 raw = *reinterpret_cast<const uint4*>(sK + (size_t)t * F + v * VN);
         float x[VN];
-        VecOf<KT>::unpack(raw, x);
+        if constexpr (F16) unpack_f16x8(raw, x);
+        else VecOf<KT>::unpack(raw, x);
         const float pw = sP[t];
 #pragma unroll
         for (int i = 0; i < VN; ++i) acc[i] = fmaf(pw, x[i], acc[i]);
@@ -593,7 +604,8 @@ attn_fwd_stream_kernel(const AttnFwdArgs a) {
       for (int t = Th; t < T; ++t) {
         const uint4 raw = *reinterpret_cast<const uint4*>(sK + (size_t)t * F + v * VN);
         float x[VN];
-        VecOf<KT>::unpack(raw, x);
+        if constexpr (F16) unpack_f16x8(raw, x);
+        else VecOf<KT>::unpack(raw, x);
         const float pw = sP[t];
 #pragma unroll
         for (int i = 0; i < VN; ++i) acc[i] = fmaf(pw, x[i], acc[i]);
@@ -1051,15 +1063,25 @@ static const void* pick_fwd_staged(int A) {
   }
 }
 // queries per pass of the multi-query kernel: 5 (the reference's beam width, features_captioning.py:131) or 8
-template <bool FAST>
+template <bool FAST, bool F16 = false>
 static const void* pick_fwd_stream(int A) {
   switch (A) {
-    case 32: return (const void*)attn_fwd_stream_kernel<FAST, 1, 288>;
-    case 64: return (const void*)attn_fwd_stream_kernel<FAST, 2, 288>;
-    case 128: return (const void*)attn_fwd_stream_kernel<FAST, 4, 288>;
-    case 256: return (const void*)attn_fwd_stream_kernel<FAST, 8, 288>;
+    case 32: return (const void*)attn_fwd_stream_kernel<FAST, 1, 288, F16>;
+    case 64: return (const void*)attn_fwd_stream_kernel<FAST, 2, 288, F16>;
+    case 128: return (const void*)attn_fwd_stream_kernel<FAST, 4, 288, F16>;
+    case 256: return (const void*)attn_fwd_stream_kernel<FAST, 8, 288, F16>;
     default: return nullptr;
   }
+}
+static size_t stream_smem(int T, int A, int F) {
+  const size_t tp = (size_t)((T + 3) & ~3);
+  return (((size_t)T * F * 2 + 127) & ~size_t(127)) + sizeof(float) * (2 * (size_t)T * A + 3 * (size_t)A + 2 * tp) + 64;
+}
+// would launch_attention_fwd take the streaming kernel for one query per key block of F 16-bit values?
+bool attention_stream_eligible(int rows, int keys_batch, int T, int A, int F) {
+  return rows == keys_batch && keys_batch > kNumSMs && F % 8 == 0 && F / 8 <= 288 && T <= ATT_MAXR * 9 &&
+         (A == 32 || A == 64 || A == 128 || A == 256) && stream_smem(T, A, F) <= kAttnMaxSmem &&
+         !getenv("MVC_B200_ATTN_NOSTREAM");
 }
 
 template <int QB>
@@ -1116,9 +1138,9 @@ int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
   // several waves of key blocks, one query each (greedy decode): the streaming kernel, one persistent CTA per SM
   if (kern && !mq && nq == 1 && a.keys_bf16 && a.k_st == F && a.keys_batch > kNumSMs && F / 8 <= 288 &&
       !getenv("MVC_B200_ATTN_NOSTREAM")) {
-    const void* ks = a.fast_math ? pick_fwd_stream<true>(A) : pick_fwd_stream<false>(A);
-    const size_t tp = (size_t)((T + 3) & ~3);
-    const size_t smem = (((size_t)T * F * 2 + 127) & ~size_t(127)) + sizeof(float) * (2 * (size_t)T * A + 3 * (size_t)A + 2 * tp) + 64;
+    const void* ks = a.keys_f16 ? (a.fast_math ? pick_fwd_stream<true, true>(A) : pick_fwd_stream<false, true>(A))
+                                : (a.fast_math ? pick_fwd_stream<true>(A) : pick_fwd_stream<false>(A));
+    const size_t smem = stream_smem(T, A, F);
     if (ks && smem <= kAttnMaxSmem) {
       MVC_TRY(ensure_big_smem(ks));
       AttnFwdArgs args = a;
@@ -1128,6 +1150,7 @@ int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st) {
       return 0;
     }
   }
+  MVC_CHECK(!a.keys_f16, "mvc_soft_attention_fwd: fp16 (projected) keys are served by the streaming kernel only");
   if (kern) {
     const size_t tp = (size_t)((T + 3) & ~3);
     const size_t tail0 = mq ? sizeof(float) * ((qb + 1) * (size_t)A + 3 * qb * tp) + 16

@@ -58,6 +58,7 @@ struct AttnFwdArgs {
   const uint8_t* mask; int64_t m_sb, m_st;
   float* ctx_f32; int64_t ctx_ld; void* ctx_bf16; int64_t ctxb_ld; float* alpha;
   int fast_math;
+  int keys_f16;               // the 16-bit "keys" are IEEE fp16 (projected keys P = keys . W_c^T): streaming kernel only
   unsigned long long* prof;   // debug: 8 globaltimer stamps per CTA (mvc_debug_set_attn_prof), normally null
 };
 int launch_attention_fwd(const AttnFwdArgs& a, bool pdl, cudaStream_t st);
@@ -110,7 +111,13 @@ struct StepFwd {
   int64_t h_ld;
   bool first;
   bool wq_ready;       // wq already holds W.h_s (written by the previous vocabulary GEMM), skip the projection            // h_s == 0: skip the wq GEMM
+  // Projected-keys form (decode loops at several waves of rows): pkeys = P [keys_batch*T, 4H] fp16 = keys . W_c^T in the
+  // gate-column order of wcat; the attention pass then returns gc = sum_t alpha_t P[b,t,:] [rows, 4H] fp32 instead of ctx,
+  // and the gate GEMM contracts over h only (K = H instead of F + H), gc riding in as an addend of the cell epilogue.
+  const void* pkeys = nullptr;
+  float* gc = nullptr;
 };
+bool attention_stream_eligible(int rows, int keys_batch, int T, int A, int F);
 
 static inline int step_forward(const StepCfg& c, const StepFwd& io, cudaStream_t st) {
   const bool bf = c.prec == MVC_BF16;
@@ -136,7 +143,25 @@ static inline int step_forward(const StepCfg& c, const StepFwd& io, cudaStream_t
   a.ctx_f32 = bf ? nullptr : (float*)io.xh_src; a.ctx_ld = ldx;
   a.ctx_bf16 = bf ? io.xh_src : nullptr; a.ctxb_ld = ldx;
   a.alpha = io.alpha; a.fast_math = bf ? 1 : 0;
+  if (io.pkeys) {
+    a.F = 4 * c.H; a.keys = io.pkeys; a.keys_bf16 = 1; a.keys_f16 = 1; a.k_sb = (int64_t)c.T * 4 * c.H; a.k_st = 4 * c.H;
+    a.ctx_f32 = io.gc; a.ctx_ld = 4 * c.H; a.ctx_bf16 = nullptr;
+  }
   MVC_TRY(launch_attention_fwd(a, bf && !io.first, st));
+  if (io.pkeys) {
+    // gates = gc + h_s . W_hh^T + embedding-table row  -> cell
+    TcEpilogue ep{};
+    ep.mode = TC_MODE_CELL;
+    ep.H = c.H;
+    ep.bias = c.cell_bias;
+    ep.gx = io.gc; ep.gx_ld = 4 * c.H;
+    ep.embtab = io.tokens ? c.embtab : nullptr; ep.tokens = io.tokens;
+    ep.c_prev = io.c_prev; ep.act = io.act; ep.c_out = io.c_out;
+    ep.h32 = io.h_out32; ep.h_ld = io.h_ld;
+    ep.hb = io.xh_dst ? (__nv_bfloat16*)mptr(io.xh_dst, c.F, es) : nullptr; ep.hb_ld = ldx;
+    return tc_gemm(R, 4 * c.H, c.H, cptr(io.xh_src, c.F, es), ldx, cptr(c.wcat, c.F, es), ldx, ep,
+                   TC_FLAG_PDL | TC_FLAG_B_CONST, st);
+  }
   // gates = [ctx_s ; h_s] . wcat^T  -> cell         (nn.LSTM, features_captioning.py:84)
   if (bf && c.perm) {
     TcEpilogue ep{};

@@ -140,7 +140,7 @@ def test_c2_fp32_exact_path_vs_oracle(dev, c2_oracle):
         torch.testing.assert_close(v.grad.cpu(), ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()) + 1e-9, msg=k)
 
 
-def test_c3_fp32_greedy_ids_identical_to_oracle(dev):
+def test_c3_fp32_greedy_ids_identical_to_oracle(dev, monkeypatch):
     """BASELINE configs[2] per-GPU shape: B=512, T=30, 30 positions, V=10547; exact caption agreement on the fp32 path."""
     from models import AVCaptioning
     B, T, L, V = 512, 30, 30, 10547
@@ -163,6 +163,16 @@ def test_c3_fp32_greedy_ids_identical_to_oracle(dev):
     rate = float((ids_b == ref).all(1).float().mean())
     print(f"bf16 greedy captions identical to fp32 oracle: {rate:.3f}")
     assert rate > 0.5
+    # the opt-in projected-keys form of the decode step (MVC_B200_GREEDY_P=1, B > 148 rows: attention sums
+    # P = keys . W_c^T rows, gate GEMM over h only) must tell the same story as the plain form
+    monkeypatch.setenv("MVC_B200_GREEDY_P", "1")
+    with torch.no_grad():
+        ids_c = model.decoder.greedy_ids((audio.to(dev), visual.to(dev)), L).cpu()
+    monkeypatch.delenv("MVC_B200_GREEDY_P")
+    rate_c = float((ids_c == ref).all(1).float().mean())
+    both = float((ids_c == ids_b).all(1).float().mean())
+    print(f"projected-keys form: {rate_c:.3f}; == plain form: {both:.3f}")
+    assert rate_c > 0.5 and rate_c >= rate - 0.05 and both > 0.5
 
 
 def test_c2_backward_without_forward_side_preparation(dev, monkeypatch):
