@@ -14,13 +14,22 @@ from salstm.trainer import FlatClipAdam, GraphedTrainStep
 import losses as Lm
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "train"
-dev = torch.device("cuda:0")
+# under torchrun (WORLD_SIZE > 1): data-parallel step with the gradient exchange; rank 0 prints its own timeline
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+    if rank != 0:
+        sys.stdout = open(os.devnull, "w")
 w = Bn.WORKLOADS[wl]
 shape = Bn.SHAPES[w["shape"]]
 model = Bn.build_model(wl, dev, "bf16")
-bs = [tuple(t.to(dev) for t in b) for b in Bn.make_batches(shape, 4)]
+bs = [tuple(t.to(dev) for t in b) for b in Bn.make_batches(shape, 4, seed0=1 + 100 * rank)]
 loss_fn = Lm.ModalityWiseReconstructionLossBuilder(rec_type=w["rec"], **Bn.LAMBDAS)
-opt = FlatClipAdam(model.parameters(), lr=1e-4)
+opt = FlatClipAdam(model.parameters(), lr=1e-4, world_size=world if world > 1 else None)
 step = GraphedTrainStep(model, loss_fn, opt, bs[0], slots=4)
 for ins, src in zip(step.input_slots, bs):
     for dst, t_ in zip(ins, src):
@@ -77,3 +86,7 @@ for e in ks:
 print("# by kernel: launches, total us, exclusive us (alone on the GPU)")
 for n, a in sorted(agg.items(), key=lambda kv: -kv[1][2]):
     print("#  %3d %9.1f %9.1f  %s" % (a[0], a[1], a[2], n))
+if world > 1:
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
