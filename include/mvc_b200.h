@@ -410,6 +410,16 @@ int mvc_clip_adam_multimem(const float* param_local, float* param_mc, const floa
                            float beta1, float beta2, float eps, float weight_decay, float clip_value, float grad_scale,
                            void* stream);
 
+/* Same update with the reduce-scatter done by peer loads: grad_replicas[r] (r = 0 .. world-1, host array of device
+ * pointers: every rank's flat gradient buffer as mapped into THIS process, e.g. the buffer_ptrs of a symmetric-memory
+ * allocation) are read by the owner of [lo, hi) and summed in rank order; the new parameters still leave by multimem.st.
+ * multimem.ld_reduce makes the switch fetch every replica over NVLink, the requester's own included; peer loads export a
+ * third fewer bytes per GPU at 2 ranks (11 % fewer at 8).  Same barriers around the call as mvc_clip_adam_multimem. */
+int mvc_clip_adam_p2p_multimem(const float* param_local, float* param_mc, const float* const* grad_replicas, int world,
+                               float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t lo, int64_t hi,
+                               float* state_dev, int tick, float beta1, float beta2, float eps, float weight_decay,
+                               float clip_value, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

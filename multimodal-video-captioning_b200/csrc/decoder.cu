@@ -231,16 +231,22 @@ __global__ void pack_wcat_kernel(const float* __restrict__ w_x, int64_t wx_ld, c
 }
 
 // bf16 variant with 16-byte loads: one block row per output row (no 64-bit division per element), 4 elements per thread
+// (rows [4H, 4H + n_extra) of the output, if any: [extra (n_extra x F) | 0])
 __global__ void __launch_bounds__(256)
 pack_wcat_vec_kernel(const float* __restrict__ w_x, int64_t wx_ld, const float* __restrict__ w_hh, int F, int H,
-                     __nv_bfloat16* __restrict__ out, int perm) {
+                     __nv_bfloat16* __restrict__ out, int perm, const float* __restrict__ extra) {
   const int ro = blockIdx.y;
-  const int64_t r = perm == 2 ? gate_unperm(-H, ro) : (perm ? gate_unperm(H, ro) : ro);
   const int K = F + H;
   const int k = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (k >= K) return;
-  const float4 v = k < F ? *reinterpret_cast<const float4*>(w_x + r * wx_ld + k)
-                         : *reinterpret_cast<const float4*>(w_hh + r * H + (k - F));
+  float4 v;
+  if (ro >= 4 * H) {
+    v = k < F ? *reinterpret_cast<const float4*>(extra + (int64_t)(ro - 4 * H) * F + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    const int64_t r = perm == 2 ? gate_unperm(-H, ro) : (perm ? gate_unperm(H, ro) : ro);
+    v = k < F ? *reinterpret_cast<const float4*>(w_x + r * wx_ld + k)
+              : *reinterpret_cast<const float4*>(w_hh + r * H + (k - F));
+  }
   const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
   uint2 o;
   o.x = *reinterpret_cast<const uint32_t*>(&lo);
@@ -301,15 +307,18 @@ __global__ void iota_i64_kernel(int64_t* __restrict__ p, int64_t n) {
 }
 
 int launch_pack_wcat(const float* w_x, int64_t wx_ld, const float* w_hh, int F, int H, void* out, int out_bf16, int perm,
-                     cudaStream_t st) {
+                     cudaStream_t st, const float* extra, int n_extra) {
   const int64_t n = (int64_t)4 * H * (F + H);
   if (out_bf16 && F % 4 == 0 && H % 4 == 0 && wx_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(w_x) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(w_hh) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
-    pack_wcat_vec_kernel<<<dim3((unsigned)cdiv(F + H, 1024), (unsigned)(4 * H)), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H,
-                                                                                             (__nv_bfloat16*)out, perm);
+      (reinterpret_cast<uintptr_t>(w_hh) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0 &&
+      (!extra || (reinterpret_cast<uintptr_t>(extra) & 15) == 0)) {
+    pack_wcat_vec_kernel<<<dim3((unsigned)cdiv(F + H, 1024), (unsigned)(4 * H + (extra ? n_extra : 0))), 256, 0, st>>>(
+        w_x, wx_ld, w_hh, F, H, (__nv_bfloat16*)out, perm, extra);
     MVC_LAUNCH_CHECK();
     return 0;
   }
+  if (extra)       // unaligned views: the extra rows by the generic cast (bf16 output only)
+    MVC_TRY(launch_cast_pad_bf16(extra, n_extra, F, F, F + H, mptr(out, (int64_t)4 * H * (F + H), 2), 0, st));
   if (out_bf16) pack_wcat_kernel<__nv_bfloat16><<<gridn(n), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H, (__nv_bfloat16*)out, perm);
   else pack_wcat_kernel<float><<<gridn(n), 256, 0, st>>>(w_x, wx_ld, w_hh, F, H, (float*)out, perm);
   MVC_LAUNCH_CHECK();
@@ -407,10 +416,9 @@ static int dec_prepare_r2(const MvcDecoderDims* d, const MvcDecoderParams* p, co
   if (mvc_get_input_format() == MVC_INPUT_BF16) MVC_TRY(mvc_concat_bf16(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, st));
   else MVC_TRY(mvc_concat_cast(audio, Fa, visual, Fv, (int64_t)B * T, w.feats, 1, st));
   MVC_TRY(launch_add_vec(p->b_ih, p->b_hh, w.bsum, 4 * H, -H, ss));
-  MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, 1, 2, ss));
   // rows 4H .. 4H+A of the packed weights: [U | 0] -- the hoisted U.k projection rides in the P GEMM as one more N tile
   // (352 -> 396 tiles of 128 x 256: three waves either way), instead of a 17 us GEMM of its own behind it
-  MVC_TRY(launch_cast_pad_bf16(p->att_U, A, F, F, (int)ldx, mptr(w.wcat, (int64_t)4 * H * ldx, 2), 0, ss));
+  MVC_TRY(launch_pack_wcat(p->w_ih + E, E + F, p->w_hh, F, H, w.wcat, 1, 2, ss, p->att_U, A));
   MVC_CUDA(cudaEventRecord(sg.side->aux[0], ss));
   MVC_CUDA(cudaStreamWaitEvent(st, sg.side->aux[0], 0));
   {
@@ -799,14 +807,25 @@ extern "C" int mvc_decoder_backward(const MvcDecoderDims* d, const MvcDecoderPar
       // under the persistent backward kernel.  Both operands are consumed where they lie as MN-major tcgen05 operands
       // (dlogits [SB, Vp] and the h halves of the xh slots [SB, F+H]): on the 20 SMs the persistent kernel leaves, the two
       // transpose passes of the K-major form cost more than the GEMM.
+      // The persistent backward kernel -- a whole-SM cluster launch, next on the caller's stream behind dhall -- wants 128
+      // free SMs; whatever the side stream holds at that moment delays it.  A caller stream that outranks the side stream
+      // (GraphedTrainStep captures on a priority -1 stream) gets its blocks placed first when both are ready together:
+      // db_out (column sum) then runs next to dhall and dW_out is released together with the kernel.  On a caller stream
+      // of equal priority (the eager loop) dW_out's 52 persistent CTAs would win that race often enough to cost 6 %, so
+      // the column sum is put between them: it is short-lived, and by the time dW_out starts the kernel is resident.
+      int prio = 0;
+      MVC_CUDA(cudaStreamGetPriority(st, &prio));
+      const bool outranks = prio < 0;
+      cudaStream_t ss = sg.side->stream;
+      if (outranks) {
+        MVC_TRY(sg.side_waits(1));
+        MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, ss));
+      }
       if (!wt_ready) MVC_TRY(mvc_transpose_to_bf16(p->out_w, 0, V, H, H, q.outwT, Vp, st));
       // dhall = dlogits . out_w
       MVC_TRY(mvc_gemm_bf16(SB, H, V, q.dlogits_b, Vp, outwT, Vp, 0.f, q.dhall, H, nullptr, nullptr, 0, st));
-      // (the side leg starts BEHIND dhall: its persistent GEMM must not hold SMs when the persistent backward kernel --
-      // a whole-SM cluster launch, next on the caller's stream -- wants 128 of them; the column sum goes first)
       MVC_TRY(sg.side_waits(1));
-      cudaStream_t ss = sg.side->stream;
-      MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, ss));
+      if (!outranks) MVC_TRY(mvc_colsum(q.dlogits, SB, V, V, g->out_b, ss));
       {
         TcEpilogue ep{};
         ep.mode = TC_MODE_PLAIN;

@@ -239,7 +239,7 @@ static inline int step_backward(const StepCfg& c, const StepBwd& io, cudaStream_
 
 // ---- small shared kernels (defined in decoder.cu) ----
 int launch_pack_wcat(const float* w_x, int64_t wx_ld, const float* w_hh, int F, int H, void* out, int out_bf16, int perm,
-                     cudaStream_t st);
+                     cudaStream_t st, const float* extra = nullptr, int n_extra = 0);
 int launch_cast_pad_bf16(const float* src, int64_t rows, int C, int64_t lds, int Cp, void* out, int permH,
                          cudaStream_t st);
 int launch_add_vec(const float* a, const float* b, float* o, int n, int permH, cudaStream_t st);

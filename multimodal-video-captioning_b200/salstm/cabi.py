@@ -120,6 +120,7 @@ SIGNATURES = {
     "mvc_loss_combine": (i32, [vp, f32, f32, f32, i32, i32, vp]),
     "mvc_scale_by_scalar": (i32, [vp, i64, vp, vp]),
     "mvc_clip_adam_multimem": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, vp, i32, f32, f32, f32, f32, f32, f32, vp]),
+    "mvc_clip_adam_p2p_multimem": (i32, [vp, vp, vp, i32, vp, vp, vp, i64, i64, vp, i32, f32, f32, f32, f32, f32, f32, vp]),
     "mvc_clip_adam_step_dev": (i32, [vp, vp, vp, vp, vp, i64, vp, i32, f32, f32, f32, f32, f32, f32, vp]),
     "mvc_clip_adam_step": (i32, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, i32, f32, vp]),
 }

@@ -19,6 +19,8 @@ from __future__ import annotations
 
 from typing import Iterable, List, Optional, Tuple
 
+import ctypes as C
+
 import torch
 
 from . import functional as Fn
@@ -56,6 +58,14 @@ class FlatClipAdam(torch.optim.Optimizer):
         # all-reduce followed by a full-size update.  None = use it when world > 1 and the fabric supports multicast.
         self.fused_comm = fused_comm
         self._mc = None             # (symmetric-memory handle of flat_p, handle of flat_g, lo, hi) when active
+        # reduce-scatter half of the fused exchange: "peer" = the owner of a slice loads the N replicas itself
+        # (mvc_clip_adam_p2p_multimem), "switch" = multimem.ld_reduce (mvc_clip_adam_multimem)
+        import os
+        # (measured at 2 GPUs: 253.0 k samples/s with peer loads, 256.6 k with the in-switch reduction -- the latter stays
+        # the default although it moves a third more NVLink bytes)
+        self._reduce = os.environ.get("MVC_B200_FUSED_REDUCE", "switch")
+        if self._reduce not in ("peer", "switch"):
+            raise ValueError("MVC_B200_FUSED_REDUCE must be 'peer' or 'switch'")
 
     # convenience mirrors of the single param group (kept in sync with lr schedulers)
     @property
@@ -232,10 +242,20 @@ class FlatClipAdam(torch.optim.Optimizer):
             self._dev_state[1] = float(g["lr"])
             self._lr_on_dev = float(g["lr"])
         hg.barrier(channel=0)
-        cabi.check(cabi.lib().mvc_clip_adam_multimem(
-            cabi.ptr(self.flat_p), C_void(hp.multicast_ptr), C_void(hg.multicast_ptr), cabi.ptr(self.m), cabi.ptr(self.v),
-            cabi.ptr(self.vmax), lo, hi, cabi.ptr(self._dev_state), 1, g["betas"][0], g["betas"][1], g["eps"],
-            g["weight_decay"], g["clip_value"], scale, cabi.stream_ptr()), "mvc_clip_adam_multimem")
+        if self._reduce == "switch":
+            cabi.check(cabi.lib().mvc_clip_adam_multimem(
+                cabi.ptr(self.flat_p), C_void(hp.multicast_ptr), C_void(hg.multicast_ptr), cabi.ptr(self.m), cabi.ptr(self.v),
+                cabi.ptr(self.vmax), lo, hi, cabi.ptr(self._dev_state), 1, g["betas"][0], g["betas"][1], g["eps"],
+                g["weight_decay"], g["clip_value"], scale, cabi.stream_ptr()), "mvc_clip_adam_multimem")
+        else:
+            # reduce-scatter by peer loads (the owner reads the N replicas itself): fewer NVLink bytes than the in-switch
+            # reduction, which fetches the requester's own replica over the link as well
+            ptrs = [int(x) for x in hg.buffer_ptrs]
+            arr = (C.c_void_p * len(ptrs))(*ptrs)
+            cabi.check(cabi.lib().mvc_clip_adam_p2p_multimem(
+                cabi.ptr(self.flat_p), C_void(hp.multicast_ptr), arr, len(ptrs), cabi.ptr(self.m), cabi.ptr(self.v),
+                cabi.ptr(self.vmax), lo, hi, cabi.ptr(self._dev_state), 1, g["betas"][0], g["betas"][1], g["eps"],
+                g["weight_decay"], g["clip_value"], scale, cabi.stream_ptr()), "mvc_clip_adam_p2p_multimem")
         hp.barrier(channel=1)
 
     # ---- checkpointing: the flat moments, addressed by parameter order

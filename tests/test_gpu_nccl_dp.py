@@ -93,11 +93,13 @@ def _worker(rank, world, port, precision, q):
         fused = "unsupported"
         torch.manual_seed(1)
         twins = []
-        for fc in (False, True):
+        for fc, reduce in ((False, None), (True, "peer"), (True, "switch")):
             m2 = AVCaptioning(Vocab(), 1.0, "global", device=dev, precision=precision).to(dev)
             m2.load_state_dict({k: p[k].clone() for k in m2.state_dict()})
             try:
                 o2 = FlatClipAdam(m2.parameters(), lr=1e-3, weight_decay=1e-5, clip_value=5.0, world_size=world, fused_comm=fc)
+                if reduce:
+                    o2._reduce = reduce          # reduce-scatter by peer loads / by multimem.ld_reduce
                 for it in range(3):
                     o2.zero_grad()
                     out, ar, vr = m2(a.to(dev), v.to(dev), c.to(dev))
@@ -110,14 +112,15 @@ def _worker(rank, world, port, precision, q):
                 if "multicast" in str(e) or "symmetric" in str(e):
                     break
                 raise
-        if len(twins) == 2:
-            (ma, oa), (mb, ob) = twins
-            assert ob._mc is not None
+        if len(twins) == 3:
+            (ma, oa) = twins[0]
             fused = "ok"
-            for (k, pa), pb in zip(ma.named_parameters(), mb.parameters()):
-                if not torch.allclose(pa, pb, rtol=2e-5, atol=2e-6):
-                    fused = f"{k}: max diff {float((pa - pb).abs().max()):.3e}"
-                    break
+            for mb, ob in twins[1:]:
+                assert ob._mc is not None
+                for (k, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+                    if not torch.allclose(pa, pb, rtol=2e-5, atol=2e-6):
+                        fused = f"{ob._reduce} {k}: max diff {float((pa - pb).abs().max()):.3e}"
+                        break
             n_live = sum(t.numel() for t in ob._live)
             flat2 = ob.flat_p[:n_live].clone()
             other2 = [torch.empty_like(flat2) for _ in range(world)]
