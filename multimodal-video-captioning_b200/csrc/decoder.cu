@@ -396,13 +396,15 @@ static int dec_prepare(const MvcDecoderDims* d, const MvcDecoderParams* p, const
 }
 
 // The whole prelude of a fully teacher-forced bf16 forward on the projected-keys path (recur2), scheduled over two
-// streams so that the serial chain in front of the persistent kernel is  features -> P GEMM -> U.k GEMM  only:
-//   side:   bias sum, [W_c | W_hh] pack (-> event 0), W_ie cast, <SOS> / caption tokens, embedding gather, gx GEMM,
-//           W cast, state clears (-> event 1: everything the persistent kernel reads); then, UNDER the persistent kernel
-//           (it leaves 20 SMs idle): W_out cast, output clears and (training) the transposed weights / keys the backward
-//           pass will need -- joined by the caller after the kernel (`dec_prepare_r2_finish`)
-//   caller: feature concat / cast, (wait event 0) P = keys . W_c^T, U cast, U.k GEMM, (wait event 1) kernel
-// (the round-2 profile of the single-stream order: 139 us from step start to the persistent kernel, 80 us of it GEMMs)
+// streams so that the serial chain in front of the persistent kernel is  features -> [P | U.k] GEMM  only:
+//   side:   bias sum, [W_c | W_hh ; U | 0] pack (-> event 0), W_ie cast, <SOS> / caption tokens, embedding gather, W cast,
+//           state + progress-counter clears, gx GEMM (-> event 1: everything the persistent kernel reads); then, UNDER the
+//           persistent kernel (it leaves 20 SMs idle): W_out cast, output clears and (training) the transposed weights /
+//           keys the backward pass will need -- joined by the caller after the kernel
+//   caller: feature concat / cast, (wait event 0) one GEMM for P = keys . W_c^T and U.k = keys . U^T, (wait event 1) kernel
+// (the round-2 profile of the single-stream order: 139 us from step start to the persistent kernel, 80 us of it GEMMs;
+// now ~100 us, 64 of it GEMMs.  A captured graph issues its root kernels one after the other in enqueue order, so the
+// features leg is enqueued first.)
 static int dec_prepare_r2(const MvcDecoderDims* d, const MvcDecoderParams* p, const float* audio, int Fa,
                           const float* visual, int Fv, const int64_t* captions, float* out_logp, float* out_hid,
                           int64_t* tokens_in, DecWs& w, bool train, SideGuard& sg, cudaStream_t st) {
