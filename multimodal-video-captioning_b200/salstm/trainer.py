@@ -50,6 +50,7 @@ class FlatClipAdam(torch.optim.Optimizer):
         self._live_set = set()
         self._views: List[torch.Tensor] = []
         self._offsets: List[int] = []
+        self._n_flat = 0            # elements of the flat buffers in use (every parameter padded to a multiple of 4)
         self._arena = None
         self._pending = []          # async all-reduce work handles of this step (bucketed mode)
         self._dev_state = None      # [step count, lr] on the device: set by GraphedTrainStep (CUDA-graph replay)
@@ -86,8 +87,14 @@ class FlatClipAdam(torch.optim.Optimizer):
         if self.flat_p is not None:       # a parameter received its first gradient later: re-flatten, keep the moments
             old = {id(p): (o, p.numel()) for p, o in zip(self._live, self._offsets)}
             old_m, old_v, old_vmax = self.m, self.v, self.vmax
-        n = sum(p.numel() for p in live)
+        # every parameter starts on a 16-byte boundary of the flat buffers (the kernels' float4 paths -- weight packing,
+        # casts, GEMM epilogues writing gradients -- fall back to scalar code on a misaligned view: one odd-sized tensor,
+        # e.g. out.bias [3201], would push every later parameter off); the <= 3 pad elements in front of a parameter stay
+        # zero in every buffer (zero gradient, zero weight: the update leaves them at zero)
+        al = lambda x: (x + 3) // 4 * 4
+        n = sum(al(p.numel()) for p in live)
         flat_p, flat_g = self._alloc_flat(n, dev)
+        flat_p.zero_(); flat_g.zero_()
         m, v, vmax = (torch.zeros(flat_p.numel(), device=dev, dtype=torch.float32) for _ in range(3))
         off, offsets = 0, []
         for p in live:
@@ -101,7 +108,8 @@ class FlatClipAdam(torch.optim.Optimizer):
             p.data = flat_p[off:off + k].view_as(p)
             p.grad = flat_g[off:off + k].view_as(p)
             offsets.append(off)
-            off += k
+            off += al(k)
+        self._n_flat = off
         self.flat_p, self.flat_g, self.m, self.v, self.vmax = flat_p, flat_g, m, v, vmax
         self._live, self._offsets = live, offsets
         self._live_set = {id(p) for p in live}
@@ -162,7 +170,8 @@ class FlatClipAdam(torch.optim.Optimizer):
         if self._live is None or any(p.grad is not None and id(p) not in self._live_set for p in self.params):
             self._flatten()
         ranges: List[Tuple[int, int]] = []
-        for p, v, o in zip(self._live, self._views, self._offsets):
+        ends = self._offsets[1:] + [self._n_flat]            # a parameter's range runs up to the next one (pads included)
+        for p, v, o, e in zip(self._live, self._views, self._offsets, ends):
             g = p.grad
             if g is None:
                 continue
@@ -170,9 +179,9 @@ class FlatClipAdam(torch.optim.Optimizer):
                 v.copy_(g)
                 p.grad = v
             if ranges and ranges[-1][1] == o:
-                ranges[-1] = (ranges[-1][0], o + p.numel())
+                ranges[-1] = (ranges[-1][0], e)
             else:
-                ranges.append((o, o + p.numel()))
+                ranges.append((o, e))
         return ranges
 
     # ---- gradient exchange
@@ -232,8 +241,7 @@ class FlatClipAdam(torch.optim.Optimizer):
         barrier (every slice has landed everywhere)."""
         from . import cabi
         hp, hg, lo, hi = self._mc
-        n_live = sum(p.numel() for p in self._live)
-        if ranges != [(0, n_live)]:
+        if ranges != [(0, self._n_flat)]:
             raise RuntimeError("FlatClipAdam(fused_comm): every live parameter must receive a gradient each step")
         if self._dev_state is None:
             self._dev_state = torch.tensor([float(self.step_count - 1), float(g["lr"])], device=self.flat_p.device)
@@ -262,7 +270,9 @@ class FlatClipAdam(torch.optim.Optimizer):
     def state_dict(self):
         sd = {"step": self.step_count, "param_group": {k: v for k, v in self.param_groups[0].items() if k != "params"}}
         if self.flat_p is not None:
-            sd.update(exp_avg=self.m.clone(), exp_avg_sq=self.v.clone(), max_exp_avg_sq=self.vmax.clone(),
+            # moments concatenated per live parameter, WITHOUT the alignment pads: independent of the buffer layout
+            pick = lambda buf: torch.cat([buf[o:o + p.numel()] for p, o in zip(self._live, self._offsets)])
+            sd.update(exp_avg=pick(self.m), exp_avg_sq=pick(self.v), max_exp_avg_sq=pick(self.vmax),
                       live=[i for i, p in enumerate(self.params) if id(p) in self._live_set])
         return sd
 
@@ -280,7 +290,12 @@ class FlatClipAdam(torch.optim.Optimizer):
                     p.grad = None
             self.flat_p = None
             self._flatten()
-            self.m.copy_(sd["exp_avg"]); self.v.copy_(sd["exp_avg_sq"]); self.vmax.copy_(sd["max_exp_avg_sq"])
+            src = 0
+            for p, o in zip(self._live, self._offsets):
+                k = p.numel()
+                self.m[o:o + k].copy_(sd["exp_avg"][src:src + k]); self.v[o:o + k].copy_(sd["exp_avg_sq"][src:src + k])
+                self.vmax[o:o + k].copy_(sd["max_exp_avg_sq"][src:src + k])
+                src += k
 
 
 class GraphedTrainStep:

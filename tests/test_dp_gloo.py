@@ -44,14 +44,17 @@ def _worker(rank, world, port, q):
         local = [p.grad.clone() for p in net.parameters()]
         opt = FlatClipAdam(list(net.parameters()) + [extra], lr=1e-3, world_size=world)
         opt.all_reduce_grads()
-        # the flat buffer holds exactly the live parameters, in order, and the .grad tensors are views of it
-        assert opt.flat_g.numel() == sum(p.numel() for p in net.parameters())
+        # the flat buffer holds exactly the live parameters, in order, each starting on a 16-byte boundary (numel rounded
+        # up to a multiple of 4), and the .grad tensors are views of it
+        al = lambda k: (k + 3) // 4 * 4
+        assert opt.flat_g.numel() == sum(al(p.numel()) for p in net.parameters())
         assert extra.grad is None
         off = 0
         for p in net.parameters():
             assert p.grad.data_ptr() == opt.flat_g[off:off + p.numel()].data_ptr()
             assert p.data.data_ptr() == opt.flat_p[off:off + p.numel()].data_ptr()
-            off += p.numel()
+            assert p.data.data_ptr() % 16 == 0 and p.grad.data_ptr() % 16 == 0
+            off += al(p.numel())
         gathered = [None] * world
         dist.all_gather_object(gathered, [t.tolist() for t in local])
         for i, p in enumerate(net.parameters()):

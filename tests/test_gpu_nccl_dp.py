@@ -121,8 +121,7 @@ def _worker(rank, world, port, precision, q):
                     if not torch.allclose(pa, pb, rtol=2e-5, atol=2e-6):
                         fused = f"{ob._reduce} {k}: max diff {float((pa - pb).abs().max()):.3e}"
                         break
-            n_live = sum(t.numel() for t in ob._live)
-            flat2 = ob.flat_p[:n_live].clone()
+            flat2 = ob.flat_p[:ob._n_flat].clone()
             other2 = [torch.empty_like(flat2) for _ in range(world)]
             dist.all_gather(other2, flat2)
             if not all(torch.equal(other2[0], o) for o in other2):
