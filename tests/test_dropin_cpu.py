@@ -206,3 +206,37 @@ def test_vectorised_detokenisation_equals_decode_indexes():
     s = Sparse()
     ok = ids.clone(); ok[ok == 17] = 5
     assert decode_batch(s, ok.tolist()) == [s.decode_indexes(r[1:]) for r in ok.tolist()]
+
+
+def test_flat_clip_adam_state_dict_round_trip_is_layout_independent():
+    """The flat buffers pad every parameter to a multiple of 4 elements (16-byte aligned views for the float4 kernels);
+    state_dict stores the moments per live parameter without the pads and load_state_dict scatters them back."""
+    from salstm.trainer import FlatClipAdam
+    torch.manual_seed(0)
+
+    def make():
+        return [torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(7)),
+                torch.nn.Parameter(torch.randn(2, 2)), torch.nn.Parameter(torch.randn(9))]
+
+    ps = make()
+    for p in ps[:3]:                                   # the last parameter never gets a gradient: not live
+        p.grad = torch.randn_like(p)
+    opt = FlatClipAdam(ps, lr=1e-3)
+    ranges = opt._sync_views()
+    assert opt._offsets == [0, 16, 24] and opt._n_flat == 28 and ranges == [(0, 28)]
+    assert all(p.data.data_ptr() % 16 == 0 for p in ps[:3])
+    assert float(opt.flat_p[15]) == 0.0 and float(opt.flat_g[23]) == 0.0          # pads are zero
+    for buf in (opt.m, opt.v, opt.vmax):
+        buf.copy_(torch.randn(buf.numel()))
+    opt.step_count = 7
+    sd = opt.state_dict()
+    assert sd["exp_avg"].numel() == 15 + 7 + 4 and sd["live"] == [0, 1, 2]
+    qs = make()
+    opt2 = FlatClipAdam(qs, lr=5e-4)
+    opt2.load_state_dict(sd)
+    assert opt2.step_count == 7 and opt2.lr == pytest.approx(1e-3)
+    for k, (p, o) in enumerate(zip(opt._live, opt._offsets)):
+        n = p.numel()
+        for a, b in ((opt.m, opt2.m), (opt.v, opt2.v), (opt.vmax, opt2.vmax)):
+            assert torch.equal(a[o:o + n], b[opt2._offsets[k]:opt2._offsets[k] + n])
+    assert qs[3].grad is None
